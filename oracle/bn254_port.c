@@ -1,0 +1,570 @@
+/* CPU restatement of the BN254 hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library; the product (CUDA engine behind include/bn254_b200.h) never does.
+ *
+ * PARITY UNPINNED: the algorithm the reference runs lives in the third-party Go module
+ * github.com/consensys/gnark-crypto v0.19.0 (/root/reference/go.mod:5), absent from disk, and
+ * the reference's tests hold no golden vectors for this path.  This file restates
+ * the *published* algorithm structure gnark documents for ecc/bn254:
+ *   - 4x64-bit Montgomery Fp (R = 2^256), tower Fp2[u]/(u^2+1), Fp6[v]/(v^3-(9+u)), Fp12[w]/(w^2-v)
+ *   - optimal-ate Miller loop over the NAF of 6x+2 with homogeneous projective G2 doubling /
+ *     mixed addition (Costello-Lange-Naehrig) and sparse "034" line multiplies, squarings shared
+ *     across the pairs of a product          [reference callers: access/tree/access_tree_node.go:106,110;
+ *     cpabe/bsw07/bsw07_cpabe.go:184; signature/bls01_signature/bls_signature.go:81-84]
+ *   - final exponentiation: easy part, then the Fuentes-Castaneda hard part with three x0-power
+ *     chains on Granger-Scott cyclotomic squarings; total exponent 2x0(6x0^2+3x0+1)(p^12-1)/r
+ *   - windowed Jacobian scalar multiplication in G1/G2 (canonical affine output)
+ *     [signature/bls01_signature/bls_signature.go:45,63], generic square-and-multiply GT.Exp
+ *     [access/tree/access_tree_node.go:156]
+ * and is pinned bit-for-bit to the definitional big-integer oracle oracle/bn254_ref.py by
+ * tests/test_oracle_port.py.  All buffers use gnark's memory layout (AoS, Montgomery, LE limbs).
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdlib.h>
+#include <pthread.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fp;
+typedef struct { fp a0, a1; } fp2;
+typedef struct { fp2 b0, b1, b2; } fp6;
+typedef struct { fp6 c0, c1; } fp12;
+typedef struct { fp x, y; } g1aff;
+typedef struct { fp2 x, y; } g2aff;
+typedef struct { fp x, y, z; } g1jac;
+typedef struct { fp2 x, y, z; } g2jac;
+
+#include "bn254_port_consts.h"
+
+/* ------------------------------------------------------------------ Fp */
+static inline int fp_is_zero(const fp* a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fp_eq(const fp* a, const fp* b) {
+  return ((a->l[0] ^ b->l[0]) | (a->l[1] ^ b->l[1]) | (a->l[2] ^ b->l[2]) | (a->l[3] ^ b->l[3])) == 0;
+}
+#include <immintrin.h>
+typedef unsigned long long ull;
+/* t - p into d, returns borrow */
+static inline unsigned char sub_p_to(ull* d, const ull* t) {
+  unsigned char b = 0;
+  b = _subborrow_u64(b, t[0], FP_P[0], &d[0]);
+  b = _subborrow_u64(b, t[1], FP_P[1], &d[1]);
+  b = _subborrow_u64(b, t[2], FP_P[2], &d[2]);
+  b = _subborrow_u64(b, t[3], FP_P[3], &d[3]);
+  return b;
+}
+static inline void reduce_once(fp* z, const ull* t) { /* t < 2p, p < 2^254 */
+  ull d[4];
+  unsigned char b = sub_p_to(d, t);
+  for (int i = 0; i < 4; i++) z->l[i] = b ? t[i] : d[i];
+}
+static inline void fp_add(fp* z, const fp* x, const fp* y) {
+  ull t[4]; unsigned char c = 0;
+  c = _addcarry_u64(c, x->l[0], y->l[0], &t[0]);
+  c = _addcarry_u64(c, x->l[1], y->l[1], &t[1]);
+  c = _addcarry_u64(c, x->l[2], y->l[2], &t[2]);
+  c = _addcarry_u64(c, x->l[3], y->l[3], &t[3]);
+  reduce_once(z, t);
+}
+static inline void fp_dbl(fp* z, const fp* x) { fp_add(z, x, x); }
+static inline void fp_sub(fp* z, const fp* x, const fp* y) {
+  ull t[4], d[4]; unsigned char b = 0, c = 0;
+  b = _subborrow_u64(b, x->l[0], y->l[0], &t[0]);
+  b = _subborrow_u64(b, x->l[1], y->l[1], &t[1]);
+  b = _subborrow_u64(b, x->l[2], y->l[2], &t[2]);
+  b = _subborrow_u64(b, x->l[3], y->l[3], &t[3]);
+  c = _addcarry_u64(c, t[0], FP_P[0], &d[0]);
+  c = _addcarry_u64(c, t[1], FP_P[1], &d[1]);
+  c = _addcarry_u64(c, t[2], FP_P[2], &d[2]);
+  c = _addcarry_u64(c, t[3], FP_P[3], &d[3]);
+  for (int i = 0; i < 4; i++) z->l[i] = b ? d[i] : t[i];
+}
+static inline void fp_neg(fp* z, const fp* x) {
+  if (fp_is_zero(x)) { *z = *x; return; }
+  fp zero = {{0, 0, 0, 0}};
+  fp_sub(z, &zero, x);
+}
+/* Montgomery product, CIOS, one spare word not needed since p < 2^254 ("no-carry" variant) */
+static inline void fp_mul(fp* z, const fp* x, const fp* y) {
+  ull t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define MUL_ROUND(yi) do { \
+    u128 c = (u128)x->l[0] * (yi) + t0; ull r0 = (ull)c; \
+    c = (u128)x->l[1] * (yi) + t1 + (ull)(c >> 64); ull r1 = (ull)c; \
+    c = (u128)x->l[2] * (yi) + t2 + (ull)(c >> 64); ull r2 = (ull)c; \
+    c = (u128)x->l[3] * (yi) + t3 + (ull)(c >> 64); ull r3 = (ull)c; ull r4 = (ull)(c >> 64); \
+    ull m = r0 * FP_INV64; \
+    c = (u128)m * FP_P[0] + r0; \
+    c = (u128)m * FP_P[1] + r1 + (ull)(c >> 64); t0 = (ull)c; \
+    c = (u128)m * FP_P[2] + r2 + (ull)(c >> 64); t1 = (ull)c; \
+    c = (u128)m * FP_P[3] + r3 + (ull)(c >> 64); t2 = (ull)c; \
+    t3 = r4 + (ull)(c >> 64); } while (0)
+  MUL_ROUND(y->l[0]); MUL_ROUND(y->l[1]); MUL_ROUND(y->l[2]); MUL_ROUND(y->l[3]);
+#undef MUL_ROUND
+  ull t[4] = {t0, t1, t2, t3};
+  reduce_once(z, t);
+}
+static inline void fp_half(fp* h) { /* h/2 mod p */
+  uint64_t t[4]; memcpy(t, h->l, 32);
+  uint64_t carry = 0;
+  if (t[0] & 1) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)t[i] + FP_P[i]; t[i] = (uint64_t)c; c >>= 64; } carry = (uint64_t)c; }
+  for (int i = 0; i < 3; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 63);
+  t[3] = (t[3] >> 1) | (carry << 63);
+  memcpy(h->l, t, 32);
+}
+static inline void fp_sqr(fp* z, const fp* x) { fp_mul(z, x, x); }
+static void fp_inv(fp* z, const fp* x) { /* x^(p-2); Inverse(0) = 0 */
+  fp acc = FP_ONE_M, b = *x;
+  for (int i = 0; i < 254; i++) {
+    if ((FP_PM2[i >> 6] >> (i & 63)) & 1) fp_mul(&acc, &acc, &b);
+    fp_sqr(&b, &b);
+  }
+  *z = acc;
+}
+
+/* ------------------------------------------------------------------ Fp2 */
+static inline void fp2_add(fp2* z, const fp2* x, const fp2* y) { fp_add(&z->a0, &x->a0, &y->a0); fp_add(&z->a1, &x->a1, &y->a1); }
+static inline void fp2_sub(fp2* z, const fp2* x, const fp2* y) { fp_sub(&z->a0, &x->a0, &y->a0); fp_sub(&z->a1, &x->a1, &y->a1); }
+static inline void fp2_dbl(fp2* z, const fp2* x) { fp_dbl(&z->a0, &x->a0); fp_dbl(&z->a1, &x->a1); }
+static inline void fp2_neg(fp2* z, const fp2* x) { fp_neg(&z->a0, &x->a0); fp_neg(&z->a1, &x->a1); }
+static inline void fp2_conj(fp2* z, const fp2* x) { z->a0 = x->a0; fp_neg(&z->a1, &x->a1); }
+static inline int fp2_is_zero(const fp2* x) { return fp_is_zero(&x->a0) && fp_is_zero(&x->a1); }
+static inline int fp2_eq(const fp2* x, const fp2* y) { return fp_eq(&x->a0, &y->a0) && fp_eq(&x->a1, &y->a1); }
+static inline void fp2_mul(fp2* z, const fp2* x, const fp2* y) {
+  fp t0, t1, s0, s1, m;
+  fp_mul(&t0, &x->a0, &y->a0);
+  fp_mul(&t1, &x->a1, &y->a1);
+  fp_add(&s0, &x->a0, &x->a1);
+  fp_add(&s1, &y->a0, &y->a1);
+  fp_mul(&m, &s0, &s1);
+  fp_sub(&m, &m, &t0);
+  fp_sub(&z->a1, &m, &t1);
+  fp_sub(&z->a0, &t0, &t1);
+}
+static inline void fp2_sqr(fp2* z, const fp2* x) {
+  fp s, d, m;
+  fp_add(&s, &x->a0, &x->a1);
+  fp_sub(&d, &x->a0, &x->a1);
+  fp_mul(&m, &x->a0, &x->a1);
+  fp_mul(&z->a0, &s, &d);
+  fp_dbl(&z->a1, &m);
+}
+static inline void fp2_mul_fp(fp2* z, const fp2* x, const fp* k) { fp_mul(&z->a0, &x->a0, k); fp_mul(&z->a1, &x->a1, k); }
+static inline void fp2_mul_xi(fp2* z, const fp2* x) { /* (9+u)(a0+a1 u) = 9a0-a1 + (a0+9a1)u */
+  fp t0, t1, e0, e1;
+  fp_dbl(&e0, &x->a0); fp_dbl(&e0, &e0); fp_dbl(&e0, &e0); fp_add(&e0, &e0, &x->a0);
+  fp_dbl(&e1, &x->a1); fp_dbl(&e1, &e1); fp_dbl(&e1, &e1); fp_add(&e1, &e1, &x->a1);
+  fp_sub(&t0, &e0, &x->a1);
+  fp_add(&t1, &e1, &x->a0);
+  z->a0 = t0; z->a1 = t1;
+}
+static void fp2_inv(fp2* z, const fp2* x) {
+  fp n, t;
+  fp_sqr(&n, &x->a0); fp_sqr(&t, &x->a1); fp_add(&n, &n, &t);
+  fp_inv(&n, &n);
+  fp_mul(&z->a0, &x->a0, &n);
+  fp_mul(&t, &x->a1, &n);
+  fp_neg(&z->a1, &t);
+}
+
+/* ------------------------------------------------------------------ Fp6 */
+static inline void fp6_add(fp6* z, const fp6* x, const fp6* y) { fp2_add(&z->b0, &x->b0, &y->b0); fp2_add(&z->b1, &x->b1, &y->b1); fp2_add(&z->b2, &x->b2, &y->b2); }
+static inline void fp6_sub(fp6* z, const fp6* x, const fp6* y) { fp2_sub(&z->b0, &x->b0, &y->b0); fp2_sub(&z->b1, &x->b1, &y->b1); fp2_sub(&z->b2, &x->b2, &y->b2); }
+static inline void fp6_neg(fp6* z, const fp6* x) { fp2_neg(&z->b0, &x->b0); fp2_neg(&z->b1, &x->b1); fp2_neg(&z->b2, &x->b2); }
+static inline void fp6_mul_v(fp6* z, const fp6* x) { fp2 t; fp2_mul_xi(&t, &x->b2); z->b2 = x->b1; z->b1 = x->b0; z->b0 = t; }
+static void fp6_mul(fp6* z, const fp6* x, const fp6* y) { /* Karatsuba, 6 Fp2 mul */
+  fp2 v0, v1, v2, s, t, u0, u1, u2;
+  fp2_mul(&v0, &x->b0, &y->b0);
+  fp2_mul(&v1, &x->b1, &y->b1);
+  fp2_mul(&v2, &x->b2, &y->b2);
+  fp2_add(&s, &x->b1, &x->b2); fp2_add(&t, &y->b1, &y->b2); fp2_mul(&u0, &s, &t);
+  fp2_sub(&u0, &u0, &v1); fp2_sub(&u0, &u0, &v2); fp2_mul_xi(&u0, &u0); fp2_add(&u0, &u0, &v0);
+  fp2_add(&s, &x->b0, &x->b1); fp2_add(&t, &y->b0, &y->b1); fp2_mul(&u1, &s, &t);
+  fp2_sub(&u1, &u1, &v0); fp2_sub(&u1, &u1, &v1); fp2_mul_xi(&s, &v2); fp2_add(&u1, &u1, &s);
+  fp2_add(&s, &x->b0, &x->b2); fp2_add(&t, &y->b0, &y->b2); fp2_mul(&u2, &s, &t);
+  fp2_sub(&u2, &u2, &v0); fp2_sub(&u2, &u2, &v2); fp2_add(&u2, &u2, &v1);
+  z->b0 = u0; z->b1 = u1; z->b2 = u2;
+}
+static void fp6_mul_fp2(fp6* z, const fp6* x, const fp2* k) { fp2_mul(&z->b0, &x->b0, k); fp2_mul(&z->b1, &x->b1, k); fp2_mul(&z->b2, &x->b2, k); }
+static void fp6_mul_01(fp6* z, const fp6* x, const fp2* c0, const fp2* c1) { /* x * (c0 + c1 v), 5 Fp2 mul */
+  fp2 a, b, s, t, r0, r1, r2;
+  fp2_mul(&a, &x->b0, c0);
+  fp2_mul(&b, &x->b1, c1);
+  fp2_add(&s, &x->b1, &x->b2); fp2_mul(&r0, &s, c1); fp2_sub(&r0, &r0, &b); fp2_mul_xi(&r0, &r0); fp2_add(&r0, &r0, &a);
+  fp2_add(&s, &x->b0, &x->b2); fp2_mul(&r2, &s, c0); fp2_sub(&r2, &r2, &a); fp2_add(&r2, &r2, &b);
+  fp2_add(&s, &x->b0, &x->b1); fp2_add(&t, c0, c1); fp2_mul(&r1, &s, &t); fp2_sub(&r1, &r1, &a); fp2_sub(&r1, &r1, &b);
+  z->b0 = r0; z->b1 = r1; z->b2 = r2;
+}
+static void fp6_inv(fp6* z, const fp6* x) {
+  fp2 t0, t1, t2, s, n;
+  fp2_sqr(&t0, &x->b0); fp2_mul(&s, &x->b1, &x->b2); fp2_mul_xi(&s, &s); fp2_sub(&t0, &t0, &s);
+  fp2_sqr(&t1, &x->b2); fp2_mul_xi(&t1, &t1); fp2_mul(&s, &x->b0, &x->b1); fp2_sub(&t1, &t1, &s);
+  fp2_sqr(&t2, &x->b1); fp2_mul(&s, &x->b0, &x->b2); fp2_sub(&t2, &t2, &s);
+  fp2_mul(&n, &x->b2, &t1); fp2_mul(&s, &x->b1, &t2); fp2_add(&n, &n, &s); fp2_mul_xi(&n, &n);
+  fp2_mul(&s, &x->b0, &t0); fp2_add(&n, &n, &s);
+  fp2_inv(&n, &n);
+  fp2_mul(&z->b0, &t0, &n); fp2_mul(&z->b1, &t1, &n); fp2_mul(&z->b2, &t2, &n);
+}
+
+/* ------------------------------------------------------------------ Fp12 */
+static void fp12_set_one(fp12* z) { memset(z, 0, sizeof *z); z->c0.b0.a0 = FP_ONE_M; }
+static int fp12_is_one(const fp12* z) { fp12 one; fp12_set_one(&one); return memcmp(z, &one, sizeof one) == 0; }
+static void fp12_mul(fp12* z, const fp12* x, const fp12* y) {
+  fp6 a, b, s, t, c;
+  fp6_mul(&a, &x->c0, &y->c0);
+  fp6_mul(&b, &x->c1, &y->c1);
+  fp6_add(&s, &x->c0, &x->c1); fp6_add(&t, &y->c0, &y->c1); fp6_mul(&c, &s, &t);
+  fp6_sub(&c, &c, &a); fp6_sub(&z->c1, &c, &b);
+  fp6_mul_v(&b, &b); fp6_add(&z->c0, &a, &b);
+}
+static void fp12_sqr(fp12* z, const fp12* x) { /* complex squaring: 2 Fp6 mul */
+  fp6 m, s, t, vc1;
+  fp6_mul(&m, &x->c0, &x->c1);
+  fp6_add(&s, &x->c0, &x->c1);
+  fp6_mul_v(&vc1, &x->c1); fp6_add(&t, &x->c0, &vc1);
+  fp6_mul(&s, &s, &t);           /* (c0+c1)(c0+v c1) = c0^2 + v c1^2 + (1+v) c0c1 */
+  fp6_sub(&s, &s, &m); fp6_mul_v(&t, &m); fp6_sub(&z->c0, &s, &t);
+  fp6_add(&z->c1, &m, &m);
+}
+static void fp12_conj(fp12* z, const fp12* x) { z->c0 = x->c0; fp6_neg(&z->c1, &x->c1); }
+static void fp12_inv(fp12* z, const fp12* x) {
+  fp6 n, t;
+  fp6_mul(&n, &x->c0, &x->c0); fp6_mul(&t, &x->c1, &x->c1); fp6_mul_v(&t, &t); fp6_sub(&n, &n, &t);
+  fp6_inv(&n, &n);
+  fp6_mul(&z->c0, &x->c0, &n);
+  fp6_mul(&t, &x->c1, &n); fp6_neg(&z->c1, &t);
+}
+/* w-basis view: g0=c0.b0 g1=c1.b0 g2=c0.b1 g3=c1.b1 g4=c0.b2 g5=c1.b2 ; pi^k: g_i -> conj^k(g_i)*gamma_k[i] */
+static void fp12_frob(fp12* z, const fp12* x, int k) {
+  const fp2* gam = k == 1 ? GAMMA1 : (k == 2 ? GAMMA2 : GAMMA3);
+  const fp2* src[6] = {&x->c0.b0, &x->c1.b0, &x->c0.b1, &x->c1.b1, &x->c0.b2, &x->c1.b2};
+  fp2 out[6];
+  for (int i = 0; i < 6; i++) {
+    fp2 t = *src[i];
+    if (k & 1) fp2_conj(&t, &t);
+    if (i == 0) out[i] = t; else fp2_mul(&out[i], &t, &gam[i]);
+  }
+  z->c0.b0 = out[0]; z->c1.b0 = out[1]; z->c0.b1 = out[2]; z->c1.b1 = out[3]; z->c0.b2 = out[4]; z->c1.b2 = out[5];
+}
+/* Granger-Scott squaring in the cyclotomic subgroup. Fp12 = Fp4[w]/(w^3 - s), s = w^3, s^2 = xi;
+ * z = A + B w + C w^2 with A=(g0,g3) B=(g1,g4) C=(g2,g5);
+ * z^2 = (3A^2 - 2conj A) + (3 s C^2 + 2 conj B) w + (3B^2 - 2 conj C) w^2. */
+static inline void fp4_sqr(fp2* r0, fp2* r1, const fp2* a, const fp2* b) { /* (a+bs)^2 = a^2+xi b^2 + ((a+b)^2-a^2-b^2) s */
+  fp2 a2, b2, s;
+  fp2_sqr(&a2, a); fp2_sqr(&b2, b);
+  fp2_add(&s, a, b); fp2_sqr(&s, &s); fp2_sub(&s, &s, &a2); fp2_sub(r1, &s, &b2);
+  fp2_mul_xi(&b2, &b2); fp2_add(r0, &a2, &b2);
+}
+static void fp12_cyclo_sqr(fp12* z, const fp12* x) {
+  fp2 a0, a1, b0, b1, c0, c1, t;
+  fp4_sqr(&a0, &a1, &x->c0.b0, &x->c1.b1);
+  fp4_sqr(&b0, &b1, &x->c1.b0, &x->c0.b2);
+  fp4_sqr(&c0, &c1, &x->c0.b1, &x->c1.b2);
+  fp2 g0 = x->c0.b0, g1 = x->c1.b0, g2 = x->c0.b1, g3 = x->c1.b1, g4 = x->c0.b2, g5 = x->c1.b2;
+  /* g0' = 3a0 - 2g0 ; g3' = 3a1 + 2g3 */
+  fp2_sub(&t, &a0, &g0); fp2_dbl(&t, &t); fp2_add(&z->c0.b0, &t, &a0);
+  fp2_add(&t, &a1, &g3); fp2_dbl(&t, &t); fp2_add(&z->c1.b1, &t, &a1);
+  /* g2' = 3b0 - 2g2 ; g5' = 3b1 + 2g5 */
+  fp2_sub(&t, &b0, &g2); fp2_dbl(&t, &t); fp2_add(&z->c0.b1, &t, &b0);
+  fp2_add(&t, &b1, &g5); fp2_dbl(&t, &t); fp2_add(&z->c1.b2, &t, &b1);
+  /* s*C^2 = (xi c1, c0): g1' = 3 xi c1 + 2 g1 ; g4' = 3 c0 - 2 g4 */
+  fp2_mul_xi(&c1, &c1);
+  fp2_add(&t, &c1, &g1); fp2_dbl(&t, &t); fp2_add(&z->c1.b0, &t, &c1);
+  fp2_sub(&t, &c0, &g4); fp2_dbl(&t, &t); fp2_add(&z->c0.b2, &t, &c0);
+}
+/* x^(x0) for x in the cyclotomic subgroup: signed width-3 sliding window, inverse = conjugate */
+static void fp12_cyclo_exp_u64(fp12* z, const fp12* x, uint64_t e) {
+  int8_t naf[66]; int n = 0;
+  u128 k = e;
+  while (k) {
+    int d = 0;
+    if (k & 1) { d = (int)(k & 7); if (d > 4) d -= 8; k -= d; }
+    naf[n++] = (int8_t)d; k >>= 1;
+  }
+  fp12 tab[2], x2; /* x, x^3 */
+  tab[0] = *x; fp12_cyclo_sqr(&x2, x); fp12_mul(&tab[1], &x2, x);
+  fp12 acc; int started = 0;
+  for (int i = n - 1; i >= 0; i--) {
+    if (started) fp12_cyclo_sqr(&acc, &acc);
+    int d = naf[i];
+    if (d) {
+      fp12 m = tab[(d < 0 ? -d : d) >> 1];
+      if (d < 0) fp12_conj(&m, &m);
+      if (started) fp12_mul(&acc, &acc, &m); else { acc = m; started = 1; }
+    }
+  }
+  *z = acc;
+}
+static void fp12_expt(fp12* z, const fp12* x) { fp12_cyclo_exp_u64(z, x, X0_SEED); }
+
+/* z * (l0 + l1 w + l3 w^3): sparse "034" multiply, 13 Fp2 mul */
+static void fp12_mul_034(fp12* z, const fp2* l0, const fp2* l1, const fp2* l3) {
+  fp6 a, b, s, c; fp2 d0;
+  fp6_mul_fp2(&a, &z->c0, l0);
+  fp6_mul_01(&b, &z->c1, l1, l3);
+  fp2_add(&d0, l0, l1);
+  fp6_add(&s, &z->c0, &z->c1);
+  fp6_mul_01(&c, &s, &d0, l3);
+  fp6_sub(&c, &c, &a); fp6_sub(&z->c1, &c, &b);
+  fp6_mul_v(&b, &b); fp6_add(&z->c0, &a, &b);
+}
+
+/* ------------------------------------------------------------------ Miller loop */
+typedef struct { fp2 x, y, z; } g2proj;
+/* tangent at T (homogeneous projective), T <- 2T; line scaled by a subfield factor:
+ * l = (-2YZ) yP + (3X^2) xP w + (3b'Z^2 - Y^2) w^3 */
+static void dbl_step(g2proj* T, fp2* r0, fp2* r1, fp2* r2) {
+  fp2 A, B, C, E, F, G, H, I, J, t;
+  fp2_mul(&A, &T->x, &T->y);
+  fp_half(&A.a0); fp_half(&A.a1);
+  fp2_sqr(&B, &T->y);
+  fp2_sqr(&C, &T->z);
+  fp2_mul(&E, &C, &TWIST_3B);          /* E = 3b'Z^2 */
+  fp2_dbl(&F, &E); fp2_add(&F, &F, &E); /* F = 9b'Z^2 */
+  fp2_add(&G, &B, &F);
+  fp_half(&G.a0); fp_half(&G.a1);
+  fp2_add(&H, &T->y, &T->z); fp2_sqr(&H, &H); fp2_sub(&H, &H, &B); fp2_sub(&H, &H, &C); /* 2YZ */
+  fp2_sub(&I, &E, &B);
+  fp2_sqr(&J, &T->x);
+  fp2_sub(&t, &B, &F); fp2_mul(&T->x, &A, &t);          /* X3 = XY/2 (Y^2 - 9b'Z^2) */
+  fp2_sqr(&t, &E); fp2 t3; fp2_dbl(&t3, &t); fp2_add(&t3, &t3, &t);
+  fp2_sqr(&G, &G); fp2_sub(&T->y, &G, &t3);              /* Y3 = ((Y^2+9b'Z^2)/2)^2 - 3E^2 */
+  fp2_mul(&T->z, &B, &H);                                /* Z3 = 2Y^3 Z */
+  fp2_neg(r0, &H);
+  fp2_dbl(r1, &J); fp2_add(r1, r1, &J);
+  *r2 = I;
+}
+/* chord through T and affine Q, T <- T+Q; l = L yP - O xP w + (O x2 - L y2) w^3, O = Y1 - y2 Z1, L = X1 - x2 Z1 */
+static void add_step(g2proj* T, const g2aff* Q, fp2* r0, fp2* r1, fp2* r2) {
+  fp2 O, L, C, D, E, F, G, H, t, t1;
+  fp2_mul(&t, &Q->y, &T->z); fp2_sub(&O, &T->y, &t);
+  fp2_mul(&t, &Q->x, &T->z); fp2_sub(&L, &T->x, &t);
+  fp2_sqr(&C, &O); fp2_sqr(&D, &L);
+  fp2_mul(&E, &L, &D);
+  fp2_mul(&F, &T->z, &C);
+  fp2_mul(&G, &T->x, &D);
+  fp2_dbl(&t, &G); fp2_add(&H, &E, &F); fp2_sub(&H, &H, &t);
+  fp2_mul(&t1, &T->y, &E);
+  fp2_mul(&T->x, &L, &H);
+  fp2_sub(&t, &G, &H); fp2_mul(&t, &t, &O); fp2_sub(&T->y, &t, &t1);
+  fp2_mul(&T->z, &E, &T->z);
+  fp2_mul(&t, &L, &Q->y); fp2_mul(&t1, &Q->x, &O); fp2_sub(r2, &t1, &t);
+  *r0 = L;
+  fp2_neg(r1, &O);
+}
+/* only the line of the chord (last step of the optimal ate loop) */
+static void line_only(const g2proj* T, const g2aff* Q, fp2* r0, fp2* r1, fp2* r2) {
+  fp2 O, L, t, t1;
+  fp2_mul(&t, &Q->y, &T->z); fp2_sub(&O, &T->y, &t);
+  fp2_mul(&t, &Q->x, &T->z); fp2_sub(&L, &T->x, &t);
+  fp2_mul(&t, &L, &Q->y); fp2_mul(&t1, &Q->x, &O); fp2_sub(r2, &t1, &t);
+  *r0 = L;
+  fp2_neg(r1, &O);
+}
+static inline int g1_is_inf(const g1aff* p) { return fp_is_zero(&p->x) && fp_is_zero(&p->y); }
+static inline int g2_is_inf(const g2aff* q) { return fp2_is_zero(&q->x) && fp2_is_zero(&q->y); }
+static inline void apply_line(fp12* f, const g1aff* P, const fp2* r0, const fp2* r1, const fp2* r2) {
+  fp2 l0, l1;
+  fp2_mul_fp(&l0, r0, &P->y);
+  fp2_mul_fp(&l1, r1, &P->x);
+  fp12_mul_034(f, &l0, &l1, r2);
+}
+#define MAX_STACK_PAIRS 64
+/* product of Miller functions over k pairs with shared squarings; pairs with infinity skipped */
+static void miller_loop(fp12* out, const g1aff* P, const g2aff* Q, size_t k) {
+  g1aff Pbuf[MAX_STACK_PAIRS]; g2aff Qbuf[MAX_STACK_PAIRS], Qn_buf[MAX_STACK_PAIRS]; g2proj Tbuf[MAX_STACK_PAIRS];
+  g1aff* p = Pbuf; g2aff* q = Qbuf; g2aff* qn = Qn_buf; g2proj* T = Tbuf;
+  if (k > MAX_STACK_PAIRS) {
+    p = malloc(k * sizeof *p); q = malloc(k * sizeof *q); qn = malloc(k * sizeof *qn); T = malloc(k * sizeof *T);
+  }
+  size_t n = 0;
+  for (size_t i = 0; i < k; i++) {
+    if (g1_is_inf(&P[i]) || g2_is_inf(&Q[i])) continue;
+    p[n] = P[i]; q[n] = Q[i]; qn[n].x = Q[i].x; fp2_neg(&qn[n].y, &Q[i].y);
+    T[n].x = Q[i].x; T[n].y = Q[i].y; memset(&T[n].z, 0, sizeof(fp2)); T[n].z.a0 = FP_ONE_M;
+    n++;
+  }
+  fp12 f; fp12_set_one(&f);
+  fp2 r0, r1, r2;
+  for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr(&f, &f);
+    for (size_t j = 0; j < n; j++) {
+      dbl_step(&T[j], &r0, &r1, &r2);
+      apply_line(&f, &p[j], &r0, &r1, &r2);
+      if (ATE_NAF[i]) {
+        add_step(&T[j], ATE_NAF[i] > 0 ? &q[j] : &qn[j], &r0, &r1, &r2);
+        apply_line(&f, &p[j], &r0, &r1, &r2);
+      }
+    }
+  }
+  for (size_t j = 0; j < n; j++) {
+    g2aff q1, q2; fp2 t;
+    fp2_conj(&t, &q[j].x); fp2_mul(&q1.x, &t, &GAMMA1[2]);
+    fp2_conj(&t, &q[j].y); fp2_mul(&q1.y, &t, &GAMMA1[3]);
+    fp2_mul(&q2.x, &q[j].x, &GAMMA2[2]); q2.y = q[j].y;   /* -pi^2(Q): gamma_{2,3} = -1 */
+    add_step(&T[j], &q1, &r0, &r1, &r2);
+    apply_line(&f, &p[j], &r0, &r1, &r2);
+    line_only(&T[j], &q2, &r0, &r1, &r2);
+    apply_line(&f, &p[j], &r0, &r1, &r2);
+  }
+  *out = f;
+  if (k > MAX_STACK_PAIRS) { free(p); free(q); free(qn); free(T); }
+}
+
+/* ------------------------------------------------------------------ final exponentiation */
+static void final_exp(fp12* out, const fp12* in) {
+  fp12 f, t0, t1, t2, t3, t4;
+  /* easy part: f^((p^6-1)(p^2+1)) */
+  fp12_conj(&t0, in); fp12_inv(&f, in); fp12_mul(&t0, &t0, &f);
+  fp12_frob(&f, &t0, 2); fp12_mul(&f, &f, &t0);
+  if (fp12_is_one(&f)) { *out = f; return; }
+  /* hard part: exponent 2x0(6x0^2+3x0+1)(p^4-p^2+1)/r (Fuentes-Castaneda et al.) */
+  fp12_expt(&t0, &f); fp12_conj(&t0, &t0); fp12_cyclo_sqr(&t0, &t0);
+  fp12_cyclo_sqr(&t1, &t0); fp12_mul(&t1, &t0, &t1);
+  fp12_expt(&t2, &t1); fp12_conj(&t2, &t2);
+  fp12_conj(&t3, &t1); fp12_mul(&t1, &t2, &t3);
+  fp12_cyclo_sqr(&t3, &t2); fp12_expt(&t4, &t3); fp12_mul(&t4, &t1, &t4);
+  fp12_mul(&t3, &t0, &t4); fp12_mul(&t0, &t2, &t4); fp12_mul(&t0, &f, &t0);
+  fp12_frob(&t2, &t3, 1); fp12_mul(&t0, &t2, &t0);
+  fp12_frob(&t2, &t4, 2); fp12_mul(&t0, &t2, &t0);
+  fp12_conj(&t2, &f); fp12_mul(&t2, &t2, &t3); fp12_frob(&t2, &t2, 3); fp12_mul(&t0, &t2, &t0);
+  *out = t0;
+}
+
+/* ------------------------------------------------------------------ G1 / G2 (Jacobian) */
+#define DEFINE_GROUP(G, F, AFF, JAC, F_ADD, F_SUB, F_MUL, F_SQR, F_DBL, F_NEG, F_INV, F_ISZERO, F_EQ, F_ONE_INIT) \
+static int G##_jac_is_inf(const JAC* p) { return F_ISZERO(&p->z); } \
+static void G##_jac_dbl(JAC* r, const JAC* p) { \
+  if (G##_jac_is_inf(p)) { *r = *p; return; } \
+  F A, B, C, D, E, Ff, t, x3, y3, z3; \
+  F_SQR(&A, &p->x); F_SQR(&B, &p->y); F_SQR(&C, &B); \
+  F_ADD(&t, &p->x, &B); F_SQR(&t, &t); F_SUB(&t, &t, &A); F_SUB(&t, &t, &C); F_DBL(&D, &t); \
+  F_DBL(&E, &A); F_ADD(&E, &E, &A); F_SQR(&Ff, &E); \
+  F_DBL(&t, &D); F_SUB(&x3, &Ff, &t); \
+  F_MUL(&z3, &p->y, &p->z); F_DBL(&z3, &z3); \
+  F_SUB(&t, &D, &x3); F_MUL(&y3, &E, &t); F_DBL(&t, &C); F_DBL(&t, &t); F_DBL(&t, &t); F_SUB(&y3, &y3, &t); \
+  r->x = x3; r->y = y3; r->z = z3; } \
+static void G##_jac_add_aff(JAC* r, const JAC* p, const AFF* q) { /* q finite */ \
+  if (G##_jac_is_inf(p)) { r->x = q->x; r->y = q->y; F_ONE_INIT(&r->z); return; } \
+  F z2, u2, s2, h, rr, h2, h3, v, t, x3, y3, z3; \
+  F_SQR(&z2, &p->z); F_MUL(&u2, &q->x, &z2); F_MUL(&s2, &q->y, &z2); F_MUL(&s2, &s2, &p->z); \
+  F_SUB(&h, &u2, &p->x); F_SUB(&rr, &s2, &p->y); \
+  if (F_ISZERO(&h)) { if (F_ISZERO(&rr)) { G##_jac_dbl(r, p); return; } memset(r, 0, sizeof *r); return; } \
+  F_SQR(&h2, &h); F_MUL(&h3, &h2, &h); F_MUL(&v, &p->x, &h2); \
+  F_SQR(&x3, &rr); F_SUB(&x3, &x3, &h3); F_DBL(&t, &v); F_SUB(&x3, &x3, &t); \
+  F_SUB(&t, &v, &x3); F_MUL(&y3, &rr, &t); F_MUL(&t, &p->y, &h3); F_SUB(&y3, &y3, &t); \
+  F_MUL(&z3, &p->z, &h); \
+  r->x = x3; r->y = y3; r->z = z3; } \
+static void G##_jac_to_aff(AFF* r, const JAC* p) { \
+  if (G##_jac_is_inf(p)) { memset(r, 0, sizeof *r); return; } \
+  F zi, zi2; F_INV(&zi, &p->z); F_SQR(&zi2, &zi); F_MUL(&r->x, &p->x, &zi2); F_MUL(&zi2, &zi2, &zi); F_MUL(&r->y, &p->y, &zi2); } \
+static int G##_aff_is_inf(const AFF* p) { return F_ISZERO(&p->x) && F_ISZERO(&p->y); } \
+/* [s]P, s = 256-bit LE unsigned; 4-bit fixed window */ \
+static void G##_mul(AFF* out, const AFF* base, const uint8_t* s) { \
+  if (G##_aff_is_inf(base)) { memset(out, 0, sizeof *out); return; } \
+  AFF tab[15]; JAC acc; tab[0] = *base; \
+  for (int i = 1; i < 15; i++) { JAC t; t.x = tab[i - 1].x; t.y = tab[i - 1].y; F_ONE_INIT(&t.z); G##_jac_add_aff(&t, &t, base); G##_jac_to_aff(&tab[i], &t); } \
+  memset(&acc, 0, sizeof acc); \
+  for (int i = 63; i >= 0; i--) { \
+    for (int k = 0; k < 4; k++) G##_jac_dbl(&acc, &acc); \
+    int d = (s[i >> 1] >> ((i & 1) * 4)) & 15; \
+    if (d && !G##_aff_is_inf(&tab[d - 1])) G##_jac_add_aff(&acc, &acc, &tab[d - 1]); \
+  } \
+  G##_jac_to_aff(out, &acc); } \
+/* affine add with gnark Add semantics */ \
+static void G##_add(AFF* out, const AFF* a, const AFF* b) { \
+  if (G##_aff_is_inf(a)) { *out = *b; return; } \
+  if (G##_aff_is_inf(b)) { *out = *a; return; } \
+  JAC t; t.x = a->x; t.y = a->y; F_ONE_INIT(&t.z); G##_jac_add_aff(&t, &t, b); G##_jac_to_aff(out, &t); }
+
+static inline void fp_one_init(fp* z) { *z = FP_ONE_M; }
+static inline void fp2_one_init(fp2* z) { memset(z, 0, sizeof *z); z->a0 = FP_ONE_M; }
+DEFINE_GROUP(g1, fp, g1aff, g1jac, fp_add, fp_sub, fp_mul, fp_sqr, fp_dbl, fp_neg, fp_inv, fp_is_zero, fp_eq, fp_one_init)
+DEFINE_GROUP(g2, fp2, g2aff, g2jac, fp2_add, fp2_sub, fp2_mul, fp2_sqr, fp2_dbl, fp2_neg, fp2_inv, fp2_is_zero, fp2_eq, fp2_one_init)
+
+/* scalar reduced mod r first when s >= r (subgroup points: [s]P = [s mod r]P); here we only need
+ * correctness for s < 2^256 on order-r points, which plain double-and-add already gives. */
+
+/* GT.Exp: generic Fp12 square-and-multiply, k = 256-bit LE unsigned; k = 0 -> 1 */
+static void gt_exp(fp12* out, const fp12* x, const uint8_t* k) {
+  fp12 acc; fp12_set_one(&acc); int started = 0;
+  for (int i = 255; i >= 0; i--) {
+    if (started) fp12_sqr(&acc, &acc);
+    if ((k[i >> 3] >> (i & 7)) & 1) { if (started) fp12_mul(&acc, &acc, x); else { acc = *x; started = 1; } }
+  }
+  *out = acc;
+}
+
+/* ------------------------------------------------------------------ threaded batch driver */
+typedef void (*item_fn)(size_t i, void* ctx);
+typedef struct { item_fn fn; void* ctx; size_t lo, hi; } job;
+static void* job_main(void* a) { job* j = a; for (size_t i = j->lo; i < j->hi; i++) j->fn(i, j->ctx); return NULL; }
+static void run_batch(item_fn fn, void* ctx, size_t n, int threads) {
+  if (threads < 1) threads = 1;
+  if ((size_t)threads > n) threads = n ? (int)n : 1;
+  if (threads == 1) { job j = {fn, ctx, 0, n}; job_main(&j); return; }
+  pthread_t* th = malloc(sizeof(pthread_t) * threads); job* jobs = malloc(sizeof(job) * threads);
+  for (int t = 0; t < threads; t++) {
+    jobs[t].fn = fn; jobs[t].ctx = ctx; jobs[t].lo = n * t / threads; jobs[t].hi = n * (t + 1) / threads;
+    pthread_create(&th[t], NULL, job_main, &jobs[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+typedef struct { const void *a, *b; void* out; size_t k; } bctx;
+
+static void it_multi_pair(size_t i, void* c_) { bctx* c = c_; fp12 f;
+  miller_loop(&f, (const g1aff*)c->a + i * c->k, (const g2aff*)c->b + i * c->k, c->k); final_exp((fp12*)c->out + i, &f); }
+static void it_miller(size_t i, void* c_) { bctx* c = c_;
+  miller_loop((fp12*)c->out + i, (const g1aff*)c->a + i * c->k, (const g2aff*)c->b + i * c->k, c->k); }
+static void it_check(size_t i, void* c_) { bctx* c = c_; fp12 f;
+  miller_loop(&f, (const g1aff*)c->a + i * c->k, (const g2aff*)c->b + i * c->k, c->k); final_exp(&f, &f);
+  ((uint8_t*)c->out)[i] = (uint8_t)fp12_is_one(&f); }
+static void it_final_exp(size_t i, void* c_) { bctx* c = c_; final_exp((fp12*)c->out + i, (const fp12*)c->a + i); }
+static void it_g1_mul(size_t i, void* c_) { bctx* c = c_; g1_mul((g1aff*)c->out + i, (const g1aff*)c->a + i, (const uint8_t*)c->b + 32 * i); }
+static void it_g2_mul(size_t i, void* c_) { bctx* c = c_; g2_mul((g2aff*)c->out + i, (const g2aff*)c->a + i, (const uint8_t*)c->b + 32 * i); }
+static void it_g1_mul_base(size_t i, void* c_) { bctx* c = c_; g1_mul((g1aff*)c->out + i, (const g1aff*)c->a, (const uint8_t*)c->b + 32 * i); }
+static void it_g2_mul_base(size_t i, void* c_) { bctx* c = c_; g2_mul((g2aff*)c->out + i, (const g2aff*)c->a, (const uint8_t*)c->b + 32 * i); }
+static void it_g1_add(size_t i, void* c_) { bctx* c = c_; g1_add((g1aff*)c->out + i, (const g1aff*)c->a + i, (const g1aff*)c->b + i); }
+static void it_g2_add(size_t i, void* c_) { bctx* c = c_; g2_add((g2aff*)c->out + i, (const g2aff*)c->a + i, (const g2aff*)c->b + i); }
+static void it_gt_exp(size_t i, void* c_) { bctx* c = c_; gt_exp((fp12*)c->out + i, (const fp12*)c->a + i, (const uint8_t*)c->b + 32 * i); }
+static void it_gt_exp_base(size_t i, void* c_) { bctx* c = c_; gt_exp((fp12*)c->out + i, (const fp12*)c->a, (const uint8_t*)c->b + 32 * i); }
+static void it_gt_mul(size_t i, void* c_) { bctx* c = c_; fp12_mul((fp12*)c->out + i, (const fp12*)c->a + i, (const fp12*)c->b + i); }
+static void it_gt_div(size_t i, void* c_) { bctx* c = c_; fp12 t; fp12_inv(&t, (const fp12*)c->b + i); fp12_mul((fp12*)c->out + i, (const fp12*)c->a + i, &t); }
+static void it_gt_sqr(size_t i, void* c_) { bctx* c = c_; fp12_sqr((fp12*)c->out + i, (const fp12*)c->a + i); }
+static void it_gt_cyclo_sqr(size_t i, void* c_) { bctx* c = c_; fp12_cyclo_sqr((fp12*)c->out + i, (const fp12*)c->a + i); }
+static void it_fp_mul(size_t i, void* c_) { bctx* c = c_; fp_mul((fp*)c->out + i, (const fp*)c->a + i, (const fp*)c->b + i); }
+
+#define EXPORT __attribute__((visibility("default")))
+#define BATCH2(name, fn) EXPORT int name(const void* a, const void* b, size_t n, void* out, int threads) { \
+  bctx c = {a, b, out, 1}; run_batch(fn, &c, n, threads); return 0; }
+#define BATCHK(name, fn) EXPORT int name(const void* a, const void* b, size_t n, size_t k, void* out, int threads) { \
+  if (k == 0) { return -1; } \
+  bctx c = {a, b, out, k}; run_batch(fn, &c, n, threads); return 0; }
+
+BATCHK(bn254_port_multi_pair_batch, it_multi_pair)      /* n products of k pairs, one final exp each */
+BATCHK(bn254_port_miller_loop_batch, it_miller)
+BATCHK(bn254_port_pairing_check_batch, it_check)
+BATCH2(bn254_port_g1_mul_batch, it_g1_mul)              /* a: n points, b: n scalars */
+BATCH2(bn254_port_g2_mul_batch, it_g2_mul)
+BATCH2(bn254_port_g1_mul_base_batch, it_g1_mul_base)    /* a: ONE point, b: n scalars */
+BATCH2(bn254_port_g2_mul_base_batch, it_g2_mul_base)
+BATCH2(bn254_port_g1_add_batch, it_g1_add)
+BATCH2(bn254_port_g2_add_batch, it_g2_add)
+BATCH2(bn254_port_gt_exp_batch, it_gt_exp)
+BATCH2(bn254_port_gt_exp_base_batch, it_gt_exp_base)
+BATCH2(bn254_port_gt_mul_batch, it_gt_mul)
+BATCH2(bn254_port_gt_div_batch, it_gt_div)
+BATCH2(bn254_port_fp_mul_batch, it_fp_mul)
+EXPORT int bn254_port_pair_batch(const void* P, const void* Q, size_t n, void* out, int threads) {
+  return bn254_port_multi_pair_batch(P, Q, n, 1, out, threads); }
+EXPORT int bn254_port_final_exp_batch(const void* in, size_t n, void* out, int threads) {
+  bctx c = {in, NULL, out, 1}; run_batch(it_final_exp, &c, n, threads); return 0; }
+EXPORT int bn254_port_gt_sqr_batch(const void* in, size_t n, void* out, int threads) {
+  bctx c = {in, NULL, out, 1}; run_batch(it_gt_sqr, &c, n, threads); return 0; }
+EXPORT int bn254_port_gt_cyclo_sqr_batch(const void* in, size_t n, void* out, int threads) {
+  bctx c = {in, NULL, out, 1}; run_batch(it_gt_cyclo_sqr, &c, n, threads); return 0; }
+EXPORT void bn254_port_generators(void* g1, void* g2) {
+  g1aff a; a.x = G1_GEN_X; a.y = G1_GEN_Y; memcpy(g1, &a, sizeof a);
+  g2aff b; b.x = G2_GEN_X; b.y = G2_GEN_Y; memcpy(g2, &b, sizeof b); }
