@@ -1,0 +1,441 @@
+"""Host-side mirror of the gnark-crypto ``ecc/bn254`` call surface used by the reference schemes,
+bound to the CUDA engine through the C ABI (include/bn254_b200.h).
+
+Two levels:
+
+* :class:`Engine` -- batch entry points on raw buffers in gnark memory layout (numpy ``uint8``
+  arrays or ``bytes``): ``pair_batch``, ``multi_pair_batch``, ``pairing_check_batch``,
+  ``miller_loop_batch``, ``final_exp_batch``, ``g1_mul_batch`` ... These are what the Go package's
+  ``PairBatch`` etc. bind.
+* gnark-named values and functions -- ``G1Affine``, ``G2Affine``, ``GT``, ``Pair``, ``PairingCheck``,
+  ``MillerLoop``, ``FinalExponentiation``, ``Generators`` -- with the reference's argument meaning
+  and error behaviour (``ValueError("invalid inputs sizes")`` where gnark returns that error;
+  nothing else validates its input).  Each call is a 1-element batch on the GPU: they exist so the
+  parity tests read like the reference's tests, not for throughput.
+
+Reference call sites: bn254.Pair access/tree/access_tree_node.go:106,110; PairingCheck
+signature/bls01_signature/bls_signature.go:81-84; ScalarMultiplication[Base]
+signature/bls01_signature/bls_signature.go:45,63; GT.Exp access/tree/access_tree_node.go:156.
+No CPU path exists: without the built CUDA library and a B200 every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _native
+
+P_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+G1_BYTES, G2_BYTES, GT_BYTES, SCALAR_BYTES = 64, 128, 384, 32
+
+_ERRORS = {-1: "invalid inputs sizes", -2: "CUDA error", -3: "out of memory", -4: "bad argument"}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _u8(x, item_bytes, what):
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(x, dtype=np.uint8)
+    else:
+        a = np.ascontiguousarray(x)
+        a = a.view(np.uint8).reshape(-1)
+    if a.size % item_bytes:
+        raise ValueError("%s: buffer of %d bytes is not a multiple of %d" % (what, a.size, item_bytes))
+    return a
+
+
+def scalars_to_bytes(ks):
+    """ints -> (n,32) little-endian regular-form scalars (the C-ABI scalar format)."""
+    out = np.empty((len(ks), SCALAR_BYTES), dtype=np.uint8)
+    for i, k in enumerate(ks):
+        k = int(k)
+        if k < 0 or k >> 256:
+            raise ValueError("scalar out of range [0, 2^256)")
+        out[i] = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8)
+    return out
+
+
+class Engine:
+    """One context per GPU (bn254_ctx).  Thread-safe; buffers are copied, nothing is retained."""
+
+    def __init__(self, device=0):
+        self._lib = _native.lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.bn254_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError("bn254_ctx_create(device=%d) failed: %s (this engine has no CPU fallback)"
+                              % (device, _ERRORS.get(rc, rc)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bn254_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launches(self):
+        return int(self._lib.bn254_launch_count(self._h))
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        if rc == -1:
+            raise ValueError("invalid inputs sizes")
+        raise EngineError("%s: %s" % (_ERRORS.get(rc, rc), self._lib.bn254_last_error(self._h).decode()))
+
+    def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8):
+        out = np.empty(n * out_bytes, dtype=np.uint8)
+        fn = getattr(self._lib, name)
+        args = [self._h] + [b.ctypes.data_as(ctypes.c_void_p) for b in bufs] + [ctypes.c_size_t(s) for s in sizes]
+        args.append(out.ctypes.data_as(ctypes.c_void_p))
+        fn.restype = ctypes.c_int
+        self._check(fn(*args))
+        return out
+
+    # ---- pairings -------------------------------------------------------------------------
+    def pair_batch(self, P, Q):
+        """n independent pairings e(P[i], Q[i]) -> (n, 384)."""
+        P, Q = _u8(P, G1_BYTES, "P"), _u8(Q, G2_BYTES, "Q")
+        n = P.size // G1_BYTES
+        if n != Q.size // G2_BYTES:
+            raise ValueError("invalid inputs sizes")
+        return self._call("bn254_pair_batch", [P, Q], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    def _kpairs(self, name, P, Q, k, out_bytes):
+        P, Q = _u8(P, G1_BYTES, "P"), _u8(Q, G2_BYTES, "Q")
+        k = int(k)
+        if k <= 0 or P.size // G1_BYTES != Q.size // G2_BYTES or (P.size // G1_BYTES) % k:
+            raise ValueError("invalid inputs sizes")
+        n = P.size // G1_BYTES // k
+        return self._call(name, [P, Q], [n, k], out_bytes, n), n
+
+    def multi_pair_batch(self, P, Q, k):
+        """n products of k pairings with ONE final exponentiation each -> (n, 384)."""
+        out, n = self._kpairs("bn254_multi_pair_batch", P, Q, k, GT_BYTES)
+        return out.reshape(n, GT_BYTES)
+
+    def miller_loop_batch(self, P, Q, k=1):
+        out, n = self._kpairs("bn254_miller_loop_batch", P, Q, k, GT_BYTES)
+        return out.reshape(n, GT_BYTES)
+
+    def pairing_check_batch(self, P, Q, k):
+        out, n = self._kpairs("bn254_pairing_check_batch", P, Q, k, 1)
+        return out.astype(bool)
+
+    def final_exp_batch(self, f):
+        f = _u8(f, GT_BYTES, "f")
+        n = f.size // GT_BYTES
+        return self._call("bn254_final_exp_batch", [f], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    # ---- groups ---------------------------------------------------------------------------
+    def _mul(self, name, base, scalars, pt_bytes, broadcast):
+        base, scalars = _u8(base, pt_bytes, "base"), _u8(scalars, SCALAR_BYTES, "scalars")
+        n = scalars.size // SCALAR_BYTES
+        if (broadcast and base.size != pt_bytes) or (not broadcast and base.size // pt_bytes != n):
+            raise ValueError("invalid inputs sizes")
+        return self._call(name, [base, scalars], [n], pt_bytes, n).reshape(n, pt_bytes)
+
+    def g1_mul_batch(self, base, scalars):
+        return self._mul("bn254_g1_mul_batch", base, scalars, G1_BYTES, False)
+
+    def g2_mul_batch(self, base, scalars):
+        return self._mul("bn254_g2_mul_batch", base, scalars, G2_BYTES, False)
+
+    def g1_mul_base_batch(self, base1, scalars):
+        return self._mul("bn254_g1_mul_base_batch", base1, scalars, G1_BYTES, True)
+
+    def g2_mul_base_batch(self, base1, scalars):
+        return self._mul("bn254_g2_mul_base_batch", base1, scalars, G2_BYTES, True)
+
+    def _binary(self, name, a, b, item):
+        a, b = _u8(a, item, "a"), _u8(b, item, "b")
+        if a.size != b.size:
+            raise ValueError("invalid inputs sizes")
+        n = a.size // item
+        return self._call(name, [a, b], [n], item, n).reshape(n, item)
+
+    def g1_add_batch(self, a, b):
+        return self._binary("bn254_g1_add_batch", a, b, G1_BYTES)
+
+    def g2_add_batch(self, a, b):
+        return self._binary("bn254_g2_add_batch", a, b, G2_BYTES)
+
+    # ---- GT -------------------------------------------------------------------------------
+    def gt_exp_batch(self, x, k):
+        x, k = _u8(x, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
+        n = k.size // SCALAR_BYTES
+        if x.size // GT_BYTES != n:
+            raise ValueError("invalid inputs sizes")
+        return self._call("bn254_gt_exp_batch", [x, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    def gt_exp_base_batch(self, x1, k):
+        x1, k = _u8(x1, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
+        n = k.size // SCALAR_BYTES
+        if x1.size != GT_BYTES:
+            raise ValueError("invalid inputs sizes")
+        return self._call("bn254_gt_exp_base_batch", [x1, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    def gt_mul_batch(self, a, b):
+        return self._binary("bn254_gt_mul_batch", a, b, GT_BYTES)
+
+    def gt_div_batch(self, a, b):
+        return self._binary("bn254_gt_div_batch", a, b, GT_BYTES)
+
+    def fp_mul_batch(self, a, b):
+        return self._binary("bn254_fp_mul_batch", a, b, 32)
+
+    # ---- device-resident entry points (pointers are ints, e.g. torch.Tensor.data_ptr()) ----
+    def _dev(self, name, *args):
+        fn = getattr(self._lib, name)
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, *args))
+
+    def pair_batch_dev(self, dP, dQ, n, d_out, stream=0):
+        self._dev("bn254_pair_batch_dev", ctypes.c_void_p(dP), ctypes.c_void_p(dQ), ctypes.c_size_t(n),
+                  ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+    def multi_pair_batch_dev(self, dP, dQ, n, k, d_out, stream=0):
+        self._dev("bn254_multi_pair_batch_dev", ctypes.c_void_p(dP), ctypes.c_void_p(dQ), ctypes.c_size_t(n),
+                  ctypes.c_size_t(k), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+    def pairing_check_batch_dev(self, dP, dQ, n, k, d_ok, stream=0):
+        self._dev("bn254_pairing_check_batch_dev", ctypes.c_void_p(dP), ctypes.c_void_p(dQ), ctypes.c_size_t(n),
+                  ctypes.c_size_t(k), ctypes.c_void_p(d_ok), ctypes.c_void_p(stream))
+
+    def miller_loop_batch_dev(self, dP, dQ, n, k, d_out, stream=0):
+        self._dev("bn254_miller_loop_batch_dev", ctypes.c_void_p(dP), ctypes.c_void_p(dQ), ctypes.c_size_t(n),
+                  ctypes.c_size_t(k), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+    def final_exp_batch_dev(self, d_in, n, d_out, stream=0):
+        self._dev("bn254_final_exp_batch_dev", ctypes.c_void_p(d_in), ctypes.c_size_t(n), ctypes.c_void_p(d_out),
+                  ctypes.c_void_p(stream))
+
+    def g1_mul_batch_dev(self, d_base, stride, d_s, n, d_out, stream=0):
+        self._dev("bn254_g1_mul_batch_dev", ctypes.c_void_p(d_base), ctypes.c_size_t(stride), ctypes.c_void_p(d_s),
+                  ctypes.c_size_t(n), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+    def g2_mul_batch_dev(self, d_base, stride, d_s, n, d_out, stream=0):
+        self._dev("bn254_g2_mul_batch_dev", ctypes.c_void_p(d_base), ctypes.c_size_t(stride), ctypes.c_void_p(d_s),
+                  ctypes.c_size_t(n), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+    def gt_exp_batch_dev(self, d_x, stride, d_k, n, d_out, stream=0):
+        self._dev("bn254_gt_exp_batch_dev", ctypes.c_void_p(d_x), ctypes.c_size_t(stride), ctypes.c_void_p(d_k),
+                  ctypes.c_size_t(n), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+
+_default = None
+_default_lock = threading.Lock()
+
+
+def default_engine():
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = Engine(0)
+        return _default
+
+
+def set_default_engine(e):
+    global _default
+    _default = e
+
+
+# =============================================================================================
+# gnark-named value types
+# =============================================================================================
+def _neg_fp_raw(b):
+    """Negate one Montgomery-form Fp element given as 32 raw little-endian bytes (p - v, 0 -> 0)."""
+    v = int.from_bytes(b, "little")
+    return ((P_MOD - v) % P_MOD).to_bytes(32, "little")
+
+
+def _norm_scalar(s):
+    """big.Int semantics for group scalars: returns (negate, s mod r)."""
+    s = int(s)
+    return (s < 0), abs(s) % R_MOD
+
+
+class _Point:
+    NBYTES = 0
+    _mul = _mul_base = _add = None
+
+    def __init__(self, raw=None):
+        self.raw = bytes(self.NBYTES) if raw is None else bytes(raw)
+        assert len(self.raw) == self.NBYTES
+
+    def Set(self, a):
+        self.raw = a.raw
+        return self
+
+    def SetInfinity(self):
+        self.raw = bytes(self.NBYTES)
+        return self
+
+    def IsInfinity(self):
+        return self.raw == bytes(self.NBYTES)
+
+    def Equal(self, other):
+        return self.raw == other.raw
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self.raw == other.raw
+
+    def __hash__(self):
+        return hash(self.raw)
+
+    def Neg(self, a):
+        half = self.NBYTES // 2
+        x, y = a.raw[:half], a.raw[half:]
+        self.raw = x + b"".join(_neg_fp_raw(y[i:i + 32]) for i in range(0, half, 32))
+        return self
+
+    def ScalarMultiplication(self, a, s):
+        neg, k = _norm_scalar(s)
+        src = type(self)().Neg(a) if neg else a
+        e = default_engine()
+        out = getattr(e, self._mul)(src.raw, scalars_to_bytes([k]))
+        self.raw = out.tobytes()
+        return self
+
+    def Add(self, a, b):
+        self.raw = getattr(default_engine(), self._add)(a.raw, b.raw).tobytes()
+        return self
+
+    def Sub(self, a, b):
+        return self.Add(a, type(self)().Neg(b))
+
+
+class G1Affine(_Point):
+    NBYTES = G1_BYTES
+    _mul, _add = "g1_mul_batch", "g1_add_batch"
+
+    def ScalarMultiplicationBase(self, s):
+        return self.ScalarMultiplication(Generators()[2], s)
+
+
+class G2Affine(_Point):
+    NBYTES = G2_BYTES
+    _mul, _add = "g2_mul_batch", "g2_add_batch"
+
+    def ScalarMultiplicationBase(self, s):
+        return self.ScalarMultiplication(Generators()[3], s)
+
+
+_GT_ONE = None
+
+
+def _gt_one_raw():
+    global _GT_ONE
+    if _GT_ONE is None:
+        one = (1 << 256) % P_MOD
+        _GT_ONE = one.to_bytes(32, "little") + bytes(GT_BYTES - 32)
+    return _GT_ONE
+
+
+class GT:
+    """bn254.GT (= fptower.E12).  Zero value is 0, not 1, exactly as in Go."""
+
+    def __init__(self, raw=None):
+        self.raw = bytes(GT_BYTES) if raw is None else bytes(raw)
+        assert len(self.raw) == GT_BYTES
+
+    def Set(self, a):
+        self.raw = a.raw
+        return self
+
+    def SetOne(self):
+        self.raw = _gt_one_raw()
+        return self
+
+    def IsZero(self):
+        return self.raw == bytes(GT_BYTES)
+
+    def Equal(self, other):
+        return self.raw == other.raw
+
+    def __eq__(self, other):
+        return isinstance(other, GT) and self.raw == other.raw
+
+    def __hash__(self):
+        return hash(self.raw)
+
+    def Mul(self, a, b):
+        self.raw = default_engine().gt_mul_batch(a.raw, b.raw).tobytes()
+        return self
+
+    def Div(self, a, b):
+        self.raw = default_engine().gt_div_batch(a.raw, b.raw).tobytes()
+        return self
+
+    def Inverse(self, a):
+        self.raw = default_engine().gt_div_batch(_gt_one_raw(), a.raw).tobytes()
+        return self
+
+    def Exp(self, x, k):
+        """z = x^k; k == 0 -> 1; k < 0 -> (x^-1)^|k| (gnark E12.Exp semantics)."""
+        k = int(k)
+        base = x
+        if k < 0:
+            base = GT().Inverse(x)
+            k = -k
+        if k >> 256:
+            raise ValueError("GT.Exp exponent must be below 2^256")
+        self.raw = default_engine().gt_exp_batch(base.raw, scalars_to_bytes([k])).tobytes()
+        return self
+
+
+def Generators():
+    """(g1Jac, g2Jac, g1Aff, g2Aff) -- Jacobian forms are returned as (affine, z=1) pairs."""
+    g1 = (ctypes.c_uint8 * G1_BYTES)()
+    g2 = (ctypes.c_uint8 * G2_BYTES)()
+    _native.lib().bn254_generators(g1, g2)
+    a1, a2 = G1Affine(bytes(g1)), G2Affine(bytes(g2))
+    return (a1, 1), (a2, 1), a1, a2
+
+
+def _pack(Ps, Qs):
+    if len(Ps) == 0 or len(Ps) != len(Qs):
+        raise ValueError("invalid inputs sizes")
+    return b"".join(p.raw for p in Ps), b"".join(q.raw for q in Qs), len(Ps)
+
+
+def Pair(P, Q):
+    """bn254.Pair(P []G1Affine, Q []G2Affine) (GT, error)"""
+    pb, qb, k = _pack(P, Q)
+    return GT(default_engine().multi_pair_batch(pb, qb, k).tobytes())
+
+
+def PairingCheck(P, Q):
+    """bn254.PairingCheck(P, Q) (bool, error)"""
+    pb, qb, k = _pack(P, Q)
+    return bool(default_engine().pairing_check_batch(pb, qb, k)[0])
+
+
+def MillerLoop(P, Q):
+    """bn254.MillerLoop(P, Q) (GT, error): defined up to factors FinalExponentiation removes."""
+    pb, qb, k = _pack(P, Q)
+    return GT(default_engine().miller_loop_batch(pb, qb, k).tobytes())
+
+
+def FinalExponentiation(z, *more):
+    """bn254.FinalExponentiation(z *GT, _z ...*GT) GT: the inputs are multiplied first."""
+    acc = z
+    for m in more:
+        acc = GT().Mul(acc, m)
+    return GT(default_engine().final_exp_batch(acc.raw).tobytes())

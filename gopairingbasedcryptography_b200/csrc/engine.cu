@@ -1,0 +1,393 @@
+// libbn254_b200.so -- kernels and host runtime behind include/bn254_b200.h.
+// sm_100a only; no CPU fallback: every entry point needs a live CUDA device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <algorithm>
+
+#include "../../include/bn254_b200.h"
+#include "curve.cuh"
+
+using namespace bn254;
+
+// =============================================================================================
+// Kernels: one batch element per thread.  AoS operands are read with 128-bit loads; every element
+// is 64/128/384 B so a warp touches a contiguous 2-12 KB span (fully used sectors).
+// =============================================================================================
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int kPairChunk = 4;  // pairs per shared-squaring pass inside one thread
+
+template <typename T>
+__device__ __forceinline__ void load_struct(T& dst, const void* base, size_t idx) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(base) + idx * sizeof(T));
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(src + i);
+}
+template <typename T>
+__device__ __forceinline__ void store_struct(void* base, size_t idx, const T& src) {
+  uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(base) + idx * sizeof(T));
+  const uint4* s = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) dst[i] = s[i];
+}
+
+// Miller product of k pairs for one batch element, in passes of kPairChunk pairs.
+__device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t first, int k) {
+  G1Aff p[kPairChunk];
+  G2Aff q[kPairChunk];
+  G2Proj T[kPairChunk];
+  bool have = false;
+  for (int base = 0; base < k; base += kPairChunk) {
+    int c = min(kPairChunk, k - base);
+    for (int j = 0; j < c; j++) { load_struct(p[j], P, first + base + j); load_struct(q[j], Q, first + base + j); }
+    if (!have) { miller_loop(f, p, q, T, c); have = true; }
+    else { Fp12 g; miller_loop(g, p, q, T, c); fp12_mul(f, f, g); }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_pair(const void* P, const void* Q, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Aff p; G2Aff q; G2Proj T;
+  load_struct(p, P, i); load_struct(q, Q, i);
+  Fp12 f;
+  miller_loop(f, &p, &q, &T, 1);
+  final_exp(f, f);
+  store_struct(out, i, f);
+}
+// mode 0: Miller product only; 1: + final exponentiation; 2: pairing check (writes one byte)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_multi_pair(const void* P, const void* Q, size_t n, int k, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f;
+  miller_product(f, P, Q, i * (size_t)k, k);
+  if (MODE >= 1) final_exp(f, f);
+  if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
+  else store_struct(out, i, f);
+}
+__global__ void __launch_bounds__(kBlock) k_final_exp(const void* in, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f; load_struct(f, in, i);
+  final_exp(f, f);
+  store_struct(out, i, f);
+}
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock) k_scalar_mul(const void* base, size_t base_stride, const void* scalars, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  A b; load_struct(b, base, i * base_stride);
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(scalars) + i * 32);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  A r;
+  scalar_mul<J, A>(r, b, s);
+  store_struct(out, i, r);
+}
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock) k_aff_add(const void* a, const void* b, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  A x, y, r; load_struct(x, a, i); load_struct(y, b, i);
+  aff_add<J, A>(r, x, y);
+  store_struct(out, i, r);
+}
+__global__ void __launch_bounds__(kBlock) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 b; load_struct(b, x, i * x_stride);
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(k) + i * 32);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  Fp12 r;
+  gt_exp(r, b, s);
+  store_struct(out, i, r);
+}
+// mode 0: a*b ; mode 1: a/b
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x, y; load_struct(x, a, i); load_struct(y, b, i);
+  if (MODE == 1) fp12_inv(y, y);
+  fp12_mul(x, x, y);
+  store_struct(out, i, x);
+}
+__global__ void __launch_bounds__(kBlock) k_fp_mul(const void* a, const void* b, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x, y; load_struct(x, a, i); load_struct(y, b, i);
+  x = fp_mul(x, y);
+  store_struct(out, i, x);
+}
+
+inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+// =============================================================================================
+// Host runtime
+// =============================================================================================
+struct Slot {
+  cudaStream_t stream = nullptr;
+  char* h = nullptr;  // pinned staging
+  char* d = nullptr;  // device staging
+  // pending output copy-back
+  void* user_out = nullptr;
+  size_t out_off = 0, out_bytes = 0;
+  bool busy = false;
+};
+
+struct bn254_ctx {
+  int device = 0;
+  std::mutex mu;
+  std::string err;
+  Slot slot[2];
+  size_t slot_bytes = 0;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+constexpr size_t kSlotBytes = 96u << 20;       // per-slot staging (pinned + device)
+constexpr size_t kMaxChunkItems = 1u << 17;   // keeps two chunks in flight for copy/compute overlap
+
+int fail(bn254_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? BN254_ERR_OOM : BN254_ERR_CUDA, #call, e_); } while (0)
+
+struct Operand { const void* ptr; size_t item_bytes; bool broadcast; };
+// launch(d_in0, d_in1, count, d_out, stream)
+template <typename L>
+int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_item, size_t n, L launch) {
+  if (!ctx) return BN254_ERR_BAD_ARG;
+  if (n == 0) return BN254_OK;
+  if (!in0.ptr || !out || (in1.item_bytes && !in1.ptr)) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  size_t b0 = in0.broadcast ? in0.item_bytes : 0, b1 = in1.broadcast ? in1.item_bytes : 0;
+  size_t per = (in0.broadcast ? 0 : in0.item_bytes) + (in1.broadcast ? 0 : in1.item_bytes) + out_item;
+  size_t chunk = std::min<size_t>({n, kMaxChunkItems, (ctx->slot_bytes - b0 - b1 - 1024) / per});
+  if (chunk == 0) return fail(ctx, BN254_ERR_BAD_ARG, "element too large for staging");
+  auto finish = [&](Slot& s) -> int {
+    if (!s.busy) return BN254_OK;
+    CU(cudaStreamSynchronize(s.stream));
+    memcpy(s.user_out, s.h + s.out_off, s.out_bytes);
+    s.busy = false;
+    return BN254_OK;
+  };
+  size_t done = 0;
+  int ci = 0;
+  while (done < n) {
+    size_t c = std::min(chunk, n - done);
+    Slot& s = ctx->slot[ci & 1];
+    int rc = finish(s);
+    if (rc) return rc;
+    size_t off = 0;
+    auto align = [&]() { off = (off + 255) & ~size_t(255); };
+    size_t o0 = off, l0 = in0.broadcast ? in0.item_bytes : in0.item_bytes * c;
+    memcpy(s.h + o0, static_cast<const char*>(in0.ptr) + (in0.broadcast ? 0 : done * in0.item_bytes), l0);
+    off += l0; align();
+    size_t o1 = off, l1 = 0;
+    if (in1.item_bytes) {
+      l1 = in1.broadcast ? in1.item_bytes : in1.item_bytes * c;
+      memcpy(s.h + o1, static_cast<const char*>(in1.ptr) + (in1.broadcast ? 0 : done * in1.item_bytes), l1);
+      off += l1; align();
+    }
+    size_t oo = off, lo = out_item * c;
+    CU(cudaMemcpyAsync(s.d, s.h, oo, cudaMemcpyHostToDevice, s.stream));
+    launch(s.d + o0, s.d + o1, c, s.d + oo, s.stream);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s.h + oo, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream));
+    s.user_out = static_cast<char*>(out) + done * out_item;
+    s.out_off = oo; s.out_bytes = lo; s.busy = true;
+    done += c; ci++;
+  }
+  for (int i = 0; i < 2; i++) { int rc = finish(ctx->slot[(ci + i) & 1]); if (rc) return rc; }
+  return BN254_OK;
+}
+
+template <typename L>
+int run_dev(bn254_ctx* ctx, size_t n, L launch) {
+  if (!ctx) return BN254_ERR_BAD_ARG;
+  if (n == 0) return BN254_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  launch();
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return BN254_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bn254_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int bn254_ctx_create(int device, bn254_ctx** out) {
+  if (!out) return BN254_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n) return BN254_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BN254_ERR_CUDA;
+  if (prop.major != 10) return BN254_ERR_CUDA;  // sm_100a binary only
+  bn254_ctx* ctx = new bn254_ctx();
+  ctx->device = device;
+  ctx->slot_bytes = kSlotBytes;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return BN254_ERR_CUDA; }
+  for (int i = 0; i < 2; i++) {
+    Slot& s = ctx->slot[i];
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void**)&s.h, kSlotBytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void**)&s.d, kSlotBytes) != cudaSuccess) {
+      bn254_ctx_destroy(ctx);
+      return BN254_ERR_OOM;
+    }
+  }
+  *out = ctx;
+  return BN254_OK;
+}
+
+void bn254_ctx_destroy(bn254_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 2; i++) {
+    Slot& s = ctx->slot[i];
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.h) cudaFreeHost(s.h);
+    if (s.d) cudaFree(s.d);
+  }
+  delete ctx;
+}
+
+const char* bn254_last_error(bn254_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* bn254_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void bn254_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void bn254_generators(void* g1, void* g2) {
+  static const uint32_t G1[16] = {
+#include "generators_g1.inc"
+  };
+  static const uint32_t G2[32] = {
+#include "generators_g2.inc"
+  };
+  memcpy(g1, G1, 64);
+  memcpy(g2, G2, 128);
+}
+
+// ---- pairings -------------------------------------------------------------------------------
+int bn254_pair_batch_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, void* d_out, void* stream) {
+  return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
+}
+int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, void* out) {
+  return run_host(ctx, {P, BN254_G1_BYTES, false}, {Q, BN254_G2_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_pair<<<grid_for(c), kBlock, 0, s>>>(a, b, c, o); });
+}
+#define MULTI_PAIR_ENTRY(name, MODE, OUT_BYTES, OUT_T)                                                                     \
+  int name##_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, size_t k, OUT_T* d_out, void* stream) {         \
+    if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
+    return run_dev(ctx, n, [&] { k_multi_pair<MODE><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, (int)k, d_out); }); \
+  }                                                                                                                        \
+  int name(bn254_ctx* ctx, const void* P, const void* Q, size_t n, size_t k, OUT_T* out) {                                 \
+    if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
+    int kk = (int)k;                                                                                                       \
+    return run_host(ctx, {P, BN254_G1_BYTES * k, false}, {Q, BN254_G2_BYTES * k, false}, out, OUT_BYTES, n,                \
+                    [kk](const void* a, const void* b, size_t c, void* o, cudaStream_t s) {                                \
+                      k_multi_pair<MODE><<<grid_for(c), kBlock, 0, s>>>(a, b, c, kk, o);                                   \
+                    });                                                                                                    \
+  }
+MULTI_PAIR_ENTRY(bn254_miller_loop_batch, 0, BN254_GT_BYTES, void)
+MULTI_PAIR_ENTRY(bn254_multi_pair_batch, 1, BN254_GT_BYTES, void)
+MULTI_PAIR_ENTRY(bn254_pairing_check_batch, 2, 1, uint8_t)
+
+int bn254_final_exp_batch_dev(bn254_ctx* ctx, const void* d_in, size_t n, void* d_out, void* stream) {
+  return run_dev(ctx, n, [&] { k_final_exp<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_in, n, d_out); });
+}
+int bn254_final_exp_batch(bn254_ctx* ctx, const void* in, size_t n, void* out) {
+  return run_host(ctx, {in, BN254_GT_BYTES, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void*, size_t c, void* o, cudaStream_t s) { k_final_exp<<<grid_for(c), kBlock, 0, s>>>(a, c, o); });
+}
+
+// ---- scalar multiplication --------------------------------------------------------------------
+int bn254_g1_mul_batch_dev(bn254_ctx* ctx, const void* d_base, size_t stride, const void* d_s, size_t n, void* d_out, void* stream) {
+  return run_dev(ctx, n, [&] { k_scalar_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_base, stride, d_s, n, d_out); });
+}
+int bn254_g2_mul_batch_dev(bn254_ctx* ctx, const void* d_base, size_t stride, const void* d_s, size_t n, void* d_out, void* stream) {
+  return run_dev(ctx, n, [&] { k_scalar_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_base, stride, d_s, n, d_out); });
+}
+#define MUL_ENTRY(name, J, A, BYTES, BCAST)                                                                           \
+  int name(bn254_ctx* ctx, const void* base, const void* scalars, size_t n, void* out) {                              \
+    return run_host(ctx, {base, BYTES, BCAST}, {scalars, BN254_SCALAR_BYTES, false}, out, BYTES, n,                   \
+                    [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) {                             \
+                      k_scalar_mul<J, A><<<grid_for(c), kBlock, 0, s>>>(a, BCAST ? 0 : 1, b, c, o);                   \
+                    });                                                                                               \
+  }
+MUL_ENTRY(bn254_g1_mul_batch, G1Jac, G1Aff, BN254_G1_BYTES, false)
+MUL_ENTRY(bn254_g2_mul_batch, G2Jac, G2Aff, BN254_G2_BYTES, false)
+MUL_ENTRY(bn254_g1_mul_base_batch, G1Jac, G1Aff, BN254_G1_BYTES, true)
+MUL_ENTRY(bn254_g2_mul_base_batch, G2Jac, G2Aff, BN254_G2_BYTES, true)
+
+int bn254_g1_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  return run_host(ctx, {a, BN254_G1_BYTES, false}, {b, BN254_G1_BYTES, false}, out, BN254_G1_BYTES, n,
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_aff_add<G1Jac, G1Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+int bn254_g2_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  return run_host(ctx, {a, BN254_G2_BYTES, false}, {b, BN254_G2_BYTES, false}, out, BN254_G2_BYTES, n,
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_aff_add<G2Jac, G2Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+
+// ---- GT ---------------------------------------------------------------------------------------
+int bn254_gt_exp_batch_dev(bn254_ctx* ctx, const void* d_x, size_t stride, const void* d_k, size_t n, void* d_out, void* stream) {
+  return run_dev(ctx, n, [&] { k_gt_exp<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_x, stride, d_k, n, d_out); });
+}
+int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
+  return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+}
+int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
+  return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+}
+int bn254_gt_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_gt_mul<0><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+int bn254_gt_div_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_gt_mul<1><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+int bn254_fp_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  return run_host(ctx, {a, 32, false}, {b, 32, false}, out, 32, n,
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_fp_mul<<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+
+}  // extern "C"

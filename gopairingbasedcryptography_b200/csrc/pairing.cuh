@@ -1,0 +1,132 @@
+// Optimal-ate pairing on BN254: Miller loop and final exponentiation.
+// Replaces (reference side): gnark-crypto v0.19.0 ecc/bn254/pairing.go {Pair, PairingCheck,
+// MillerLoop, FinalExponentiation}, called at access/tree/access_tree_node.go:106,110,
+// cpabe/bsw07/bsw07_cpabe.go:184, ibe/waters05_ibe/waters05_ibe.go:214,259,262,
+// bibe/afp25_bibe/afp25_bibe.go:395-403, signature/bls01_signature/bls_signature.go:81-84.
+//
+// Conventions: D-type twist, untwist (x',y') -> (x' w^2, y' w^3); a line through
+// twist points with slope lam evaluated at P=(xP,yP) is  yP - lam xP w + (lam xT - yT) w^3, i.e. the
+// sparse Fp12 with non-zero slots (c0.b0, c1.b0, c1.b1).  Lines are kept up to Fp2 factors (killed by
+// the final exponentiation).  Final exponent d' = 2x0(6x0^2+3x0+1) (p^12-1)/r as in gnark.
+#pragma once
+#include "tower.cuh"
+
+namespace bn254 {
+
+struct G1Aff { Fp x, y; };
+struct G2Aff { Fp2 x, y; };
+struct G2Proj { Fp2 x, y, z; };
+
+BN_HD bool g1_is_inf(const G1Aff& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
+BN_HD bool g2_is_inf(const G2Aff& q) { return fp2_is_zero(q.x) && fp2_is_zero(q.y); }
+
+// Tangent at T (homogeneous projective), T <- 2T.  With E = 3b'Z^2:
+//   X3 = XY/2 (Y^2 - 3E), Y3 = ((Y^2+3E)/2)^2 - 3E^2, Z3 = 2Y^3Z
+//   line (times a subfield factor) = (-2YZ) yP + (3X^2) xP w + (E - Y^2) w^3
+BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
+  Fp2 A, B, C, E, F, G, H, J, t;
+  fp2_mul(A, T.x, T.y); A = fp2_half(A);
+  fp2_sqr(B, T.y);
+  fp2_sqr(C, T.z);
+  fp2_mul(E, C, TWIST_3B);
+  F = fp2_add(fp2_dbl(E), E);
+  G = fp2_half(fp2_add(B, F));
+  fp2_sqr(H, fp2_add(T.y, T.z)); H = fp2_sub(fp2_sub(H, B), C);
+  fp2_sqr(J, T.x);
+  fp2_mul(T.x, A, fp2_sub(B, F));
+  fp2_sqr(t, E);
+  fp2_sqr(G, G);
+  T.y = fp2_sub(G, fp2_add(fp2_dbl(t), t));
+  fp2_mul(T.z, B, H);
+  r0 = fp2_neg(H);
+  r1 = fp2_add(fp2_dbl(J), J);
+  r2 = fp2_sub(E, B);
+}
+// Chord through T and affine Q, T <- T + Q.  O = Y1 - y2 Z1, L = X1 - x2 Z1:
+//   line = L yP - O xP w + (O x2 - L y2) w^3
+BN_NOINLINE void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, bool update) {
+  Fp2 O, L, C, D, E, F, G, H, t, t1;
+  fp2_mul(t, Q.y, T.z); O = fp2_sub(T.y, t);
+  fp2_mul(t, Q.x, T.z); L = fp2_sub(T.x, t);
+  fp2_mul(t, L, Q.y); fp2_mul(t1, Q.x, O);
+  r2 = fp2_sub(t1, t);
+  r0 = L;
+  r1 = fp2_neg(O);
+  if (!update) return;
+  fp2_sqr(C, O); fp2_sqr(D, L);
+  fp2_mul(E, L, D);
+  fp2_mul(F, T.z, C);
+  fp2_mul(G, T.x, D);
+  H = fp2_sub(fp2_add(E, F), fp2_dbl(G));
+  fp2_mul(t1, T.y, E);
+  fp2_mul(T.x, L, H);
+  fp2_mul(t, fp2_sub(G, H), O);
+  T.y = fp2_sub(t, t1);
+  fp2_mul(T.z, E, T.z);
+}
+BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, const Fp2& r2) {
+  fp12_mul_034(f, fp2_mul_fp(r0, P.y), fp2_mul_fp(r1, P.x), r2);
+}
+
+// f *= Miller function of one pair.  Used with f = running product: the caller squares f between
+// NAF digits.  For the single-pair and small-k paths we run the digits inside (shared squarings).
+// P, Q: k pairs (pairs containing infinity are skipped).  T: scratch of k projective points.
+BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
+  fp12_set_one(f);
+  int live = 0;
+  for (int j = 0; j < k; j++) {
+    bool skip = g1_is_inf(P[j]) || g2_is_inf(Q[j]);
+    T[j].x = Q[j].x; T[j].y = Q[j].y;
+    T[j].z = skip ? fp2_zero() : fp2_one();  // z == 0 marks a skipped pair
+    live += skip ? 0 : 1;
+  }
+  if (live == 0) return;
+  Fp2 r0, r1, r2;
+  for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
+    int d = ATE_NAF[i];
+    for (int j = 0; j < k; j++) {
+      if (fp2_is_zero(T[j].z)) continue;
+      g2_dbl_step(T[j], r0, r1, r2);
+      apply_line(f, P[j], r0, r1, r2);
+      if (d) {
+        G2Aff q = Q[j];
+        if (d < 0) q.y = fp2_neg(q.y);
+        g2_add_step(T[j], q, r0, r1, r2, true);
+        apply_line(f, P[j], r0, r1, r2);
+      }
+    }
+  }
+  for (int j = 0; j < k; j++) {
+    if (fp2_is_zero(T[j].z)) continue;
+    G2Aff q1, q2;
+    fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
+    fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
+    q2.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q2.y = Q[j].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
+    g2_add_step(T[j], q1, r0, r1, r2, true);
+    apply_line(f, P[j], r0, r1, r2);
+    g2_add_step(T[j], q2, r0, r1, r2, false);
+    apply_line(f, P[j], r0, r1, r2);
+  }
+}
+
+// z^(d'), d' = 2x0(6x0^2+3x0+1)(p^12-1)/r.  Returns 1 early when the easy part is 1 (gnark behaviour).
+// z == 0 is mapped to 0 by the inversion convention inv(0) = 0.
+BN_NOINLINE void final_exp(Fp12& out, const Fp12& in) {
+  Fp12 f, t0, t1, t2, t3, t4;
+  fp12_conj(t0, in); fp12_inv(f, in); fp12_mul(t0, t0, f);
+  fp12_frob(f, t0, 2); fp12_mul(f, f, t0);
+  if (fp12_is_one(f)) { out = f; return; }
+  fp12_expt(t0, f); fp12_conj(t0, t0); fp12_cyclo_sqr(t0, t0);
+  fp12_cyclo_sqr(t1, t0); fp12_mul(t1, t0, t1);
+  fp12_expt(t2, t1); fp12_conj(t2, t2);
+  fp12_conj(t3, t1); fp12_mul(t1, t2, t3);
+  fp12_cyclo_sqr(t3, t2); fp12_expt(t4, t3); fp12_mul(t4, t1, t4);
+  fp12_mul(t3, t0, t4); fp12_mul(t0, t2, t4); fp12_mul(t0, f, t0);
+  fp12_frob(t2, t3, 1); fp12_mul(t0, t2, t0);
+  fp12_frob(t2, t4, 2); fp12_mul(t0, t2, t0);
+  fp12_conj(t2, f); fp12_mul(t2, t2, t3); fp12_frob(t2, t2, 3); fp12_mul(t0, t2, t0);
+  out = t0;
+}
+
+}  // namespace bn254

@@ -1,0 +1,218 @@
+// Extension tower over Fp for BN254, in gnark's E2/E6/E12 memory order:
+//   Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3-(9+u)), Fp12 = Fp6[w]/(w^2-v).
+// Replaces (reference side): gnark-crypto v0.19.0 ecc/bn254/internal/fptower/{e2,e6,e12,e12_pairing,
+// frobenius}.go, reached through GT.Mul/Div/Exp (access/tree/access_tree_node.go:114,156-157;
+// cpabe/bsw07/bsw07_cpabe.go:189-190) and every bn254.Pair call.
+//
+// Layering: Fp2 arithmetic is register-level (one thread, 16+16 limbs live); Fp6/Fp12 values live in
+// memory (per-thread local or shared) and are combined by out-of-line routines built from Fp2 steps,
+// which keeps the instruction footprint small enough for the SM instruction caches.
+#pragma once
+#include "fp.cuh"
+
+namespace bn254 {
+
+struct Fp6 { Fp2 b0, b1, b2; };
+struct Fp12 { Fp6 c0, c1; };
+
+// ------------------------------------------------------------------------------------------ Fp2
+BN_HD Fp2 fp2_zero() { Fp2 z; z.a0 = fp_zero(); z.a1 = fp_zero(); return z; }
+BN_HD Fp2 fp2_one() { Fp2 z; z.a0 = fp_one(); z.a1 = fp_zero(); return z; }
+BN_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.a0) && fp_is_zero(a.a1); }
+BN_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.a0, b.a0) && fp_eq(a.a1, b.a1); }
+BN_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_add(a.a0, b.a0); z.a1 = fp_add(a.a1, b.a1); return z; }
+BN_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sub(a.a0, b.a0); z.a1 = fp_sub(a.a1, b.a1); return z; }
+BN_HD Fp2 fp2_dbl(const Fp2& a) { Fp2 z; z.a0 = fp_dbl(a.a0); z.a1 = fp_dbl(a.a1); return z; }
+BN_HD Fp2 fp2_neg(const Fp2& a) { Fp2 z; z.a0 = fp_neg(a.a0); z.a1 = fp_neg(a.a1); return z; }
+BN_HD Fp2 fp2_conj(const Fp2& a) { Fp2 z; z.a0 = a.a0; z.a1 = fp_neg(a.a1); return z; }
+BN_HD Fp2 fp2_half(const Fp2& a) { Fp2 z; z.a0 = fp_half(a.a0); z.a1 = fp_half(a.a1); return z; }
+BN_HD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = fp_mul(a.a0, k); z.a1 = fp_mul(a.a1, k); return z; }
+// (9+u)(a0 + a1 u) = (9a0 - a1) + (a0 + 9a1) u
+BN_HD Fp2 fp2_mul_xi(const Fp2& a) {
+  Fp e0 = fp_dbl(fp_dbl(fp_dbl(a.a0))), e1 = fp_dbl(fp_dbl(fp_dbl(a.a1)));
+  Fp2 z;
+  z.a0 = fp_sub(fp_add(e0, a.a0), a.a1);
+  z.a1 = fp_add(fp_add(e1, a.a1), a.a0);
+  return z;
+}
+// Karatsuba: 3 Fp products
+BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
+  Fp t0 = fp_mul(a.a0, b.a0);
+  Fp t1 = fp_mul(a.a1, b.a1);
+  Fp m = fp_mul(fp_add(a.a0, a.a1), fp_add(b.a0, b.a1));
+  Fp2 z;
+  z.a0 = fp_sub(t0, t1);
+  z.a1 = fp_sub(fp_sub(m, t0), t1);
+  return z;
+}
+// complex squaring: 2 Fp products
+BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
+  Fp m = fp_mul(a.a0, a.a1);
+  Fp2 z;
+  z.a0 = fp_mul(fp_add(a.a0, a.a1), fp_sub(a.a0, a.a1));
+  z.a1 = fp_dbl(m);
+  return z;
+}
+// out-of-line bodies shared by every tower routine
+BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_inl(a, b); }
+BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_inl(a); }
+BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
+BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
+  Fp n = fp_add(fp_sqr(a.a0), fp_sqr(a.a1));
+  Fp ni; fp_inv_ool(ni, n);
+  Fp2 r; r.a0 = fp_mul(a.a0, ni); r.a1 = fp_neg(fp_mul(a.a1, ni));
+  z = r;
+}
+
+// ------------------------------------------------------------------------------------------ Fp6
+BN_HD void fp6_add(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_add(x.b0, y.b0); z.b1 = fp2_add(x.b1, y.b1); z.b2 = fp2_add(x.b2, y.b2); }
+BN_HD void fp6_sub(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_sub(x.b0, y.b0); z.b1 = fp2_sub(x.b1, y.b1); z.b2 = fp2_sub(x.b2, y.b2); }
+BN_HD void fp6_neg(Fp6& z, const Fp6& x) { z.b0 = fp2_neg(x.b0); z.b1 = fp2_neg(x.b1); z.b2 = fp2_neg(x.b2); }
+BN_HD void fp6_mul_v(Fp6& z, const Fp6& x) { Fp2 t = fp2_mul_xi(x.b2); z.b2 = x.b1; z.b1 = x.b0; z.b0 = t; }
+// Karatsuba, 6 Fp2 products.  z may alias x or y.
+BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
+  Fp2 v0, v1, v2, t, u0, u1, u2;
+  fp2_mul(v0, x.b0, y.b0);
+  fp2_mul(v1, x.b1, y.b1);
+  fp2_mul(v2, x.b2, y.b2);
+  fp2_mul(t, fp2_add(x.b1, x.b2), fp2_add(y.b1, y.b2));
+  u0 = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(t, v1), v2)), v0);
+  fp2_mul(t, fp2_add(x.b0, x.b1), fp2_add(y.b0, y.b1));
+  u1 = fp2_add(fp2_sub(fp2_sub(t, v0), v1), fp2_mul_xi(v2));
+  fp2_mul(t, fp2_add(x.b0, x.b2), fp2_add(y.b0, y.b2));
+  u2 = fp2_add(fp2_sub(fp2_sub(t, v0), v2), v1);
+  z.b0 = u0; z.b1 = u1; z.b2 = u2;
+}
+BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
+  Fp2 r0, r1, r2;
+  fp2_mul(r0, x.b0, k); fp2_mul(r1, x.b1, k); fp2_mul(r2, x.b2, k);
+  z.b0 = r0; z.b1 = r1; z.b2 = r2;
+}
+// x * (c0 + c1 v), 5 Fp2 products
+BN_NOINLINE void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& c0, const Fp2& c1) {
+  Fp2 a, b, t, r0, r1, r2;
+  fp2_mul(a, x.b0, c0);
+  fp2_mul(b, x.b1, c1);
+  fp2_mul(t, fp2_add(x.b1, x.b2), c1);
+  r0 = fp2_add(fp2_mul_xi(fp2_sub(t, b)), a);
+  fp2_mul(t, fp2_add(x.b0, x.b2), c0);
+  r2 = fp2_add(fp2_sub(t, a), b);
+  fp2_mul(t, fp2_add(x.b0, x.b1), fp2_add(c0, c1));
+  r1 = fp2_sub(fp2_sub(t, a), b);
+  z.b0 = r0; z.b1 = r1; z.b2 = r2;
+}
+BN_NOINLINE void fp6_inv(Fp6& z, const Fp6& x) {
+  Fp2 t0, t1, t2, s, n;
+  fp2_sqr(t0, x.b0); fp2_mul(s, x.b1, x.b2); t0 = fp2_sub(t0, fp2_mul_xi(s));
+  fp2_sqr(t1, x.b2); fp2_mul(s, x.b0, x.b1); t1 = fp2_sub(fp2_mul_xi(t1), s);
+  fp2_sqr(t2, x.b1); fp2_mul(s, x.b0, x.b2); t2 = fp2_sub(t2, s);
+  fp2_mul(n, x.b2, t1); fp2_mul(s, x.b1, t2); n = fp2_mul_xi(fp2_add(n, s));
+  fp2_mul(s, x.b0, t0); n = fp2_add(n, s);
+  fp2_inv(n, n);
+  Fp2 r0, r1, r2;
+  fp2_mul(r0, t0, n); fp2_mul(r1, t1, n); fp2_mul(r2, t2, n);
+  z.b0 = r0; z.b1 = r1; z.b2 = r2;
+}
+
+// ------------------------------------------------------------------------------------------ Fp12
+BN_HD void fp12_set_one(Fp12& z) {
+  z.c0.b0 = fp2_one(); z.c0.b1 = fp2_zero(); z.c0.b2 = fp2_zero();
+  z.c1.b0 = fp2_zero(); z.c1.b1 = fp2_zero(); z.c1.b2 = fp2_zero();
+}
+BN_HD bool fp12_is_one(const Fp12& z) {
+  return fp2_eq(z.c0.b0, fp2_one()) && fp2_is_zero(z.c0.b1) && fp2_is_zero(z.c0.b2) &&
+         fp2_is_zero(z.c1.b0) && fp2_is_zero(z.c1.b1) && fp2_is_zero(z.c1.b2);
+}
+BN_NOINLINE void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
+  Fp6 a, b, s, t;
+  fp6_mul(a, x.c0, y.c0);
+  fp6_mul(b, x.c1, y.c1);
+  fp6_add(s, x.c0, x.c1); fp6_add(t, y.c0, y.c1);
+  fp6_mul(s, s, t);
+  fp6_sub(s, s, a); fp6_sub(z.c1, s, b);
+  fp6_mul_v(b, b); fp6_add(z.c0, a, b);
+}
+// complex squaring, 2 Fp6 products
+BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x) {
+  Fp6 m, s, t;
+  fp6_mul(m, x.c0, x.c1);
+  fp6_add(s, x.c0, x.c1);
+  fp6_mul_v(t, x.c1); fp6_add(t, t, x.c0);
+  fp6_mul(s, s, t);  // c0^2 + v c1^2 + (1+v) c0 c1
+  fp6_sub(s, s, m); fp6_mul_v(t, m); fp6_sub(z.c0, s, t);
+  fp6_add(z.c1, m, m);
+}
+BN_HD void fp12_conj(Fp12& z, const Fp12& x) { z.c0 = x.c0; fp6_neg(z.c1, x.c1); }
+BN_NOINLINE void fp12_inv(Fp12& z, const Fp12& x) {
+  Fp6 n, t;
+  fp6_mul(n, x.c0, x.c0); fp6_mul(t, x.c1, x.c1); fp6_mul_v(t, t); fp6_sub(n, n, t);
+  fp6_inv(n, n);
+  fp6_mul(t, x.c1, n);
+  fp6_mul(z.c0, x.c0, n);
+  fp6_neg(z.c1, t);
+}
+// p^k-power Frobenius, k in {1,2,3}.  In the w-basis (g0=c0.b0 g1=c1.b0 g2=c0.b1 g3=c1.b1 g4=c0.b2
+// g5=c1.b2) the map is g_i -> conj^k(g_i) * xi^(i (p^k-1)/6).
+BN_NOINLINE void fp12_frob(Fp12& z, const Fp12& x, int k) {
+  Fp2 g[6] = {x.c0.b0, x.c1.b0, x.c0.b1, x.c1.b1, x.c0.b2, x.c1.b2};
+  if (k & 1) { for (int i = 0; i < 6; i++) g[i] = fp2_conj(g[i]); }
+  for (int i = 1; i < 6; i++) {
+    if (k == 2) g[i] = fp2_mul_fp(g[i], GAMMA2[i]);
+    else { Fp2 c = (k == 1) ? GAMMA1[i] : GAMMA3[i]; fp2_mul(g[i], g[i], c); }
+  }
+  z.c0.b0 = g[0]; z.c1.b0 = g[1]; z.c0.b1 = g[2]; z.c1.b1 = g[3]; z.c0.b2 = g[4]; z.c1.b2 = g[5];
+}
+// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
+// exponentiation).  Fp12 = Fp4[w]/(w^3 - s), s = w^3, s^2 = xi; z = A + B w + C w^2 with
+// A=(g0,g3) B=(g1,g4) C=(g2,g5):  z^2 = (3A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.
+BN_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b) {
+  Fp2 a2, b2, s;
+  fp2_sqr(a2, a); fp2_sqr(b2, b);
+  fp2_sqr(s, fp2_add(a, b));
+  r1 = fp2_sub(fp2_sub(s, a2), b2);
+  r0 = fp2_add(a2, fp2_mul_xi(b2));
+}
+BN_NOINLINE void fp12_cyclo_sqr(Fp12& z, const Fp12& x) {
+  Fp2 a0, a1, b0, b1, c0, c1;
+  fp4_sqr(a0, a1, x.c0.b0, x.c1.b1);
+  fp4_sqr(b0, b1, x.c1.b0, x.c0.b2);
+  fp4_sqr(c0, c1, x.c0.b1, x.c1.b2);
+  c1 = fp2_mul_xi(c1);
+  Fp2 g0 = x.c0.b0, g1 = x.c1.b0, g2 = x.c0.b1, g3 = x.c1.b1, g4 = x.c0.b2, g5 = x.c1.b2;
+  z.c0.b0 = fp2_add(fp2_dbl(fp2_sub(a0, g0)), a0);  // 3 a0 - 2 g0
+  z.c1.b1 = fp2_add(fp2_dbl(fp2_add(a1, g3)), a1);  // 3 a1 + 2 g3
+  z.c0.b1 = fp2_add(fp2_dbl(fp2_sub(b0, g2)), b0);
+  z.c1.b2 = fp2_add(fp2_dbl(fp2_add(b1, g5)), b1);
+  z.c1.b0 = fp2_add(fp2_dbl(fp2_add(c1, g1)), c1);  // 3 xi c1 + 2 g1
+  z.c0.b2 = fp2_add(fp2_dbl(fp2_sub(c0, g4)), c0);  // 3 c0 - 2 g4
+}
+// z *= l0 + l1 w + l3 w^3  (sparse "034" line), 13 Fp2 products
+BN_NOINLINE void fp12_mul_034(Fp12& z, const Fp2& l0, const Fp2& l1, const Fp2& l3) {
+  Fp6 a, b, s;
+  fp6_mul_fp2(a, z.c0, l0);
+  fp6_mul_01(b, z.c1, l1, l3);
+  fp6_add(s, z.c0, z.c1);
+  fp6_mul_01(s, s, fp2_add(l0, l1), l3);
+  fp6_sub(s, s, a); fp6_sub(z.c1, s, b);
+  fp6_mul_v(b, b); fp6_add(z.c0, a, b);
+}
+// x^e for x in the cyclotomic subgroup, e given as width-3 signed digits (LSB first); inverse = conjugate
+BN_NOINLINE void fp12_cyclo_exp_naf3(Fp12& z, const Fp12& x, const signed char* digits, int len) {
+  Fp12 x3, acc, m;
+  fp12_cyclo_sqr(x3, x); fp12_mul(x3, x3, x);
+  bool started = false;
+  for (int i = len - 1; i >= 0; i--) {
+    if (started) fp12_cyclo_sqr(acc, acc);
+    int d = digits[i];
+    if (d) {
+      int ad = d < 0 ? -d : d;
+      if (ad == 1) m = x; else m = x3;
+      if (d < 0) fp12_conj(m, m);
+      if (started) fp12_mul(acc, acc, m); else { acc = m; started = true; }
+    }
+  }
+  z = acc;
+}
+BN_HD void fp12_expt(Fp12& z, const Fp12& x) { fp12_cyclo_exp_naf3(z, x, X0_NAF3, X0_NAF3_LEN); }
+
+}  // namespace bn254

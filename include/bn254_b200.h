@@ -1,0 +1,119 @@
+/* bn254_b200.h -- C ABI of the B200-native batched BN254 pairing engine (libbn254_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of mmsyan/GoPairingBasedCryptography: the calls the
+ * schemes make into github.com/consensys/gnark-crypto v0.19.0 `ecc/bn254` (go.mod:5), re-exposed
+ * as BATCH entry points.  A Go package binds these through cgo (INTEGRATION.md shows the stubs);
+ * in this repository the Python mirror gopairingbasedcryptography_b200/bn254.py binds them through
+ * ctypes.  There is no CPU fallback: every entry point fails with BN254_ERR_CUDA when no sm_100
+ * device is usable.
+ *
+ * Data layout = gnark's in-memory layout, so Go values can be passed with unsafe.Pointer, no
+ * conversion:
+ *   fp.Element / fr.Element  32 B   4 x u64 little-endian limbs, Montgomery form (R = 2^256), < p
+ *   G1Affine {X,Y fp}        64 B   point at infinity = all zero
+ *   G2Affine {X,Y E2{A0,A1}} 128 B  point at infinity = all zero
+ *   GT = E12{C0,C1 E6{B0,B1,B2 E2}}  384 B
+ *   scalar                   32 B   little-endian unsigned integer, REGULAR form (big.Int value);
+ *                                   the Go shim reduces fr.Element -> big.Int exactly as the
+ *                                   reference does with x.BigInt(new(big.Int)).
+ * Arrays are contiguous AoS.  "_dev" variants take device pointers already resident in HBM and a
+ * cudaStream_t (as void*), enqueue asynchronously and do not synchronize; the others take host
+ * pointers (pageable or pinned), copy through per-context pinned staging on the context's streams
+ * and return when the results are in `out`.
+ *
+ * Return value: 0 on success, negative BN254_ERR_* otherwise.  Thread-safety: a context is
+ * internally locked; use one context per GPU (or several per GPU for concurrency).
+ */
+#ifndef BN254_B200_H
+#define BN254_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BN254_OK 0
+#define BN254_ERR_INVALID_SIZES (-1) /* gnark: errors.New("invalid inputs sizes") from Pair/MillerLoop/PairingCheck */
+#define BN254_ERR_CUDA (-2)          /* no device, launch or copy failure; see bn254_last_error */
+#define BN254_ERR_OOM (-3)
+#define BN254_ERR_BAD_ARG (-4)
+
+#define BN254_G1_BYTES 64
+#define BN254_G2_BYTES 128
+#define BN254_GT_BYTES 384
+#define BN254_SCALAR_BYTES 32
+
+typedef struct bn254_ctx bn254_ctx;
+
+/* lifecycle: one context per GPU ordinal */
+int bn254_ctx_create(int device, bn254_ctx** out);
+void bn254_ctx_destroy(bn254_ctx* ctx);
+const char* bn254_last_error(bn254_ctx* ctx); /* text of the last failure on this context */
+int bn254_device_count(void);
+/* pinned host memory for zero-staging transfers (optional) */
+void* bn254_host_alloc(size_t bytes);
+void bn254_host_free(void* p);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+uint64_t bn254_launch_count(bn254_ctx* ctx);
+
+/* bn254.Generators()  [31 call sites, e.g. signature/bls01_signature/bls_signature.go:32] */
+void bn254_generators(void* g1_aff_64, void* g2_aff_128);
+
+/* n independent bn254.Pair([]G1Affine{P[i]}, []G2Affine{Q[i]})
+ * [access/tree/access_tree_node.go:106,110; cpabe/bsw07/bsw07_cpabe.go:184;
+ *  ibe/waters05_ibe/waters05_ibe.go:214,259,262; bibe/afp25_bibe/afp25_bibe.go:395-403] */
+int bn254_pair_batch(bn254_ctx*, const void* P, const void* Q, size_t n, void* out_gt);
+int bn254_pair_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, void* d_out_gt, void* stream);
+
+/* n products bn254.Pair(P[i*k..i*k+k), Q[i*k..i*k+k)): one Miller product, ONE final exponentiation
+ * each; pairs containing infinity are skipped; k == 0 -> BN254_ERR_INVALID_SIZES.
+ * [the fused multi-pairing shape of access/tree/access_tree_node.go:96-164 + bsw07_cpabe.go:172-195] */
+int bn254_multi_pair_batch(bn254_ctx*, const void* P, const void* Q, size_t n, size_t k, void* out_gt);
+int bn254_multi_pair_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, size_t k, void* d_out_gt, void* stream);
+
+/* n x bn254.PairingCheck(P[i*k..], Q[i*k..]) -> ok[i] in {0,1}
+ * [signature/bls01_signature/bls_signature.go:81-84] */
+int bn254_pairing_check_batch(bn254_ctx*, const void* P, const void* Q, size_t n, size_t k, uint8_t* ok);
+int bn254_pairing_check_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, size_t k, uint8_t* d_ok, void* stream);
+
+/* bn254.MillerLoop / bn254.FinalExponentiation (0 call sites in the reference; named by north_star).
+ * The raw Miller value is defined only up to factors the final exponentiation kills;
+ * final_exp(miller_loop(P,Q)) == pair(P,Q) bit-exactly. */
+int bn254_miller_loop_batch(bn254_ctx*, const void* P, const void* Q, size_t n, size_t k, void* out_gt);
+int bn254_final_exp_batch(bn254_ctx*, const void* in_gt, size_t n, void* out_gt);
+int bn254_miller_loop_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, size_t k, void* d_out_gt, void* stream);
+int bn254_final_exp_batch_dev(bn254_ctx*, const void* d_in_gt, size_t n, void* d_out_gt, void* stream);
+
+/* (*G1Affine).ScalarMultiplication(&base[i], s[i]) / (*G2Affine).ScalarMultiplication
+ * [bls_signature.go:63; waters05_ibe.go:237; bsw07_cpabe.go:149,160; afp25_bibe_utils.go:48,51] */
+int bn254_g1_mul_batch(bn254_ctx*, const void* base, const void* scalars, size_t n, void* out);
+int bn254_g2_mul_batch(bn254_ctx*, const void* base, const void* scalars, size_t n, void* out);
+/* ScalarMultiplicationBase and any other fixed point: ONE base, n scalars
+ * [bls_signature.go:45; waters05_ibe.go:224; bsw07_cpabe.go:69,157; afp25_bibe.go:160] */
+int bn254_g1_mul_base_batch(bn254_ctx*, const void* base1, const void* scalars, size_t n, void* out);
+int bn254_g2_mul_base_batch(bn254_ctx*, const void* base1, const void* scalars, size_t n, void* out);
+int bn254_g1_mul_batch_dev(bn254_ctx*, const void* d_base, size_t base_stride_elems, const void* d_scalars, size_t n, void* d_out, void* stream);
+int bn254_g2_mul_batch_dev(bn254_ctx*, const void* d_base, size_t base_stride_elems, const void* d_scalars, size_t n, void* d_out, void* stream);
+
+/* (*G1Affine).Add / (*G2Affine).Add, canonical affine result, gnark semantics for infinity,
+ * doubling and P + (-P)  [waters05_ibe.go:227-233; bsw07_cpabe.go:104,119] */
+int bn254_g1_add_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+int bn254_g2_add_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+
+/* (*GT).Exp(x[i], k[i]) with k >= 0 (the Go shim inverts x for negative k as gnark does); generic
+ * Fp12 exponentiation, no subgroup assumption; k == 0 -> 1
+ * [access/tree/access_tree_node.go:156; waters05_ibe.go:219; bsw07_cpabe.go:80,146] */
+int bn254_gt_exp_batch(bn254_ctx*, const void* x, const void* k, size_t n, void* out);
+int bn254_gt_exp_base_batch(bn254_ctx*, const void* x1, const void* k, size_t n, void* out);
+int bn254_gt_exp_batch_dev(bn254_ctx*, const void* d_x, size_t x_stride_elems, const void* d_k, size_t n, void* d_out, void* stream);
+/* (*GT).Mul / (*GT).Div  [access_tree_node.go:114,157; bsw07_cpabe.go:189-190] */
+int bn254_gt_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+int bn254_gt_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+
+/* diagnostics used by the parity tests: raw Fp Montgomery product, 32 B operands */
+int bn254_fp_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

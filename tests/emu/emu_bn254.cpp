@@ -1,0 +1,46 @@
+// Host emulation of the DEVICE algorithms (csrc/*.cuh compiled by a plain C++ compiler; the PTX carry
+// wrappers fall back to a C model).  TEST HARNESS ONLY: lets `-m "not gpu"` tests check the tower,
+// Miller loop, final exponentiation and group code bit-for-bit against the oracle without a GPU.
+// Never linked into libbn254_b200.so.
+#include <cstring>
+#include <cstddef>
+#include "../../gopairingbasedcryptography_b200/csrc/curve.cuh"
+using namespace bn254;
+
+template <typename T> static T ld(const void* p, size_t i) { T t; memcpy(&t, (const char*)p + i * sizeof(T), sizeof(T)); return t; }
+template <typename T> static void st(void* p, size_t i, const T& t) { memcpy((char*)p + i * sizeof(T), &t, sizeof(T)); }
+
+extern "C" {
+void emu_fp_mul(const void* a, const void* b, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp_mul(ld<Fp>(a, i), ld<Fp>(b, i))); }
+void emu_fp_add(const void* a, const void* b, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp_add(ld<Fp>(a, i), ld<Fp>(b, i))); }
+void emu_fp_sub(const void* a, const void* b, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp_sub(ld<Fp>(a, i), ld<Fp>(b, i))); }
+void emu_fp_half(const void* a, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp_half(ld<Fp>(a, i))); }
+void emu_fp_inv(const void* a, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp_inv(ld<Fp>(a, i))); }
+void emu_multi_pair(const void* P, const void* Q, size_t n, size_t k, int mode, void* out) {
+  for (size_t i = 0; i < n; i++) {
+    Fp12 f; bool have = false;
+    for (size_t base = 0; base < k; base += 4) {
+      G1Aff p[4]; G2Aff q[4]; G2Proj T[4];
+      int c = (int)((k - base) < 4 ? (k - base) : 4);
+      for (int j = 0; j < c; j++) { p[j] = ld<G1Aff>(P, i * k + base + j); q[j] = ld<G2Aff>(Q, i * k + base + j); }
+      if (!have) { miller_loop(f, p, q, T, c); have = true; } else { Fp12 g; miller_loop(g, p, q, T, c); fp12_mul(f, f, g); }
+    }
+    if (mode >= 1) final_exp(f, f);
+    if (mode == 2) ((unsigned char*)out)[i] = fp12_is_one(f) ? 1 : 0; else st(out, i, f);
+  }
+}
+void emu_final_exp(const void* in, size_t n, void* out) { for (size_t i = 0; i < n; i++) { Fp12 f = ld<Fp12>(in, i); final_exp(f, f); st(out, i, f); } }
+void emu_g1_mul(const void* base, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { G1Aff b = ld<G1Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); scalar_mul<G1Jac, G1Aff>(r, b, k); st(out, i, r); } }
+void emu_g2_mul(const void* base, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); scalar_mul<G2Jac, G2Aff>(r, b, k); st(out, i, r); } }
+void emu_g1_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G1Aff r; aff_add<G1Jac, G1Aff>(r, ld<G1Aff>(a, i), ld<G1Aff>(b, i)); st(out, i, r); } }
+void emu_g2_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G2Aff r; aff_add<G2Jac, G2Aff>(r, ld<G2Aff>(a, i), ld<G2Aff>(b, i)); st(out, i, r); } }
+void emu_gt_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); gt_exp(r, b, k); st(out, i, r); } }
+void emu_gt_mul(const void* a, const void* b, size_t n, int div, void* out) {
+  for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i), y = ld<Fp12>(b, i); if (div) fp12_inv(y, y); fp12_mul(x, x, y); st(out, i, x); } }
+void emu_gt_sqr(const void* a, size_t n, int cyclo, void* out) {
+  for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i); if (cyclo) fp12_cyclo_sqr(x, x); else fp12_sqr(x, x); st(out, i, x); } }
+void emu_gt_frob(const void* a, size_t n, int k, void* out) { for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i); fp12_frob(x, x, k); st(out, i, x); } }
+}

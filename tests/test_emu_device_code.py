@@ -1,0 +1,134 @@
+"""The DEVICE algorithms (csrc/*.cuh) compiled for the host with an emulated PTX carry flag, checked
+bit-for-bit against the oracle.  This is a test harness for the CUDA sources on a box without a GPU;
+it is not a product code path (the shipped .so has no CPU fallback)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bn254_ref as o
+from oracle import port
+
+import common
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu_bn254.cpp")
+SO = os.path.join(HERE, "emu", "_emu_bn254.so")
+CSRC = os.path.join(HERE, "..", "gopairingbasedcryptography_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+sz = ctypes.c_size_t
+
+
+def test_fp_arithmetic(emu):
+    rng = o.SplitMix64(11)
+    edge = [0, 1, o.P - 1, o.P - 2, 1 << 253, (1 << 32) - 1, 1 << 224]
+    n = 512
+    A = edge + [rng.fp() for _ in range(n - len(edge))]
+    B = [rng.fp() for _ in range(n - len(edge))] + edge
+    enc = lambda v: np.frombuffer(b"".join(x.to_bytes(32, "little") for x in v), dtype=np.uint8).copy()
+    dec = lambda a: [int.from_bytes(a[32 * i:32 * i + 32].tobytes(), "little") for i in range(len(a) // 32)]
+    a, b, z = enc(A), enc(B), np.zeros(32 * n, np.uint8)
+    rinv = pow(1 << 256, -1, o.P)
+    emu.emu_fp_mul(vp(a), vp(b), sz(n), vp(z))
+    assert dec(z) == [x * y * rinv % o.P for x, y in zip(A, B)]
+    emu.emu_fp_add(vp(a), vp(b), sz(n), vp(z))
+    assert dec(z) == [(x + y) % o.P for x, y in zip(A, B)]
+    emu.emu_fp_sub(vp(a), vp(b), sz(n), vp(z))
+    assert dec(z) == [(x - y) % o.P for x, y in zip(A, B)]
+    emu.emu_fp_half(vp(a), sz(n), vp(z))
+    assert dec(z) == [x * pow(2, -1, o.P) % o.P for x in A]
+    emu.emu_fp_inv(vp(a), sz(16), vp(z))
+    assert dec(z)[:16] == [(pow(x * rinv, -1, o.P) * (1 << 256) % o.P if x else 0) for x in A[:16]]
+    # inputs up to 2p are tolerated by the Montgomery product (used by lazy-reduction paths)
+    A2 = [rng.u256() % (2 * o.P) for _ in range(n)]
+    B2 = [rng.u256() % (2 * o.P) for _ in range(n)]
+    a, b = enc(A2), enc(B2)
+    emu.emu_fp_mul(vp(a), vp(b), sz(n), vp(z))
+    assert dec(z) == [x * y * rinv % o.P for x, y in zip(A2, B2)]
+
+
+def test_pairing_paths(emu):
+    n = 6
+    P, Q, _, _ = common.points(n)
+    ref = port.pair_batch(P, Q, n)
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_multi_pair(vp(P), vp(Q), sz(n), sz(1), 1, vp(out))
+    assert (out == ref).all()
+    for k in (2, 3, 6):
+        m = n // k
+        out = np.zeros(384 * m, np.uint8)
+        emu.emu_multi_pair(vp(P), vp(Q), sz(m), sz(k), 1, vp(out))
+        assert (out == port.multi_pair_batch(P, Q, m, k)).all()
+    ml = np.zeros(384 * n, np.uint8)
+    emu.emu_multi_pair(vp(P), vp(Q), sz(n), sz(1), 0, vp(ml))
+    fe = np.zeros(384 * n, np.uint8)
+    emu.emu_final_exp(vp(ml), sz(n), vp(fe))
+    assert (fe == ref).all()
+    assert (fe == port.final_exp_batch(ml, n)).all()
+
+
+def test_pairing_infinity_and_check(emu):
+    n = 4
+    P, Q, _, _ = common.points(n, seed=21)
+    P2, Q2 = common.with_infinities(P, Q)
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_multi_pair(vp(P2), vp(Q2), sz(n), sz(1), 1, vp(out))
+    assert (out == port.pair_batch(P2, Q2, n)).all()
+    one = o.gt_to_bytes(o.FP12_ONE)
+    assert out[:384].tobytes() == one and out[768:1152].tobytes() == one
+    # check: e(P,Q) e(-P,Q) == 1
+    Pn = np.frombuffer(o.g1_to_bytes(o.g1_neg(o.g1_from_bytes(P[:64].tobytes()))), dtype=np.uint8)
+    PP = np.concatenate([P[:64], Pn, P[:64], P[:64]])
+    QQ = np.concatenate([Q[:128]] * 4)
+    ok = np.zeros(2, np.uint8)
+    emu.emu_multi_pair(vp(PP), vp(QQ), sz(2), sz(2), 2, vp(ok))
+    assert list(ok) == [1, 0]
+
+
+def test_groups_and_gt(emu):
+    n = 10
+    ks = common.scalars(n)
+    sb = common.scalar_bytes(ks)
+    P, Q, _, _ = common.points(n, seed=31)
+    out = np.zeros(64 * n, np.uint8)
+    emu.emu_g1_mul(vp(P), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == port.g1_mul_batch(P, sb, n)).all()
+    out = np.zeros(128 * n, np.uint8)
+    emu.emu_g2_mul(vp(Q), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == port.g2_mul_batch(Q, sb, n)).all()
+    Pr, Qr = np.roll(P, 64), np.roll(Q, 128)
+    out = np.zeros(64 * n, np.uint8)
+    emu.emu_g1_add(vp(P), vp(Pr), sz(n), vp(out))
+    assert (out == port.g1_add_batch(P, Pr, n)).all()
+    emu.emu_g1_add(vp(P), vp(P), sz(n), vp(out))
+    assert (out == port.g1_add_batch(P, P, n)).all()
+    out = np.zeros(128 * n, np.uint8)
+    emu.emu_g2_add(vp(Q), vp(Qr), sz(n), vp(out))
+    assert (out == port.g2_add_batch(Q, Qr, n)).all()
+    m = 4
+    gt = port.pair_batch(P[:64 * m], Q[:128 * m], m)
+    out = np.zeros(384 * m, np.uint8)
+    emu.emu_gt_exp(vp(gt), sz(1), vp(sb), sz(m), vp(out))
+    assert (out == port.gt_exp_batch(gt, sb[:32 * m], m)).all()
+    gt2 = np.roll(gt, 384)
+    emu.emu_gt_mul(vp(gt), vp(gt2), sz(m), 0, vp(out))
+    assert (out == port.gt_mul_batch(gt, gt2, m)).all()
+    emu.emu_gt_mul(vp(gt), vp(gt2), sz(m), 1, vp(out))
+    assert (out == port.gt_div_batch(gt, gt2, m)).all()
+    emu.emu_gt_sqr(vp(gt), sz(m), 1, vp(out))
+    assert (out == port.gt_sqr_batch(gt, m)).all()

@@ -1,0 +1,217 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs -- bit-exact (integer work).  Run with `-m gpu` on a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bn254_ref as o
+from oracle import port
+
+import common
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def hx(s):
+    return np.frombuffer(bytes.fromhex(s), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(HERE, "golden", "bn254_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_fp_mul(engine):
+    rng = o.SplitMix64(1)
+    n = 1 << 14
+    a = np.frombuffer(b"".join(rng.fp().to_bytes(32, "little") for _ in range(n)), dtype=np.uint8)
+    b = np.frombuffer(b"".join(rng.fp().to_bytes(32, "little") for _ in range(n)), dtype=np.uint8)
+    assert (engine.fp_mul_batch(a, b).reshape(-1) == port.fp_mul_batch(a, b, n, 8)).all()
+
+
+def test_golden_vectors(engine, golden):
+    for v in golden["pair"]:
+        assert engine.pair_batch(hx(v["P"]), hx(v["Q"])).tobytes().hex() == v["gt"]
+    for v in golden["multi_pair"]:
+        assert engine.multi_pair_batch(hx(v["P"]), hx(v["Q"]), v["k"]).tobytes().hex() == v["gt"]
+    v = golden["final_exp"]
+    assert engine.final_exp_batch(hx(v["in"])).tobytes().hex() == v["out"]
+    for v in golden["g1_mul"]:
+        assert engine.g1_mul_batch(hx(v["base"]), hx(v["k"])).tobytes().hex() == v["out"]
+    for v in golden["g2_mul"]:
+        assert engine.g2_mul_batch(hx(v["base"]), hx(v["k"])).tobytes().hex() == v["out"]
+    for v in golden["g1_add"]:
+        assert engine.g1_add_batch(hx(v["a"]), hx(v["b"])).tobytes().hex() == v["out"]
+    for v in golden["g2_add"]:
+        assert engine.g2_add_batch(hx(v["a"]), hx(v["b"])).tobytes().hex() == v["out"]
+    for v in golden["gt_exp"]:
+        assert engine.gt_exp_batch(hx(v["x"]), hx(v["k"])).tobytes().hex() == v["out"]
+    v = golden["gt_mul"]
+    assert engine.gt_mul_batch(hx(v["a"]), hx(v["b"])).tobytes().hex() == v["mul"]
+    assert engine.gt_div_batch(hx(v["a"]), hx(v["b"])).tobytes().hex() == v["div"]
+
+
+def test_pair_batch_vs_oracle(engine):
+    n = 1024 + 7  # ragged: not a multiple of the block size
+    P, Q, _, _ = common.points(n, threads=8)
+    P, Q = common.with_infinities(P, Q)
+    out = engine.pair_batch(P, Q)
+    assert (out.reshape(-1) == port.pair_batch(P, Q, n, 8)).all()
+    one = o.gt_to_bytes(o.FP12_ONE)
+    assert out[0].tobytes() == one and out[1].tobytes() == one and out[2].tobytes() == one
+
+
+def test_single_element_and_errors(engine):
+    P, Q, _, _ = common.points(1, seed=99)
+    assert (engine.pair_batch(P, Q).reshape(-1) == port.pair_batch(P, Q, 1)).all()
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        engine.pair_batch(P, np.concatenate([Q, Q]))
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        engine.multi_pair_batch(P, Q, 0)
+    assert engine.pair_batch(b"", b"").shape == (0, 384)
+
+
+@pytest.mark.parametrize("k", [2, 3, 5, 9])
+def test_multi_pair_and_check(engine, k):
+    n = 48
+    P, Q, _, _ = common.points(n * k, seed=1000 + k, threads=8)
+    P, Q = common.with_infinities(P, Q)
+    assert (engine.multi_pair_batch(P, Q, k).reshape(-1) == port.multi_pair_batch(P, Q, n, k, 8)).all()
+    ml = engine.miller_loop_batch(P, Q, k)
+    assert (engine.final_exp_batch(ml).reshape(-1) == port.multi_pair_batch(P, Q, n, k, 8)).all()
+    assert (engine.pairing_check_batch(P, Q, k) == port.pairing_check_batch(P, Q, n, k, 8).astype(bool)).all()
+
+
+def test_bls_verify_batch(engine):
+    """Config 1 shape (signature/bls01_signature/bls_signature.go:58-89), H(m) := [h_i]G2 synthetic hash:
+    sign on the GPU, verify on the GPU, flip some messages -> those verify false."""
+    n = 256
+    g1, g2 = port.generators()
+    sk = 0x1F2E3D4C5B6A79880123456789ABCDEF % o.R
+    hs = common.scalars(n, seed=4242, edges=False)
+    skb = common.scalar_bytes([sk])
+    pk = engine.g1_mul_base_batch(g1, skb)
+    hm = engine.g2_mul_base_batch(g2, common.scalar_bytes(hs))
+    sigma = engine.g2_mul_batch(hm, np.tile(skb, n))
+    assert (sigma.reshape(-1) == port.g2_mul_batch(hm.reshape(-1), np.tile(skb, n), n, 8)).all()
+    neg = sigma.copy().reshape(n, 4, 32)
+    for i in range(n):
+        for c in (2, 3):
+            v = int.from_bytes(neg[i, c].tobytes(), "little")
+            neg[i, c] = np.frombuffer(((o.P - v) % o.P).to_bytes(32, "little"), dtype=np.uint8)
+    hm_bad = hm.copy()
+    bad = list(range(0, n, 4))
+    hm_bad[bad] = engine.g2_mul_base_batch(g2, common.scalar_bytes([hs[i] + 1 for i in bad]))
+    P = np.concatenate([np.tile(pk.reshape(1, 64), (n, 1)), np.tile(g1.reshape(1, 64), (n, 1))], axis=1)  # (n, 2*64)
+    Qg = np.concatenate([hm_bad, neg.reshape(n, 128)], axis=1)
+    ok = engine.pairing_check_batch(P, Qg, 2)
+    expect = np.array([i not in bad for i in range(n)])
+    assert (ok == expect).all()
+    assert (ok == port.pairing_check_batch(P, Qg, n, 2, 8).astype(bool)).all()
+
+
+def test_groups_vs_oracle(engine):
+    n = 300
+    ks = common.scalars(n) + [(1 << 256) - 1]
+    n += 1
+    sb = common.scalar_bytes(ks)
+    P, Q, _, _ = common.points(n, seed=31, threads=8)
+    P[64 * 9:64 * 10] = 0  # infinity base
+    assert (engine.g1_mul_batch(P, sb).reshape(-1) == port.g1_mul_batch(P, sb, n, 8)).all()
+    assert (engine.g2_mul_batch(Q, sb).reshape(-1) == port.g2_mul_batch(Q, sb, n, 8)).all()
+    g1, g2 = port.generators()
+    assert (engine.g1_mul_base_batch(g1, sb).reshape(-1) == port.g1_mul_base_batch(g1, sb, n, 8)).all()
+    assert (engine.g2_mul_base_batch(g2, sb).reshape(-1) == port.g2_mul_base_batch(g2, sb, n, 8)).all()
+    Pr, Qr = np.roll(P, 64), np.roll(Q, 128)
+    assert (engine.g1_add_batch(P, Pr).reshape(-1) == port.g1_add_batch(P, Pr, n, 8)).all()
+    assert (engine.g1_add_batch(P, P).reshape(-1) == port.g1_add_batch(P, P, n, 8)).all()
+    assert (engine.g2_add_batch(Q, Qr).reshape(-1) == port.g2_add_batch(Q, Qr, n, 8)).all()
+
+
+def test_gt_vs_oracle(engine):
+    n = 64
+    P, Q, _, _ = common.points(n, seed=55, threads=8)
+    gt = engine.pair_batch(P, Q)
+    sb = common.scalar_bytes(common.scalars(n))
+    assert (engine.gt_exp_batch(gt, sb).reshape(-1) == port.gt_exp_batch(gt.reshape(-1), sb, n, 8)).all()
+    assert (engine.gt_exp_base_batch(gt[0], sb).reshape(-1) == port.gt_exp_base_batch(gt[0], sb, n, 8)).all()
+    gt2 = np.roll(gt, 1, axis=0)
+    assert (engine.gt_mul_batch(gt, gt2).reshape(-1) == port.gt_mul_batch(gt.reshape(-1), gt2.reshape(-1), n, 8)).all()
+    assert (engine.gt_div_batch(gt, gt2).reshape(-1) == port.gt_div_batch(gt.reshape(-1), gt2.reshape(-1), n, 8)).all()
+
+
+def test_bilinearity_checksum_large(engine):
+    """Size-independent property at a size the oracle cannot finish: prod_i e(a_i G1, b_i G2) ==
+    e(G1,G2)^(sum a_i b_i), with the points generated on the GPU."""
+    n = 1 << 14
+    a = common.scalars(n, seed=7, edges=False)
+    b = common.scalars(n, seed=8, edges=False)
+    g1, g2 = port.generators()
+    P = engine.g1_mul_base_batch(g1, common.scalar_bytes(a))
+    Q = engine.g2_mul_base_batch(g2, common.scalar_bytes(b))
+    gt = engine.pair_batch(P, Q)
+    # sampled bit-exact check
+    idx = [0, 1, n // 2, n - 1]
+    ref = port.pair_batch(P[idx].reshape(-1), Q[idx].reshape(-1), len(idx), 4).reshape(len(idx), 384)
+    assert (gt[idx] == ref).all()
+    # product tree on the GPU
+    cur = gt
+    while cur.shape[0] > 1:
+        h = cur.shape[0] // 2
+        cur = engine.gt_mul_batch(cur[:h], cur[h:2 * h])
+    s = sum(x * y for x, y in zip(a, b)) % o.R
+    e = port.pair_batch(g1, g2, 1)
+    assert cur[0].tobytes() == port.gt_exp_batch(e, common.scalar_bytes([s]), 1).tobytes()
+
+
+def test_gnark_named_api(engine):
+    """Reads like the reference's tests (e.g. signature/zss04_signature/zss04_signature_test.go:26-38)."""
+    from gopairingbasedcryptography_b200 import bn254
+
+    _, _, g1, g2 = bn254.Generators()
+    e1 = bn254.Pair([g1], [g2])
+    e2 = bn254.Pair([g1], [g2])
+    assert e1 == e2 and e1.Equal(e2)  # deterministic
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        bn254.Pair([], [])
+    x = 0x1234567
+    pk = bn254.G1Affine().ScalarMultiplicationBase(x)
+    hm = bn254.G2Affine().ScalarMultiplicationBase(987654321)
+    sig = bn254.G2Affine().ScalarMultiplication(hm, x)
+    assert bn254.PairingCheck([pk, g1], [hm, bn254.G2Affine().Neg(sig)])
+    assert not bn254.PairingCheck([pk, g1], [hm, sig])
+    assert bn254.FinalExponentiation(bn254.MillerLoop([pk], [hm])) == bn254.Pair([pk], [hm])
+    # GT.Exp / Mul / Div / Inverse and negative exponents
+    a = bn254.GT().Exp(e1, 5)
+    b = bn254.GT().Exp(e1, -5)
+    assert bn254.GT().Mul(a, b) == bn254.GT().SetOne()
+    assert bn254.GT().Div(a, a) == bn254.GT().SetOne()
+    assert bn254.GT().Exp(e1, 0) == bn254.GT().SetOne()
+    assert bn254.Pair([pk], [hm]) == bn254.GT().Exp(bn254.Pair([g1], [hm]), x)
+    # negative / oversized group scalars follow big.Int semantics
+    assert bn254.G1Affine().ScalarMultiplication(g1, -1) == bn254.G1Affine().Neg(g1)
+    assert bn254.G1Affine().ScalarMultiplication(g1, bn254.R_MOD + 2) == bn254.G1Affine().Add(g1, g1)
+    assert bn254.G1Affine().Sub(g1, g1).IsInfinity()
+
+
+def test_device_pointer_entry_points(engine):
+    import torch
+
+    n = 512
+    P, Q, _, _ = common.points(n, seed=77, threads=8)
+    dP = torch.from_numpy(P.copy()).cuda()
+    dQ = torch.from_numpy(Q.copy()).cuda()
+    dO = torch.empty(n * 384, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    engine.pair_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, dO.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert (dO.cpu().numpy() == port.pair_batch(P, Q, n, 8)).all()
+    dM = torch.empty(n * 384, dtype=torch.uint8, device="cuda")
+    engine.miller_loop_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, 1, dM.data_ptr(), s)
+    engine.final_exp_batch_dev(dM.data_ptr(), n, dM.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert torch.equal(dM, dO)
