@@ -4,6 +4,7 @@
 // Run on the GPU box: ./imad_peak > gpurun_out/imad_peak.json
 #include <cstdio>
 #include <cstdint>
+#include <string>
 #include <cuda_runtime.h>
 #include "../../gopairingbasedcryptography_b200/csrc/fp.cuh"
 
@@ -113,7 +114,8 @@ static float time_kernel(F launch) {
   return ms / reps;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  bool quick = argc > 1 && std::string(argv[1]) == "--quick";
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   int sms = prop.multiProcessorCount;
   int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
@@ -121,6 +123,13 @@ int main() {
   const int threads = 256, blocks = sms * 8;
   double total_threads = (double)threads * blocks;
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_rate_khz\": %d,\n", prop.name, sms, clk_khz);
+  if (quick) {  // only the carry-chained IMAD.WIDE kernel: the live roofline denominator for bench.py
+    float ms = time_kernel([&] { k_imad_wide_x<<<blocks, threads>>>(out, 7); });
+    double ops = total_threads * (ITERS / 2) * 8;
+    printf(" \"imad_wide_x_chain\": {\"ms\": %.4f, \"ops_per_s\": %.4e, \"ops_per_clk_per_sm_at_max_clock\": %.2f}}\n", ms,
+           ops / (ms * 1e-3), ops / (ms * 1e-3) / sms / (clk_khz * 1e3));
+    return 0;
+  }
   struct { const char* name; float ms; double ops; } r[6];
   r[0] = {"imad_lo", time_kernel([&] { k_imad_lo<<<blocks, threads>>>(out, 3, 5); }), total_threads * ITERS * CH};
   r[1] = {"imad_hi", time_kernel([&] { k_imad_hi<<<blocks, threads>>>(out, 3, 5); }), total_threads * ITERS * CH};
