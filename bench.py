@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--log2-batch", type=int, default=20)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairings in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--light", action="store_true", help="kernel sweep mode: skip e2e, cpu_baseline and the live IMAD peak")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -215,6 +216,16 @@ def main():
 
     # ---- end to end through the host-buffer API --------------------------------------------------
     hP_np, hQ_np = hP.numpy(), hQ.numpy()
+    if args.light:
+        sampler.stop_flag = True
+        if rank == 0:
+            idx = np.array([0, 1, n // 2, n - 1])
+            from oracle import port
+            ref = port.pair_batch(P[idx].reshape(-1), Q[idx].reshape(-1), len(idx), 4).reshape(len(idx), 384)
+            ok = bool((dO.cpu().numpy()[idx] == ref).all())
+            print(json.dumps({"variant": os.environ.get("BN254_VARIANT", ""), "value": value, "ms_per_step": ms_max / args.steps,
+                              "log2_batch": args.log2_batch, "parity_sample_ok": ok, "clocks": sampler.summary()}))
+        return
     out_host = eng.pair_batch(hP_np[:4096], hQ_np[:4096])  # warm the staging path
     barrier()
     t0 = time.perf_counter()

@@ -7,7 +7,24 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libbn254_b200.so")
+# Default flags = the measured best of the profiles/r1 sweep: out-of-line add-type leaves and Montgomery
+# product (instruction footprint 380 KB -> 100 KB) and 3 CTAs/SM (168 registers): 1.30M -> 2.03M pairings/s.
+DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"]
+VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
+    "": DEFAULT,
+    "inline_255": [],
+    "b3": ["-DBN254_MIN_BLOCKS=3"],
+    "b4": ["-DBN254_MIN_BLOCKS=4"],
+    "ool": ["-DBN254_OOL_ADDS"],
+    "ool_b3": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=3"],
+    "ool_b4": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=4"],
+    "oolm": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL"],
+    "oolm_b3": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
+    "oolm_b4": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4"],
+    "oolm_b6": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=6"],
+}
+VARIANT = os.environ.get("BN254_VARIANT", "")
+LIB = os.path.join(HERE, "lib", "libbn254_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
@@ -31,7 +48,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + VARIANTS[VARIANT] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")]
     subprocess.check_call(cmd)
     return LIB
 

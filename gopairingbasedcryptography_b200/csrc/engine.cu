@@ -20,6 +20,9 @@ using namespace bn254;
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef BN254_MIN_BLOCKS
+#define BN254_MIN_BLOCKS 1
+#endif
 constexpr int kPairChunk = 4;  // pairs per shared-squaring pass inside one thread
 
 template <typename T>
@@ -52,7 +55,7 @@ __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t fir
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_pair(const void* P, const void* Q, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P, const void* Q, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   G1Aff p; G2Aff q; G2Proj T;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(kBlock) k_pair(const void* P, const void* Q, s
 }
 // mode 0: Miller product only; 1: + final exponentiation; 2: pairing check (writes one byte)
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_multi_pair(const void* P, const void* Q, size_t n, int k, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const void* P, const void* Q, size_t n, int k, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kBlock) k_multi_pair(const void* P, const void
   if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
   else store_struct(out, i, f);
 }
-__global__ void __launch_bounds__(kBlock) k_final_exp(const void* in, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const void* in, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f; load_struct(f, in, i);
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kBlock) k_final_exp(const void* in, size_t n, 
   store_struct(out, i, f);
 }
 template <typename J, typename A>
-__global__ void __launch_bounds__(kBlock) k_scalar_mul(const void* base, size_t base_stride, const void* scalars, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul(const void* base, size_t base_stride, const void* scalars, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   A b; load_struct(b, base, i * base_stride);
@@ -94,14 +97,14 @@ __global__ void __launch_bounds__(kBlock) k_scalar_mul(const void* base, size_t 
   store_struct(out, i, r);
 }
 template <typename J, typename A>
-__global__ void __launch_bounds__(kBlock) k_aff_add(const void* a, const void* b, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_aff_add(const void* a, const void* b, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   A x, y, r; load_struct(x, a, i); load_struct(y, b, i);
   aff_add<J, A>(r, x, y);
   store_struct(out, i, r);
 }
-__global__ void __launch_bounds__(kBlock) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 b; load_struct(b, x, i * x_stride);
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kBlock) k_gt_exp(const void* x, size_t x_strid
 }
 // mode 0: a*b ; mode 1: a/b
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 x, y; load_struct(x, a, i); load_struct(y, b, i);
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kBlock) k_gt_mul(const void* a, const void* b,
   fp12_mul(x, x, y);
   store_struct(out, i, x);
 }
-__global__ void __launch_bounds__(kBlock) k_fp_mul(const void* a, const void* b, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fp_mul(const void* a, const void* b, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp x, y; load_struct(x, a, i); load_struct(y, b, i);

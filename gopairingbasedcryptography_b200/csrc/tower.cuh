@@ -15,20 +15,35 @@ namespace bn254 {
 struct Fp6 { Fp2 b0, b1, b2; };
 struct Fp12 { Fp6 c0, c1; };
 
+// Add-type Fp2 leaves: inline by default; -DBN254_OOL_ADDS makes them out-of-line calls, trading
+// call overhead for a much smaller instruction footprint (ncu: k_pair v1 stalls on no_instruction).
+#ifdef BN254_OOL_ADDS
+#define BN_LEAF BN_NOINLINE
+#else
+#define BN_LEAF BN_HD
+#endif
+// -DBN254_OOL_FPMUL: the Montgomery product itself becomes ONE out-of-line body (operands and result
+// passed by value in registers), so fp2_mul / fp2_sqr / fp2_mul_fp shrink to a few calls.
+#ifdef BN254_OOL_FPMUL
+BN_NOINLINE Fp fp_mul_call(Fp a, Fp b) { return fp_mul(a, b); }
+#define FP_MUL(a, b) fp_mul_call(a, b)
+#else
+#define FP_MUL(a, b) fp_mul(a, b)
+#endif
 // ------------------------------------------------------------------------------------------ Fp2
 BN_HD Fp2 fp2_zero() { Fp2 z; z.a0 = fp_zero(); z.a1 = fp_zero(); return z; }
 BN_HD Fp2 fp2_one() { Fp2 z; z.a0 = fp_one(); z.a1 = fp_zero(); return z; }
 BN_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.a0) && fp_is_zero(a.a1); }
 BN_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.a0, b.a0) && fp_eq(a.a1, b.a1); }
-BN_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_add(a.a0, b.a0); z.a1 = fp_add(a.a1, b.a1); return z; }
-BN_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sub(a.a0, b.a0); z.a1 = fp_sub(a.a1, b.a1); return z; }
-BN_HD Fp2 fp2_dbl(const Fp2& a) { Fp2 z; z.a0 = fp_dbl(a.a0); z.a1 = fp_dbl(a.a1); return z; }
-BN_HD Fp2 fp2_neg(const Fp2& a) { Fp2 z; z.a0 = fp_neg(a.a0); z.a1 = fp_neg(a.a1); return z; }
-BN_HD Fp2 fp2_conj(const Fp2& a) { Fp2 z; z.a0 = a.a0; z.a1 = fp_neg(a.a1); return z; }
-BN_HD Fp2 fp2_half(const Fp2& a) { Fp2 z; z.a0 = fp_half(a.a0); z.a1 = fp_half(a.a1); return z; }
-BN_HD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = fp_mul(a.a0, k); z.a1 = fp_mul(a.a1, k); return z; }
+BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_add(a.a0, b.a0); z.a1 = fp_add(a.a1, b.a1); return z; }
+BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sub(a.a0, b.a0); z.a1 = fp_sub(a.a1, b.a1); return z; }
+BN_LEAF Fp2 fp2_dbl(const Fp2& a) { Fp2 z; z.a0 = fp_dbl(a.a0); z.a1 = fp_dbl(a.a1); return z; }
+BN_LEAF Fp2 fp2_neg(const Fp2& a) { Fp2 z; z.a0 = fp_neg(a.a0); z.a1 = fp_neg(a.a1); return z; }
+BN_LEAF Fp2 fp2_conj(const Fp2& a) { Fp2 z; z.a0 = a.a0; z.a1 = fp_neg(a.a1); return z; }
+BN_LEAF Fp2 fp2_half(const Fp2& a) { Fp2 z; z.a0 = fp_half(a.a0); z.a1 = fp_half(a.a1); return z; }
+BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = FP_MUL(a.a0, k); z.a1 = FP_MUL(a.a1, k); return z; }
 // (9+u)(a0 + a1 u) = (9a0 - a1) + (a0 + 9a1) u
-BN_HD Fp2 fp2_mul_xi(const Fp2& a) {
+BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) {
   Fp e0 = fp_dbl(fp_dbl(fp_dbl(a.a0))), e1 = fp_dbl(fp_dbl(fp_dbl(a.a1)));
   Fp2 z;
   z.a0 = fp_sub(fp_add(e0, a.a0), a.a1);
@@ -37,9 +52,9 @@ BN_HD Fp2 fp2_mul_xi(const Fp2& a) {
 }
 // Karatsuba: 3 Fp products
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
-  Fp t0 = fp_mul(a.a0, b.a0);
-  Fp t1 = fp_mul(a.a1, b.a1);
-  Fp m = fp_mul(fp_add(a.a0, a.a1), fp_add(b.a0, b.a1));
+  Fp t0 = FP_MUL(a.a0, b.a0);
+  Fp t1 = FP_MUL(a.a1, b.a1);
+  Fp m = FP_MUL(fp_add(a.a0, a.a1), fp_add(b.a0, b.a1));
   Fp2 z;
   z.a0 = fp_sub(t0, t1);
   z.a1 = fp_sub(fp_sub(m, t0), t1);
@@ -47,9 +62,9 @@ BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
 }
 // complex squaring: 2 Fp products
 BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
-  Fp m = fp_mul(a.a0, a.a1);
+  Fp m = FP_MUL(a.a0, a.a1);
   Fp2 z;
-  z.a0 = fp_mul(fp_add(a.a0, a.a1), fp_sub(a.a0, a.a1));
+  z.a0 = FP_MUL(fp_add(a.a0, a.a1), fp_sub(a.a0, a.a1));
   z.a1 = fp_dbl(m);
   return z;
 }
