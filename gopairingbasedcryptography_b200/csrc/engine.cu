@@ -10,6 +10,7 @@
 
 #include "../../include/bn254_b200.h"
 #include "curve.cuh"
+#include "vm.cuh"
 
 using namespace bn254;
 
@@ -134,6 +135,124 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fp_mul(const void*
   store_struct(out, i, x);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Lane-group ("tower VM") kernels: K lanes per pairing, state in shared memory.  See vm.cuh.
+// ---------------------------------------------------------------------------------------------
+#ifndef BN254_VM_K
+#define BN254_VM_K 3
+#endif
+#ifndef BN254_VM_WARPS
+#define BN254_VM_WARPS 4
+#endif
+constexpr int kVmK = BN254_VM_K;
+constexpr int kVmWarps = BN254_VM_WARPS;
+constexpr int kVmGroups = 32 / kVmK;            // pairings per warp
+constexpr int kVmNP = kVmGroups * kVmWarps;     // pairings per CTA
+constexpr int kVmStride = kVmNP | 1;            // odd stride: sub-lanes of a group hit different bank quads
+constexpr int kVmColdSlots = 64;                // cold slots reserved per pairing in the global scratch
+
+#define VM_CAT_(a, b, c) a##b##c
+#define VM_CAT(a, b, c) VM_CAT_(a, b, c)
+#define VM_SYM(name, suffix) VM_CAT(vm::name##_K, BN254_VM_K, suffix)
+#if BN254_VM_K == 1
+#define VM_INC_PAIR "vm_prog_pair_k1.inc"
+#define VM_INC_MILLER "vm_prog_miller_k1.inc"
+#define VM_INC_FINALEXP "vm_prog_finalexp_k1.inc"
+#elif BN254_VM_K == 2
+#define VM_INC_PAIR "vm_prog_pair_k2.inc"
+#define VM_INC_MILLER "vm_prog_miller_k2.inc"
+#define VM_INC_FINALEXP "vm_prog_finalexp_k2.inc"
+#elif BN254_VM_K == 3
+#define VM_INC_PAIR "vm_prog_pair_k3.inc"
+#define VM_INC_MILLER "vm_prog_miller_k3.inc"
+#define VM_INC_FINALEXP "vm_prog_finalexp_k3.inc"
+#elif BN254_VM_K == 4
+#define VM_INC_PAIR "vm_prog_pair_k4.inc"
+#define VM_INC_MILLER "vm_prog_miller_k4.inc"
+#define VM_INC_FINALEXP "vm_prog_finalexp_k4.inc"
+#elif BN254_VM_K == 6
+#define VM_INC_PAIR "vm_prog_pair_k6.inc"
+#define VM_INC_MILLER "vm_prog_miller_k6.inc"
+#define VM_INC_FINALEXP "vm_prog_finalexp_k6.inc"
+#else
+#error "BN254_VM_K must be 1, 2, 3, 4 or 6"
+#endif
+__device__ const uint64_t kProgPair[] = {
+#include VM_INC_PAIR
+};
+__device__ const uint64_t kProgMiller[] = {
+#include VM_INC_MILLER
+};
+__device__ const uint64_t kProgFinalExp[] = {
+#include VM_INC_FINALEXP
+};
+
+struct VmProgPair { static constexpr int rounds = VM_SYM(PAIR, _ROUNDS), nslots = VM_SYM(PAIR, _NSLOTS), nin = 3;
+  __device__ static const uint64_t* prog() { return kProgPair; }
+  __device__ static int in(int i) { return VM_SYM(PAIR, _IN)[i]; } __device__ static int out(int i) { return VM_SYM(PAIR, _OUT)[i]; } };
+struct VmProgMiller { static constexpr int rounds = VM_SYM(MILLER, _ROUNDS), nslots = VM_SYM(MILLER, _NSLOTS), nin = 3;
+  __device__ static const uint64_t* prog() { return kProgMiller; }
+  __device__ static int in(int i) { return VM_SYM(MILLER, _IN)[i]; } __device__ static int out(int i) { return VM_SYM(MILLER, _OUT)[i]; } };
+struct VmProgFinalExp { static constexpr int rounds = VM_SYM(FINALEXP, _ROUNDS), nslots = VM_SYM(FINALEXP, _NSLOTS), nin = 6;
+  __device__ static const uint64_t* prog() { return kProgFinalExp; }
+  __device__ static int in(int i) { return VM_SYM(FINALEXP, _IN)[i]; } __device__ static int out(int i) { return VM_SYM(FINALEXP, _OUT)[i]; } };
+
+template <typename PROG> constexpr size_t vm_smem_bytes() { return (size_t)PROG::nslots * 4 * kVmStride * sizeof(uint4); }
+
+// Persistent CTAs: each warp owns kVmGroups pairings at a time; warps never synchronise with each other.
+// PROG::nin == 3: inputs are (P, Q.x, Q.y) from the G1/G2 arrays; PROG::nin == 6: the six Fp2 of a GT.
+template <typename PROG>
+__global__ void __launch_bounds__(32 * kVmWarps) k_vm(const void* in0, const void* in1, size_t n, void* out, uint4* cold) {
+  extern __shared__ uint4 vm_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / kVmK, j = lane % kVmK;
+  const bool lane_ok = g < kVmGroups;
+  const int pid = warp * kVmGroups + (lane_ok ? g : 0);
+  vm::SlotFile f;
+  f.hot = vm_smem; f.nslots = PROG::nslots; f.hot_stride = kVmStride; f.pid = pid;
+  f.cold = cold; f.cold_stride = gridDim.x * kVmNP; f.gpid = blockIdx.x * kVmNP + pid;
+  const unsigned gmask = lane_ok ? (((1u << kVmK) - 1u) << (g * kVmK)) : 0u;
+  for (size_t base = (size_t)blockIdx.x * kVmNP; base < n; base += (size_t)gridDim.x * kVmNP) {
+    const size_t idx = base + pid;
+    const bool active = lane_ok && idx < n;
+    // ---- prologue: operands -> slots; pairs containing the point at infinity are flagged ----
+    unsigned nzP = 0, nzQ = 0;
+    for (int i = 0; i < PROG::nin; i++) {
+      bool mine = active && (i % kVmK) == j;
+      uint32_t nz = 0;
+      if (mine) {
+        const char* src;
+        if (PROG::nin == 3) src = (i == 0) ? static_cast<const char*>(in0) + idx * 64 : static_cast<const char*>(in1) + idx * 128 + (i - 1) * 64;
+        else src = static_cast<const char*>(in0) + idx * 384 + i * 64;
+        Fp2 v;
+        uint4* d = reinterpret_cast<uint4*>(&v);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { d[c] = __ldg(reinterpret_cast<const uint4*>(src) + c); nz |= d[c].x | d[c].y | d[c].z | d[c].w; }
+        vm::st_slot(f, PROG::in(i), v);
+      }
+      unsigned b = __ballot_sync(0xffffffffu, nz != 0);
+      if (i == 0) nzP = b & gmask; else nzQ |= b & gmask;
+    }
+    const bool skip = (PROG::nin == 3) && (nzP == 0 || nzQ == 0);
+    __syncwarp();
+    vm::run<kVmK>(f, PROG::prog(), PROG::rounds, j, active);
+    // ---- epilogue ----
+    if (active) {
+      for (int i = j; i < 6; i += kVmK) {
+        Fp2 v;
+        if (skip) { v = fp2_zero(); if (i == 0) v.a0 = fp_one(); }
+        else v = vm::ld_slot(f, PROG::out(i));
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(out) + idx * 384 + i * 64);
+        const uint4* sv = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+        for (int c = 0; c < 4; c++) dst[c] = sv[c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 inline unsigned grid_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -145,6 +264,7 @@ struct Slot {
   cudaStream_t stream = nullptr;
   char* h = nullptr;  // pinned staging
   char* d = nullptr;  // device staging
+  uint4* vm_cold = nullptr;  // cold slot scratch of the lane-group kernels launched on this stream
   // pending output copy-back
   void* user_out = nullptr;
   size_t out_off = 0, out_bytes = 0;
@@ -158,6 +278,12 @@ struct bn254_ctx {
   Slot slot[2];
   size_t slot_bytes = 0;
   uint64_t launches = 0;
+  // lane-group (tower VM) kernels
+  bool use_vm = false;         // BN254_IMPL=vm selects the lane-group (tower VM) kernels
+  int sms = 0;
+  int vm_blocks_per_sm[3] = {0, 0, 0};  // pair, miller, finalexp
+  uint4* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
+  cudaEvent_t vm_dev_done = nullptr;
 };
 
 namespace {
@@ -214,7 +340,7 @@ int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_ite
     }
     size_t oo = off, lo = out_item * c;
     CU(cudaMemcpyAsync(s.d, s.h, oo, cudaMemcpyHostToDevice, s.stream));
-    launch(s.d + o0, s.d + o1, c, s.d + oo, s.stream);
+    launch(s.d + o0, s.d + o1, c, s.d + oo, s.stream, s.vm_cold);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h + oo, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream));
@@ -235,6 +361,48 @@ int run_dev(bn254_ctx* ctx, size_t n, L launch) {
   launch();
   ctx->launches++;
   CU(cudaGetLastError());
+  return BN254_OK;
+}
+
+
+template <typename PROG> constexpr int vm_prog_index();
+template <> constexpr int vm_prog_index<VmProgPair>() { return 0; }
+template <> constexpr int vm_prog_index<VmProgMiller>() { return 1; }
+template <> constexpr int vm_prog_index<VmProgFinalExp>() { return 2; }
+
+inline size_t vm_cold_bytes(const bn254_ctx* ctx) {
+  int maxb = std::max({ctx->vm_blocks_per_sm[0], ctx->vm_blocks_per_sm[1], ctx->vm_blocks_per_sm[2]});
+  return (size_t)kVmColdSlots * 4 * sizeof(uint4) * (size_t)ctx->sms * maxb * kVmNP;
+}
+template <typename PROG>
+void launch_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out, uint4* cold, cudaStream_t s) {
+  size_t want = (n + kVmNP - 1) / kVmNP;
+  unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sms * ctx->vm_blocks_per_sm[vm_prog_index<PROG>()]);
+  k_vm<PROG><<<grid, 32 * kVmWarps, vm_smem_bytes<PROG>(), s>>>(a, b, n, out, cold);
+}
+template <typename PROG>
+cudaError_t vm_prepare(bn254_ctx* ctx) {
+  cudaError_t e = cudaFuncSetAttribute(k_vm<PROG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<PROG>());
+  if (e != cudaSuccess) return e;
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_vm<PROG>, 32 * kVmWarps, vm_smem_bytes<PROG>());
+  if (e != cudaSuccess) return e;
+  if (nb < 1) return cudaErrorLaunchOutOfResources;
+  ctx->vm_blocks_per_sm[vm_prog_index<PROG>()] = nb;
+  return cudaSuccess;
+}
+// device-pointer launches of one context share vm_cold_dev: order them across streams with an event
+template <typename PROG>
+int run_dev_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out, cudaStream_t s) {
+  if (!ctx) return BN254_ERR_BAD_ARG;
+  if (n == 0) return BN254_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamWaitEvent(s, ctx->vm_dev_done, 0));
+  launch_vm<PROG>(ctx, a, b, n, out, ctx->vm_cold_dev, s);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->vm_dev_done, s));
   return BN254_OK;
 }
 
@@ -270,6 +438,15 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
       return BN254_ERR_OOM;
     }
   }
+  const char* impl = getenv("BN254_IMPL");
+  ctx->use_vm = impl && std::string(impl) == "vm";  // default: one-thread-per-pairing kernels (faster so far)
+  ctx->sms = prop.multiProcessorCount;
+  if (vm_prepare<VmProgPair>(ctx) != cudaSuccess || vm_prepare<VmProgMiller>(ctx) != cudaSuccess ||
+      vm_prepare<VmProgFinalExp>(ctx) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
+  size_t cb = vm_cold_bytes(ctx);
+  if (cudaMalloc((void**)&ctx->vm_cold_dev, cb) != cudaSuccess || cudaMalloc((void**)&ctx->slot[0].vm_cold, cb) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->slot[1].vm_cold, cb) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->vm_dev_done, cudaEventDisableTiming) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_OOM; }
   *out = ctx;
   return BN254_OK;
 }
@@ -282,7 +459,10 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
     if (s.h) cudaFreeHost(s.h);
     if (s.d) cudaFree(s.d);
+    if (s.vm_cold) cudaFree(s.vm_cold);
   }
+  if (ctx->vm_cold_dev) cudaFree(ctx->vm_cold_dev);
+  if (ctx->vm_dev_done) cudaEventDestroy(ctx->vm_dev_done);
   delete ctx;
 }
 
@@ -309,23 +489,31 @@ void bn254_generators(void* g1, void* g2) {
 
 // ---- pairings -------------------------------------------------------------------------------
 int bn254_pair_batch_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, void* d_out, void* stream) {
+  if (ctx && ctx->use_vm) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);
   return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
 }
 int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, void* out) {
   return run_host(ctx, {P, BN254_G1_BYTES, false}, {Q, BN254_G2_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_pair<<<grid_for(c), kBlock, 0, s>>>(a, b, c, o); });
+                  [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {
+                    if (ctx->use_vm) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);
+                    else k_pair<<<grid_for(c), kBlock, 0, s>>>(a, b, c, o);
+                  });
 }
 #define MULTI_PAIR_ENTRY(name, MODE, OUT_BYTES, OUT_T)                                                                     \
   int name##_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, size_t k, OUT_T* d_out, void* stream) {         \
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
+    if (ctx && ctx->use_vm && k == 1 && MODE == 0) return run_dev_vm<VmProgMiller>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream); \
+    if (ctx && ctx->use_vm && k == 1 && MODE == 1) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);   \
     return run_dev(ctx, n, [&] { k_multi_pair<MODE><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, (int)k, d_out); }); \
   }                                                                                                                        \
   int name(bn254_ctx* ctx, const void* P, const void* Q, size_t n, size_t k, OUT_T* out) {                                 \
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
     int kk = (int)k;                                                                                                       \
     return run_host(ctx, {P, BN254_G1_BYTES * k, false}, {Q, BN254_G2_BYTES * k, false}, out, OUT_BYTES, n,                \
-                    [kk](const void* a, const void* b, size_t c, void* o, cudaStream_t s) {                                \
-                      k_multi_pair<MODE><<<grid_for(c), kBlock, 0, s>>>(a, b, c, kk, o);                                   \
+                    [kk, ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {                  \
+                      if (ctx->use_vm && kk == 1 && MODE == 0) launch_vm<VmProgMiller>(ctx, a, b, c, o, cold, s);          \
+                      else if (ctx->use_vm && kk == 1 && MODE == 1) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);       \
+                      else k_multi_pair<MODE><<<grid_for(c), kBlock, 0, s>>>(a, b, c, kk, o);                              \
                     });                                                                                                    \
   }
 MULTI_PAIR_ENTRY(bn254_miller_loop_batch, 0, BN254_GT_BYTES, void)
@@ -333,11 +521,15 @@ MULTI_PAIR_ENTRY(bn254_multi_pair_batch, 1, BN254_GT_BYTES, void)
 MULTI_PAIR_ENTRY(bn254_pairing_check_batch, 2, 1, uint8_t)
 
 int bn254_final_exp_batch_dev(bn254_ctx* ctx, const void* d_in, size_t n, void* d_out, void* stream) {
+  if (ctx && ctx->use_vm) return run_dev_vm<VmProgFinalExp>(ctx, d_in, nullptr, n, d_out, (cudaStream_t)stream);
   return run_dev(ctx, n, [&] { k_final_exp<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_in, n, d_out); });
 }
 int bn254_final_exp_batch(bn254_ctx* ctx, const void* in, size_t n, void* out) {
   return run_host(ctx, {in, BN254_GT_BYTES, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void*, size_t c, void* o, cudaStream_t s) { k_final_exp<<<grid_for(c), kBlock, 0, s>>>(a, c, o); });
+                  [ctx](const void* a, const void*, size_t c, void* o, cudaStream_t s, uint4* cold) {
+                    if (ctx->use_vm) launch_vm<VmProgFinalExp>(ctx, a, nullptr, c, o, cold, s);
+                    else k_final_exp<<<grid_for(c), kBlock, 0, s>>>(a, c, o);
+                  });
 }
 
 // ---- scalar multiplication --------------------------------------------------------------------
@@ -350,7 +542,7 @@ int bn254_g2_mul_batch_dev(bn254_ctx* ctx, const void* d_base, size_t stride, co
 #define MUL_ENTRY(name, J, A, BYTES, BCAST)                                                                           \
   int name(bn254_ctx* ctx, const void* base, const void* scalars, size_t n, void* out) {                              \
     return run_host(ctx, {base, BYTES, BCAST}, {scalars, BN254_SCALAR_BYTES, false}, out, BYTES, n,                   \
-                    [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) {                             \
+                    [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) {                             \
                       k_scalar_mul<J, A><<<grid_for(c), kBlock, 0, s>>>(a, BCAST ? 0 : 1, b, c, o);                   \
                     });                                                                                               \
   }
@@ -361,11 +553,11 @@ MUL_ENTRY(bn254_g2_mul_base_batch, G2Jac, G2Aff, BN254_G2_BYTES, true)
 
 int bn254_g1_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_G1_BYTES, false}, {b, BN254_G1_BYTES, false}, out, BN254_G1_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_aff_add<G1Jac, G1Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_aff_add<G1Jac, G1Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 int bn254_g2_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_G2_BYTES, false}, {b, BN254_G2_BYTES, false}, out, BN254_G2_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_aff_add<G2Jac, G2Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_aff_add<G2Jac, G2Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 
 // ---- GT ---------------------------------------------------------------------------------------
@@ -374,23 +566,23 @@ int bn254_gt_exp_batch_dev(bn254_ctx* ctx, const void* d_x, size_t stride, const
 }
 int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
 }
 int bn254_gt_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_gt_mul<0><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<0><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 int bn254_gt_div_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_gt_mul<1><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<1><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 int bn254_fp_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, 32, false}, {b, 32, false}, out, 32, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s) { k_fp_mul<<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_fp_mul<<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 
 }  // extern "C"

@@ -21,6 +21,7 @@
 #define BN_HD static inline
 #define BN_D static inline
 #define BN_NOINLINE static __attribute__((noinline))
+struct uint4 { uint32_t x, y, z, w; };  // host-emulation stand-in for the CUDA vector type
 #endif
 
 #if defined(__CUDACC__)

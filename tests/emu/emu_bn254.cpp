@@ -44,3 +44,52 @@ void emu_gt_sqr(const void* a, size_t n, int cyclo, void* out) {
   for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i); if (cyclo) fp12_cyclo_sqr(x, x); else fp12_sqr(x, x); st(out, i, x); } }
 void emu_gt_frob(const void* a, size_t n, int k, void* out) { for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i); fp12_frob(x, x, k); st(out, i, x); } }
 }
+
+// ---- tower-VM programs executed on the host with lock-step round semantics (all lanes of a group load
+// their operands before any lane stores), exactly what the warp does between two __syncwarp().
+#include "../../gopairingbasedcryptography_b200/csrc/vm.cuh"
+namespace {
+const uint64_t kPair3[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/vm_prog_pair_k3.inc"
+};
+const uint64_t kMiller3[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/vm_prog_miller_k3.inc"
+};
+const uint64_t kFinalExp3[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/vm_prog_finalexp_k3.inc"
+};
+const uint64_t kPair1[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/vm_prog_pair_k1.inc"
+};
+void run_rounds(Fp2* slots, const uint64_t* prog, int rounds, int K) {
+  vm::SlotFile f; f.hot = reinterpret_cast<uint4*>(slots); f.cold = nullptr; f.nslots = 256; f.hot_stride = 0; f.pid = 0; f.cold_stride = 0; f.gpid = 0;
+  for (int r = 0; r < rounds; r++) {
+    int dst[8]; Fp2 val[8]; bool st[8];
+    for (int j = 0; j < K; j++) st[j] = vm::exec_op(f, prog[(size_t)r * K + j], dst[j], val[j]);
+    for (int j = 0; j < K; j++) if (st[j]) slots[dst[j]] = val[j];
+  }
+}
+}
+extern "C" {
+// mode 0: pair (K=3), 1: miller only, 2: final exp only, 3: pair with the K=1 program
+void emu_vm(const void* in0, const void* in1, size_t n, int mode, void* out) {
+  using namespace vm;
+  for (size_t i = 0; i < n; i++) {
+    Fp2 slots[256];
+    const int* IN; const int* OUT; const uint64_t* prog; int rounds, K = 3, nin = 3;
+    if (mode == 0) { IN = PAIR_K3_IN; OUT = PAIR_K3_OUT; prog = kPair3; rounds = PAIR_K3_ROUNDS; }
+    else if (mode == 1) { IN = MILLER_K3_IN; OUT = MILLER_K3_OUT; prog = kMiller3; rounds = MILLER_K3_ROUNDS; }
+    else if (mode == 2) { IN = FINALEXP_K3_IN; OUT = FINALEXP_K3_OUT; prog = kFinalExp3; rounds = FINALEXP_K3_ROUNDS; nin = 6; }
+    else { IN = PAIR_K1_IN; OUT = PAIR_K1_OUT; prog = kPair1; rounds = PAIR_K1_ROUNDS; K = 1; }
+    if (nin == 3) {
+      memcpy(&slots[IN[0]], (const char*)in0 + i * 64, 64);
+      memcpy(&slots[IN[1]], (const char*)in1 + i * 128, 64);
+      memcpy(&slots[IN[2]], (const char*)in1 + i * 128 + 64, 64);
+    } else {
+      for (int k = 0; k < 6; k++) memcpy(&slots[IN[k]], (const char*)in0 + i * 384 + k * 64, 64);
+    }
+    run_rounds(slots, prog, rounds, K);
+    for (int k = 0; k < 6; k++) memcpy((char*)out + i * 384 + k * 64, &slots[OUT[k]], 64);
+  }
+}
+}

@@ -21,9 +21,10 @@ CSRC = os.path.join(HERE, "..", "gopairingbasedcryptography_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL",
+                               "-o", SO, SRC])
     return ctypes.CDLL(SO)
 
 
@@ -132,3 +133,43 @@ def test_groups_and_gt(emu):
     assert (out == port.gt_div_batch(gt, gt2, m)).all()
     emu.emu_gt_sqr(vp(gt), sz(m), 1, vp(out))
     assert (out == port.gt_sqr_batch(gt, m)).all()
+
+
+def test_tower_vm_programs_on_host(emu):
+    """The lane-group kernels' generated micro-op programs (vmgen.py), run by the C++ interpreter (vm.cuh)
+    with lock-step round semantics: pair (K=3 and K=1), miller-only and final-exp-only programs."""
+    n = 3
+    P, Q, _, _ = common.points(n, seed=123)
+    ref = port.pair_batch(P, Q, n)
+    for mode in (0, 3):
+        out = np.zeros(384 * n, np.uint8)
+        emu.emu_vm(vp(P), vp(Q), sz(n), mode, vp(out))
+        assert (out == ref).all()
+    ml = np.zeros(384 * n, np.uint8)
+    emu.emu_vm(vp(P), vp(Q), sz(n), 1, vp(ml))
+    fe = np.zeros(384 * n, np.uint8)
+    emu.emu_vm(vp(ml), None, sz(n), 2, vp(fe))
+    assert (fe == ref).all()
+    # final exponentiation of an arbitrary (non-Miller) Fp12 input
+    rng = o.SplitMix64(77)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(12)), dtype=np.uint8).copy()
+    emu.emu_vm(vp(x), None, sz(1), 2, vp(fe))
+    assert (fe[:384] == port.final_exp_batch(x, 1)).all()
+
+
+def test_vmgen_python_evaluator_matches_oracle():
+    """The generator's own integer evaluator on the scheduled K=3 and K=6 programs (independent of C++)."""
+    import sys
+
+    sys.path.insert(0, CSRC)
+    import vmgen as g
+
+    rng = o.SplitMix64(5)
+    Pt, Qt = o.g1_mul(o.G1_GEN, rng.scalar()), o.g2_mul(o.G2_GEN, rng.scalar())
+    for K in (3, 6):
+        words, meta = g.build_pair_program(K, window=g.WINDOW[K])
+        ins = meta["in_slots"]
+        slots = g.evaluate(words, K, 256, {ins[0]: Pt, ins[1]: Qt[0], ins[2]: Qt[1]})
+        out = [slots[s] for s in meta["out_slots"]]
+        assert ((out[0], out[1], out[2]), (out[3], out[4], out[5])) == o.pair([Pt], [Qt])
+        assert meta["nslots"] <= 48 and meta["ncold"] <= 64
