@@ -219,6 +219,129 @@ BN_HD Fp fp_mul_v(const Fp& a, const Fp& b) {
 BN_HD Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_v<BN254_MUL_VARIANT>(a, b); }
 BN_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 
+// ---- lazy reduction building blocks (Aranha et al. style): a wide 8x8 -> 16-limb product and a
+// separate Montgomery reduction, so an Fp2 product costs 3 wide products + 2 reductions (320 IMAD.WIDE)
+// instead of 3 full Montgomery products (384).
+// x[0..7] += (a0,a1,a2,a3) * b laid on the four aligned word pairs, carry out added into cw.
+BN_HD void mac4(uint32_t* x, uint32_t& cw, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if defined(__CUDACC__)
+  asm volatile(
+      "mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(cw)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+  x[0] = mad_lo_cc(a0, b, x[0]);  x[1] = madc_hi_cc(a0, b, x[1]);
+  x[2] = madc_lo_cc(a1, b, x[2]); x[3] = madc_hi_cc(a1, b, x[3]);
+  x[4] = madc_lo_cc(a2, b, x[4]); x[5] = madc_hi_cc(a2, b, x[5]);
+  x[6] = madc_lo_cc(a3, b, x[6]); x[7] = madc_hi_cc(a3, b, x[7]);
+  cw = addc(cw, 0u);
+#endif
+}
+// t[0..15] = a * b (plain integer product of the limb vectors; a, b < 2^256)
+BN_HD void fp_mul_wide(uint32_t* t, const Fp& a, const Fp& b) {
+  uint32_t E[18], O[18];  // E[k]: word position k (aligned pairs (0,1),(2,3)..); O[k]: word position k+1
+#pragma unroll
+  for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    // even multiplier word b[i]: a-even products sit on E pairs at i, a-odd products on O pairs at i
+    mac4(&E[i], E[i + 8], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+    mac4(&O[i], O[i + 8], a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+    // odd multiplier word b[i+1]: a-odd products at position i+1+j (even) -> E pairs at i+2; a-even -> O pairs at i
+    mac4(&E[i + 2], E[i + 10], a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+    mac4(&O[i], O[i + 8], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+  }
+  t[0] = E[0];
+  t[1] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) t[k] = addc_cc(E[k], O[k - 1]);
+  t[15] = addc(E[15], O[14]);
+}
+// one row of the windowed Montgomery reduction: frame shifts right by one word (ev <-> od swap roles),
+// the next input word t_in enters at frame position 7, and m*p is added.  See fp_redc.
+BN_HD void redc_row(uint32_t* ev, uint32_t* od, uint32_t t_in) {
+#if defined(__CUDACC__)
+  asm volatile(
+      "{\n\t.reg .u32 m;\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "mul.lo.u32 m, %0, %25;\n\t"
+      "madc.lo.cc.u32 %8, %18, m, %10;\n\t madc.hi.cc.u32 %9, %18, m, %11;\n\t"
+      "madc.lo.cc.u32 %10, %20, m, %12;\n\t madc.hi.cc.u32 %11, %20, m, %13;\n\t"
+      "madc.lo.cc.u32 %12, %22, m, %14;\n\t madc.hi.cc.u32 %13, %22, m, %15;\n\t"
+      "madc.lo.cc.u32 %14, %24, m, %16;\n\t madc.hi.u32 %15, %24, m, 0;\n\t"
+      "mad.lo.cc.u32 %0, %17, m, %0;\n\t madc.hi.cc.u32 %1, %17, m, %1;\n\t"
+      "madc.lo.cc.u32 %2, %19, m, %2;\n\t madc.hi.cc.u32 %3, %19, m, %3;\n\t"
+      "madc.lo.cc.u32 %4, %21, m, %4;\n\t madc.hi.cc.u32 %5, %21, m, %5;\n\t"
+      "madc.lo.cc.u32 %6, %23, m, %6;\n\t madc.hi.cc.u32 %7, %23, m, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(t_in), "r"(P0), "r"(P1), "r"(P2), "r"(P3), "r"(P4), "r"(P5), "r"(P6), "r"(P7), "r"(P_INV32));
+#else
+  ev[0] = add_cc(ev[0], od[1]);
+  uint32_t m = ev[0] * P_INV32;
+  od[0] = madc_lo_cc(P1, m, od[2]); od[1] = madc_hi_cc(P1, m, od[3]);
+  od[2] = madc_lo_cc(P3, m, od[4]); od[3] = madc_hi_cc(P3, m, od[5]);
+  od[4] = madc_lo_cc(P5, m, od[6]); od[5] = madc_hi_cc(P5, m, od[7]);
+  od[6] = madc_lo_cc(P7, m, t_in);  od[7] = madc_hi(P7, m, 0u);
+  ev[0] = mad_lo_cc(P0, m, ev[0]);  ev[1] = madc_hi_cc(P0, m, ev[1]);
+  ev[2] = madc_lo_cc(P2, m, ev[2]); ev[3] = madc_hi_cc(P2, m, ev[3]);
+  ev[4] = madc_lo_cc(P4, m, ev[4]); ev[5] = madc_hi_cc(P4, m, ev[5]);
+  ev[6] = madc_lo_cc(P6, m, ev[6]); ev[7] = madc_hi_cc(P6, m, ev[7]);
+  od[7] = addc(od[7], 0u);
+#endif
+}
+// z = t / R mod p, canonical, for a 16-limb t < p * 2^256.
+BN_HD Fp fp_redc(const uint32_t* t) {
+  uint32_t e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { e[i] = t[i]; o[i] = 0; }
+  mont_row_reduce(e, o);          // frame 0: e positions 0..7, o positions 1..8
+  redc_row(o, e, t[8]);           // frame 1
+  redc_row(e, o, t[9]);
+  redc_row(o, e, t[10]);
+  redc_row(e, o, t[11]);
+  redc_row(o, e, t[12]);
+  redc_row(e, o, t[13]);
+  redc_row(o, e, t[14]);          // frame 7: o is even-aligned with o[0] == 0
+  Fp z;
+  z.l[0] = add_cc(e[0], o[1]); z.l[1] = addc_cc(e[1], o[2]); z.l[2] = addc_cc(e[2], o[3]); z.l[3] = addc_cc(e[3], o[4]);
+  z.l[4] = addc_cc(e[4], o[5]); z.l[5] = addc_cc(e[5], o[6]); z.l[6] = addc_cc(e[6], o[7]); z.l[7] = addc(e[7], t[15]);
+  fp_reduce_once(z);
+  return z;
+}
+// 16-limb helpers
+BN_HD void wide_sub(uint32_t* z, const uint32_t* a, const uint32_t* b, uint32_t& borrow_mask) {
+  z[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 16; i++) z[i] = subc_cc(a[i], b[i]);
+  borrow_mask = subc(0u, 0u);
+}
+BN_HD uint32_t psq_limb(int i) {
+  switch (i) { case 0: return PSQ0; case 1: return PSQ1; case 2: return PSQ2; case 3: return PSQ3; case 4: return PSQ4;
+               case 5: return PSQ5; case 6: return PSQ6; case 7: return PSQ7; case 8: return PSQ8; case 9: return PSQ9;
+               case 10: return PSQ10; case 11: return PSQ11; case 12: return PSQ12; case 13: return PSQ13;
+               case 14: return PSQ14; default: return PSQ15; }
+}
+// z += p^2 & mask
+BN_HD void wide_add_psq_masked(uint32_t* z, uint32_t mask) {
+  z[0] = add_cc(z[0], PSQ0 & mask);
+#pragma unroll
+  for (int i = 1; i < 15; i++) z[i] = addc_cc(z[i], psq_limb(i) & mask);
+  z[15] = addc(z[15], PSQ15 & mask);
+}
+// a + b without reduction (a, b < p: fits 8 limbs since 2p < 2^255)
+BN_HD Fp fp_add_noreduce(const Fp& a, const Fp& b) {
+  Fp t;
+  t.l[0] = add_cc(a.l[0], b.l[0]); t.l[1] = addc_cc(a.l[1], b.l[1]); t.l[2] = addc_cc(a.l[2], b.l[2]); t.l[3] = addc_cc(a.l[3], b.l[3]);
+  t.l[4] = addc_cc(a.l[4], b.l[4]); t.l[5] = addc_cc(a.l[5], b.l[5]); t.l[6] = addc_cc(a.l[6], b.l[6]); t.l[7] = addc(a.l[7], b.l[7]);
+  return t;
+}
+
 // a^(p-2); inv(0) = 0 like gnark's Inverse.
 BN_HD Fp fp_inv(const Fp& a) {
   Fp acc = fp_one(), b = a;

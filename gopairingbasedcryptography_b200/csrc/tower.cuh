@@ -35,21 +35,31 @@ BN_HD Fp2 fp2_zero() { Fp2 z; z.a0 = fp_zero(); z.a1 = fp_zero(); return z; }
 BN_HD Fp2 fp2_one() { Fp2 z; z.a0 = fp_one(); z.a1 = fp_zero(); return z; }
 BN_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.a0) && fp_is_zero(a.a1); }
 BN_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.a0, b.a0) && fp_eq(a.a1, b.a1); }
-BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_add(a.a0, b.a0); z.a1 = fp_add(a.a1, b.a1); return z; }
-BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sub(a.a0, b.a0); z.a1 = fp_sub(a.a1, b.a1); return z; }
-BN_LEAF Fp2 fp2_dbl(const Fp2& a) { Fp2 z; z.a0 = fp_dbl(a.a0); z.a1 = fp_dbl(a.a1); return z; }
-BN_LEAF Fp2 fp2_neg(const Fp2& a) { Fp2 z; z.a0 = fp_neg(a.a0); z.a1 = fp_neg(a.a1); return z; }
-BN_LEAF Fp2 fp2_conj(const Fp2& a) { Fp2 z; z.a0 = a.a0; z.a1 = fp_neg(a.a1); return z; }
-BN_LEAF Fp2 fp2_half(const Fp2& a) { Fp2 z; z.a0 = fp_half(a.a0); z.a1 = fp_half(a.a1); return z; }
-BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = FP_MUL(a.a0, k); z.a1 = FP_MUL(a.a1, k); return z; }
+// _i = always-inline bodies (used by the tower VM, where each op exists once); the unsuffixed names are
+// the BN_LEAF versions used by the one-thread-per-pairing routines.
+BN_HD Fp2 fp2_add_i(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_add(a.a0, b.a0); z.a1 = fp_add(a.a1, b.a1); return z; }
+BN_HD Fp2 fp2_sub_i(const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sub(a.a0, b.a0); z.a1 = fp_sub(a.a1, b.a1); return z; }
+BN_HD Fp2 fp2_dbl_i(const Fp2& a) { Fp2 z; z.a0 = fp_dbl(a.a0); z.a1 = fp_dbl(a.a1); return z; }
+BN_HD Fp2 fp2_neg_i(const Fp2& a) { Fp2 z; z.a0 = fp_neg(a.a0); z.a1 = fp_neg(a.a1); return z; }
+BN_HD Fp2 fp2_conj_i(const Fp2& a) { Fp2 z; z.a0 = a.a0; z.a1 = fp_neg(a.a1); return z; }
+BN_HD Fp2 fp2_half_i(const Fp2& a) { Fp2 z; z.a0 = fp_half(a.a0); z.a1 = fp_half(a.a1); return z; }
+BN_HD Fp2 fp2_mul_fp_i(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = FP_MUL(a.a0, k); z.a1 = FP_MUL(a.a1, k); return z; }
 // (9+u)(a0 + a1 u) = (9a0 - a1) + (a0 + 9a1) u
-BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) {
+BN_HD Fp2 fp2_mul_xi_i(const Fp2& a) {
   Fp e0 = fp_dbl(fp_dbl(fp_dbl(a.a0))), e1 = fp_dbl(fp_dbl(fp_dbl(a.a1)));
   Fp2 z;
   z.a0 = fp_sub(fp_add(e0, a.a0), a.a1);
   z.a1 = fp_add(fp_add(e1, a.a1), a.a0);
   return z;
 }
+BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { return fp2_add_i(a, b); }
+BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return fp2_sub_i(a, b); }
+BN_LEAF Fp2 fp2_dbl(const Fp2& a) { return fp2_dbl_i(a); }
+BN_LEAF Fp2 fp2_neg(const Fp2& a) { return fp2_neg_i(a); }
+BN_LEAF Fp2 fp2_conj(const Fp2& a) { return fp2_conj_i(a); }
+BN_LEAF Fp2 fp2_half(const Fp2& a) { return fp2_half_i(a); }
+BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return fp2_mul_fp_i(a, k); }
+BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(a); }
 // Karatsuba: 3 Fp products
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
   Fp t0 = FP_MUL(a.a0, b.a0);
@@ -60,6 +70,30 @@ BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
   z.a1 = fp_sub(fp_sub(m, t0), t1);
   return z;
 }
+struct Wide { uint32_t w[16]; };
+#ifdef BN254_OOL_FPMUL
+BN_NOINLINE Wide fp_mul_wide_call(Fp a, Fp b) { Wide t; fp_mul_wide(t.w, a, b); return t; }
+BN_NOINLINE Fp fp_redc_call(Wide t) { return fp_redc(t.w); }
+#else
+BN_HD Wide fp_mul_wide_call(const Fp& a, const Fp& b) { Wide t; fp_mul_wide(t.w, a, b); return t; }
+BN_HD Fp fp_redc_call(const Wide& t) { return fp_redc(t.w); }
+#endif
+// Lazy-reduction Karatsuba: 3 wide products, 2 Montgomery reductions.
+//   c1 = (a0+a1)(b0+b1) - a0b0 - a1b1 >= 0 ;  c0 = a0b0 - a1b1 (+ p^2 if negative) ; both < 2p^2 < p*2^256
+BN_HD Fp2 fp2_mul_lazy(const Fp2& a, const Fp2& b) {
+  Wide t0 = fp_mul_wide_call(a.a0, b.a0);
+  Wide t1 = fp_mul_wide_call(a.a1, b.a1);
+  Wide t2 = fp_mul_wide_call(fp_add_noreduce(a.a0, a.a1), fp_add_noreduce(b.a0, b.a1));
+  uint32_t mask;
+  wide_sub(t2.w, t2.w, t0.w, mask);
+  wide_sub(t2.w, t2.w, t1.w, mask);
+  wide_sub(t0.w, t0.w, t1.w, mask);
+  wide_add_psq_masked(t0.w, mask);
+  Fp2 z;
+  z.a0 = fp_redc_call(t0);
+  z.a1 = fp_redc_call(t2);
+  return z;
+}
 // complex squaring: 2 Fp products
 BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
   Fp m = FP_MUL(a.a0, a.a1);
@@ -68,8 +102,14 @@ BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
   z.a1 = fp_dbl(m);
   return z;
 }
+// the Fp2 product every routine uses; -DBN254_LAZY_FP2 selects lazy reduction (fewer MACs, measured slower so far)
+#ifndef BN254_LAZY_FP2
+BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_inl(a, b); }
+#else
+BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_lazy(a, b); }
+#endif
 // out-of-line bodies shared by every tower routine
-BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_inl(a, b); }
+BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_best(a, b); }
 BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_inl(a); }
 BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
 BN_HD void fp2_inv(Fp2& z, const Fp2& a) {

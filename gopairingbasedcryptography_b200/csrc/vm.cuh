@@ -65,7 +65,7 @@ BN_D void st_slot(const SlotFile& f, int s, const Fp2& v) { reinterpret_cast<Fp2
 BN_D void vm_sync() {}
 #endif
 
-BN_HD Fp2 fp2_triple(const Fp2& a) { return fp2_add(fp2_dbl(a), a); }
+BN_HD Fp2 fp2_triple_i(const Fp2& a) { return fp2_add_i(fp2_dbl_i(a), a); }
 
 // One micro-op: returns true and the value to store in `out` when the op writes a slot.
 BN_HD bool exec_op(const SlotFile& f, uint64_t w, int& dst, Fp2& out) {
@@ -76,40 +76,42 @@ BN_HD bool exec_op(const SlotFile& f, uint64_t w, int& dst, Fp2& out) {
   int imm = (int)((w >> 48) & 0xFF);
   Fp2 A, B;
   if (a != SLOT_NONE) A = ld_slot(f, a);
+  bool do_mul = false;  // MUL and MULC share ONE copy of the product code after the switch
   switch (op) {
     case OP_MUL:
-      if (a2 != SLOT_NONE) A = fp2_add(A, ld_slot(f, a2));
+      if (a2 != SLOT_NONE) A = fp2_add_i(A, ld_slot(f, a2));
       B = ld_slot(f, b);
-      if (b2 != SLOT_NONE) B = fp2_add(B, ld_slot(f, b2));
-      fp2_mul(out, A, B);
+      if (b2 != SLOT_NONE) B = fp2_add_i(B, ld_slot(f, b2));
+      do_mul = true;
       break;
     case OP_SQR:
-      if (a2 != SLOT_NONE) A = fp2_add(A, ld_slot(f, a2));
-      fp2_sqr(out, A);
+      if (a2 != SLOT_NONE) A = fp2_add_i(A, ld_slot(f, a2));
+      out = fp2_sqr_inl(A);
       break;
-    case OP_ADD: out = fp2_add(A, ld_slot(f, b)); break;
-    case OP_SUB: out = fp2_sub(A, ld_slot(f, b)); break;
-    case OP_SUB2: out = fp2_sub(fp2_sub(A, ld_slot(f, b)), ld_slot(f, b2)); break;
-    case OP_DBL: out = fp2_dbl(A); break;
-    case OP_TRIPLE: out = fp2_triple(A); break;
-    case OP_NEG: out = fp2_neg(A); break;
-    case OP_CONJ: out = fp2_conj(A); break;
-    case OP_MULXI: out = fp2_mul_xi(A); break;
-    case OP_ADDXI: out = fp2_add(A, fp2_mul_xi(ld_slot(f, b))); break;
-    case OP_SUBXI: out = fp2_sub(A, fp2_mul_xi(ld_slot(f, b))); break;
-    case OP_HALF: out = fp2_half(A); break;
+    case OP_ADD: out = fp2_add_i(A, ld_slot(f, b)); break;
+    case OP_SUB: out = fp2_sub_i(A, ld_slot(f, b)); break;
+    case OP_SUB2: out = fp2_sub_i(fp2_sub_i(A, ld_slot(f, b)), ld_slot(f, b2)); break;
+    case OP_DBL: out = fp2_dbl_i(A); break;
+    case OP_TRIPLE: out = fp2_triple_i(A); break;
+    case OP_NEG: out = fp2_neg_i(A); break;
+    case OP_CONJ: out = fp2_conj_i(A); break;
+    case OP_MULXI: out = fp2_mul_xi_i(A); break;
+    case OP_ADDXI: out = fp2_add_i(A, fp2_mul_xi_i(ld_slot(f, b))); break;
+    case OP_SUBXI: out = fp2_sub_i(A, fp2_mul_xi_i(ld_slot(f, b))); break;
+    case OP_HALF: out = fp2_half_i(A); break;
     case OP_MULFP: {
       B = ld_slot(f, b);
-      out = fp2_mul_fp(A, (imm & 1) ? B.a1 : B.a0);
+      out = fp2_mul_fp_i(A, (imm & 1) ? B.a1 : B.a0);
       break;
     }
-    case OP_MULC: { Fp2 c = VM_CONST2[imm]; fp2_mul(out, A, c); break; }
-    case OP_MULCFP: { Fp c = VM_CONSTFP[imm]; out = fp2_mul_fp(A, c); break; }
+    case OP_MULC: B = VM_CONST2[imm]; do_mul = true; break;
+    case OP_MULCFP: { Fp c = VM_CONSTFP[imm]; out = fp2_mul_fp_i(A, c); break; }
     case OP_MOV: out = A; break;
     case OP_LDC: out = VM_CONST2[imm]; break;
     case OP_INV: fp2_inv(out, A); break;
     default: return false;
   }
+  if (do_mul) out = fp2_mul_best(A, B);
   return true;
 }
 

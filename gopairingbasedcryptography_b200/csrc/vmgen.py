@@ -365,6 +365,8 @@ def fp12_mul_034(t, z, l0, l1, l3):
 
 def fp12_cyclo_exp(t, x, digits, cold_table=True):
     """x^e, e as width-3 signed digits LSB first; x in the cyclotomic subgroup (inverse = conjugate)."""
+    if cold_table and not all(v.cold for h in x for v in h):
+        x = park12(t, x)
     x3 = fp12_mul(t, fp12_cyclo_sqr(t, x), x)
     if cold_table:
         x3 = park12(t, x3)
@@ -454,6 +456,7 @@ def trace_final_exp(t, z, park=True):
     f = fp12_mul(t, fp12_frob(t, f, 2), f)
     expt = lambda v: fp12_cyclo_exp(t, v, x0d)
     fc = park12(t, f) if park else f  # f is needed again only at the very end
+    f = fc
     t0 = fp12_cyclo_sqr(t, fp12_conj(t, expt(f)))
     t1 = fp12_mul(t, t0, fp12_cyclo_sqr(t, t0))
     t0 = park12(t, t0) if park else t0
@@ -557,6 +560,26 @@ def schedule(t, K, window=400):
 
 
 COLD_BASE = 160  # slot ids >= COLD_BASE live in global memory (parked values)
+
+
+def auto_cold(t, rounds, min_lifetime):
+    """Values that stay live for more than `min_lifetime` rounds (exponentiation tables and their CSE'd
+    Karatsuba sums, parked partial results) are produced straight into the cold space."""
+    defr, last = {}, {}
+    for r, ops in enumerate(rounds):
+        for n in ops:
+            defr[n.id] = r
+            for s in n.src:
+                if s is not None:
+                    last[s.id] = r
+    outs = set(v.id for v, _ in t.outputs)
+    count = 0
+    for ops in rounds:
+        for n in ops:
+            if not n.cold and n.id not in outs and last.get(n.id, defr[n.id]) - defr[n.id] > min_lifetime:
+                n.cold = True
+                count += 1
+    return count
 
 
 def allocate(t, rounds, nslots_max=COLD_BASE):
@@ -691,7 +714,7 @@ def evaluate(words, K, nslots, slots_init):
 
 
 # ----------------------------------------------------------------------------------------- programs
-def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, park=True):
+def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, park=True, cold_lifetime=0):
     """Inputs: slot 0 = (xP, yP), slot 1 = Q.x, slot 2 = Q.y (pair) or slots 0..5 = f (final exp only).
     Outputs: 6 slots holding the result in gnark memory order."""
     t = Tracer()
@@ -707,6 +730,8 @@ def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, par
     for i, v in enumerate(outs):
         t.output(v, "out%d" % i)
     rounds = schedule(t, K, window)
+    if cold_lifetime:
+        auto_cold(t, rounds, cold_lifetime)
     nslots, ncold = allocate(t, rounds)
     words = encode(rounds, K)
     meta = {"K": K, "rounds": len(rounds), "nslots": nslots, "ncold": ncold, "window": window, "in_slots": [n.slot for n in t.inputs],
@@ -722,6 +747,7 @@ def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, par
 
 
 WINDOW = {1: 0, 2: 20, 3: 30, 4: 40, 6: 60}
+COLD_LIFETIME = 60  # rounds; longer-lived values go to the cold (global, L2-resident) slot space
 
 
 def mont32(v):
@@ -741,7 +767,7 @@ def emit(outdir, Ks=(1, 3)):
     lines.append("};")
     for name, kw in (("pair", {}), ("miller", {"with_final_exp": False}), ("finalexp", {"with_miller": False})):
         for K in Ks:
-            words, meta = build_pair_program(K, window=WINDOW.get(K, 30), **kw)
+            words, meta = build_pair_program(K, window=WINDOW.get(K, 30), cold_lifetime=COLD_LIFETIME, **kw)
             inc = "vm_prog_%s_k%d.inc" % (name, K)
             with open(os.path.join(outdir, inc), "w") as f:
                 for i in range(0, len(words), 4):

@@ -93,3 +93,9 @@ void emu_vm(const void* in0, const void* in1, size_t n, int mode, void* out) {
   }
 }
 }
+extern "C" void emu_fp2_mul_lazy(const void* a, const void* b, size_t n, void* z) {
+  for (size_t i = 0; i < n; i++) st(z, i, fp2_mul_lazy(ld<Fp2>(a, i), ld<Fp2>(b, i))); }
+extern "C" void emu_fp2_mul(const void* a, const void* b, size_t n, void* z) {
+  for (size_t i = 0; i < n; i++) st(z, i, fp2_mul_inl(ld<Fp2>(a, i), ld<Fp2>(b, i))); }
+extern "C" void emu_fp_mul_wide_redc(const void* a, const void* b, size_t n, void* z) {
+  for (size_t i = 0; i < n; i++) { uint32_t t[16]; fp_mul_wide(t, ld<Fp>(a, i), ld<Fp>(b, i)); st(z, i, fp_redc(t)); } }

@@ -167,7 +167,7 @@ def test_vmgen_python_evaluator_matches_oracle():
     rng = o.SplitMix64(5)
     Pt, Qt = o.g1_mul(o.G1_GEN, rng.scalar()), o.g2_mul(o.G2_GEN, rng.scalar())
     for K in (3, 6):
-        words, meta = g.build_pair_program(K, window=g.WINDOW[K])
+        words, meta = g.build_pair_program(K, window=g.WINDOW[K], cold_lifetime=g.COLD_LIFETIME)
         ins = meta["in_slots"]
         slots = g.evaluate(words, K, 256, {ins[0]: Pt, ins[1]: Qt[0], ins[2]: Qt[1]})
         out = [slots[s] for s in meta["out_slots"]]
