@@ -108,6 +108,107 @@ BN_HD void aff_add(A& out, const A& a, const A& b) {
   jac_to_aff(out, t);
 }
 
+// Jacobian + Jacobian (add-2007-bl) with the same edge handling as jac_add_aff
+template <typename J>
+BN_HD void jac_add(J& r, const J& p, const J& q) {
+  if (jac_is_inf(p)) { r = q; return; }
+  if (jac_is_inf(q)) { r = p; return; }
+  auto z1z1 = f_sqr(p.z), z2z2 = f_sqr(q.z);
+  auto u1 = f_mul(p.x, z2z2), u2 = f_mul(q.x, z1z1);
+  auto s1 = f_mul(f_mul(p.y, q.z), z2z2), s2 = f_mul(f_mul(q.y, p.z), z1z1);
+  auto h = f_sub(u2, u1), rr = f_sub(s2, s1);
+  if (f_is_zero(h)) {
+    if (f_is_zero(rr)) { jac_dbl(r, p); return; }
+    f_set_zero(r.x); f_set_zero(r.y); f_set_zero(r.z); return;
+  }
+  auto hh = f_sqr(h), hhh = f_mul(hh, h), v = f_mul(u1, hh);
+  auto x3 = f_sub(f_sub(f_sqr(rr), hhh), f_dbl(v));
+  auto y3 = f_sub(f_mul(rr, f_sub(v, x3)), f_mul(s1, hhh));
+  auto z3 = f_mul(f_mul(p.z, q.z), h);
+  r.x = x3; r.y = y3; r.z = z3;
+}
+
+// ---- GLV: k = k1 + k2*lambda (mod r), |k1|,|k2| < 2^GLV_MAX_BITS, for ANY
+// 256-bit k.  c_i = floor(k * G_iC / 2^256); k1 = k + c1*K1_M1 + c2*K1_M2, k2 = c1*K2_M1 + c2*K2_M2
+// (mod 2^256, two's complement); the constants and their self-check live in gen_constants.py.
+BN_HD void u256_mulhi(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+  uint32_t t[16];
+  for (int i = 0; i < 16; i++) t[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) { c += (uint64_t)a[i] * b[j] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+    t[i + 8] = (uint32_t)c;
+  }
+  for (int i = 0; i < 8; i++) out[i] = t[i + 8];
+}
+BN_HD void u256_mullo_acc(uint32_t* acc, const uint32_t* a, const uint32_t* b) {  // acc += a*b mod 2^256
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; i + j < 8; j++) { c += (uint64_t)a[i] * b[j] + acc[i + j]; acc[i + j] = (uint32_t)c; c >>= 32; }
+  }
+}
+BN_HD bool u256_abs(uint32_t* x) {  // two's complement -> magnitude; returns true when negative
+  if (!(x[7] >> 31)) return false;
+  uint64_t c = 1;
+  for (int i = 0; i < 8; i++) { c += (uint32_t)~x[i]; x[i] = (uint32_t)c; c >>= 32; }
+  return true;
+}
+BN_HD void glv_decompose(const uint32_t* k, uint32_t* k1, bool& neg1, uint32_t* k2, bool& neg2) {
+  uint32_t g1[8], g2[8], m11[8], m12[8], m21[8], m22[8], c1[8], c2[8];
+  for (int i = 0; i < 8; i++) { g1[i] = GLV_G1C[i]; g2[i] = GLV_G2C[i]; m11[i] = GLV_K1_M1[i]; m12[i] = GLV_K1_M2[i];
+                                m21[i] = GLV_K2_M1[i]; m22[i] = GLV_K2_M2[i]; }
+  u256_mulhi(c1, k, g1);
+  u256_mulhi(c2, k, g2);
+  for (int i = 0; i < 8; i++) { k1[i] = k[i]; k2[i] = 0; }
+  u256_mullo_acc(k1, c1, m11); u256_mullo_acc(k1, c2, m12);
+  u256_mullo_acc(k2, c1, m21); u256_mullo_acc(k2, c2, m22);
+  neg1 = u256_abs(k1);
+  neg2 = u256_abs(k2);
+}
+BN_HD Fp f_mul_beta(const Fp& x, const Fp& beta) { return f_mul(x, beta); }
+BN_HD Fp2 f_mul_beta(const Fp2& x, const Fp& beta) { return fp2_mul_fp(x, beta); }
+
+// [s]base by 2-dimensional GLV with the joint (Shamir) ladder over {P1, P2, P1+P2}; canonical affine out.
+template <typename J, typename A>
+BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& beta) {
+  if (aff_is_inf(base)) { out = base; return; }
+  uint32_t k1[8], k2[8];
+  bool n1, n2;
+  glv_decompose(s, k1, n1, k2, n2);
+  A p1 = base, p2;
+  p2.x = f_mul_beta(base.x, beta); p2.y = base.y;
+  if (n1) p1.y = f_neg(p1.y);
+  if (n2) p2.y = f_neg(p2.y);
+  J p3; p3.x = p1.x; p3.y = p1.y; f_set_one(p3.z);
+  jac_add_aff(p3, p3, p2);
+  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
+  int top = GLV_MAX_BITS - 1;
+  while (top >= 0 && !(((k1[top >> 5] | k2[top >> 5]) >> (top & 31)) & 1u)) top--;
+  for (int i = top; i >= 0; i--) {
+    jac_dbl(acc, acc);
+    int b = (int)((k1[i >> 5] >> (i & 31)) & 1u) | ((int)((k2[i >> 5] >> (i & 31)) & 1u) << 1);
+    if (b == 1) jac_add_aff(acc, acc, p1);
+    else if (b == 2) jac_add_aff(acc, acc, p2);
+    else if (b == 3) jac_add(acc, acc, p3);
+  }
+  jac_to_aff(out, acc);
+}
+
+// Fixed base: table[w*255 + d-1] = [d * 2^(8w)] base (affine), w = 0..31, d = 1..255; 32 mixed additions.
+constexpr int kFixedWindows = 32, kFixedEntries = 255;
+template <typename J, typename A>
+BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
+  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
+  for (int w = 0; w < kFixedWindows; w++) {
+    int d = (int)((s[w >> 2] >> ((w & 3) * 8)) & 0xFFu);
+    if (d) {
+      A e = table[w * kFixedEntries + d - 1];
+      if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+    }
+  }
+  jac_to_aff(out, acc);
+}
+
 // GT.Exp: generic Fp12 square-and-multiply (no subgroup assumption), k = 256-bit LE; k == 0 -> 1
 BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
   Fp12 acc; fp12_set_one(acc);

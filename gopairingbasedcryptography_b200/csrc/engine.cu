@@ -77,6 +77,31 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const v
   if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
   else store_struct(out, i, f);
 }
+// Large products (BSW07-style decryption, k ~ 200 pairs): the k pairs of one product are split into groups of
+// kMpChunk pairs, one thread per group (n * ceil(k/kMpChunk) threads), then k_mp_combine multiplies the
+// partial Miller values of a product and finishes with ONE final exponentiation / check.
+constexpr int kMpChunk = 8;
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_partial(const void* P, const void* Q, size_t n, int k, int nchunks, void* partial) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)nchunks) return;
+  size_t i = t / nchunks;
+  int ci = (int)(t % nchunks);
+  int first = ci * kMpChunk, cnt = min(kMpChunk, k - first);
+  Fp12 f;
+  miller_product(f, P, Q, i * (size_t)k + first, cnt);
+  store_struct(partial, t, f);
+}
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_combine(const void* partial, size_t n, int nchunks, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f, g;
+  load_struct(f, partial, i * (size_t)nchunks);
+  for (int c = 1; c < nchunks; c++) { load_struct(g, partial, i * (size_t)nchunks + c); fp12_mul(f, f, g); }
+  if (MODE >= 1) final_exp(f, f);
+  if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
+  else store_struct(out, i, f);
+}
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const void* in, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -94,7 +119,21 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul(const v
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
   s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
   A r;
-  scalar_mul<J, A>(r, b, s);
+  Fp beta = (sizeof(A) == sizeof(G1Aff)) ? GLV_BETA : GLV_BETA_G2;
+  scalar_mul_glv<J, A>(r, b, s, beta);
+  store_struct(out, i, r);
+}
+// fixed base: 32 windowed mixed additions from a precomputed affine table (L2-resident, 0.5-1 MB)
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A* table, const void* scalars, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(scalars) + i * 32);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  A r;
+  scalar_mul_fixed<J, A>(r, table, s);
   store_struct(out, i, r);
 }
 template <typename J, typename A>
@@ -265,6 +304,8 @@ struct Slot {
   char* h = nullptr;  // pinned staging
   char* d = nullptr;  // device staging
   uint4* vm_cold = nullptr;  // cold slot scratch of the lane-group kernels launched on this stream
+  void* mp_scratch = nullptr;  // partial Miller values of split multi-pairings launched on this stream
+  size_t mp_scratch_bytes = 0;
   // pending output copy-back
   void* user_out = nullptr;
   size_t out_off = 0, out_bytes = 0;
@@ -283,6 +324,11 @@ struct bn254_ctx {
   int sms = 0;
   int vm_blocks_per_sm[3] = {0, 0, 0};  // pair, miller, finalexp
   uint4* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
+  // fixed-base window tables (one cached base per group), built on first use with the GLV kernel
+  Slot dev_slot;  // only mp_scratch is used: scratch of the *_dev multi-pairing launches
+  void* fixed_table[2] = {nullptr, nullptr};
+  unsigned char fixed_base[2][BN254_G2_BYTES] = {};
+  bool fixed_valid[2] = {false, false};
   cudaEvent_t vm_dev_done = nullptr;
 };
 
@@ -406,6 +452,51 @@ int run_dev_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out
   return BN254_OK;
 }
 
+
+// multi-pairing launch: single kernel for small k, split + combine for large k
+template <int MODE>
+cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
+  if (k <= 2 * kMpChunk) { k_multi_pair<MODE><<<grid_for(n), kBlock, 0, s>>>(a, b, n, k, o); return cudaSuccess; }
+  int nchunks = (k + kMpChunk - 1) / kMpChunk;
+  size_t need = n * (size_t)nchunks * BN254_GT_BYTES;
+  if (sl.mp_scratch_bytes < need) {
+    if (sl.mp_scratch) { cudaStreamSynchronize(s); cudaFree(sl.mp_scratch); sl.mp_scratch = nullptr; sl.mp_scratch_bytes = 0; }
+    cudaError_t e = cudaMalloc(&sl.mp_scratch, need);
+    if (e != cudaSuccess) return e;
+    sl.mp_scratch_bytes = need;
+  }
+  k_mp_partial<<<grid_for(n * (size_t)nchunks), kBlock, 0, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
+  k_mp_combine<MODE><<<grid_for(n), kBlock, 0, s>>>(sl.mp_scratch, n, nchunks, o);
+  return cudaSuccess;
+}
+// One base, n scalars.  Small batches run the GLV kernel on the broadcast base; from kFixedMin scalars on a
+// 32 x 255 affine window table of the base is built once (8160 GLV multiplications of d << 8w, cached in the
+// context until the base changes) and every scalar costs 32 mixed additions.
+constexpr size_t kFixedMin = 4096;
+template <typename J, typename A>
+int ensure_fixed_table(bn254_ctx* ctx, int g, const void* base) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->fixed_valid[g] && memcmp(ctx->fixed_base[g], base, sizeof(A)) == 0) return BN254_OK;
+  const size_t entries = (size_t)kFixedWindows * kFixedEntries;
+  if (!ctx->fixed_table[g]) CU(cudaMalloc(&ctx->fixed_table[g], entries * sizeof(A)));
+  Slot& s = ctx->slot[0];
+  unsigned char* h = reinterpret_cast<unsigned char*>(s.h);
+  memcpy(h, base, sizeof(A));
+  unsigned char* hs = h + 256;
+  memset(hs, 0, entries * 32);
+  for (int w = 0; w < kFixedWindows; w++)
+    for (int d = 1; d <= kFixedEntries; d++) hs[((size_t)w * kFixedEntries + d - 1) * 32 + w] = (unsigned char)d;
+  CU(cudaMemcpyAsync(s.d, s.h, 256 + entries * 32, cudaMemcpyHostToDevice, s.stream));
+  k_scalar_mul<J, A><<<grid_for(entries), kBlock, 0, s.stream>>>(s.d, 0, s.d + 256, entries, ctx->fixed_table[g]);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s.stream));
+  memcpy(ctx->fixed_base[g], base, sizeof(A));
+  ctx->fixed_valid[g] = true;
+  return BN254_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -460,8 +551,11 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
     if (s.h) cudaFreeHost(s.h);
     if (s.d) cudaFree(s.d);
     if (s.vm_cold) cudaFree(s.vm_cold);
+    if (s.mp_scratch) cudaFree(s.mp_scratch);
   }
+  if (ctx->dev_slot.mp_scratch) { cudaFree(ctx->dev_slot.mp_scratch); }
   if (ctx->vm_cold_dev) cudaFree(ctx->vm_cold_dev);
+  for (int g = 0; g < 2; g++) if (ctx->fixed_table[g]) cudaFree(ctx->fixed_table[g]);
   if (ctx->vm_dev_done) cudaEventDestroy(ctx->vm_dev_done);
   delete ctx;
 }
@@ -504,7 +598,7 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
     if (ctx && ctx->use_vm && k == 1 && MODE == 0) return run_dev_vm<VmProgMiller>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream); \
     if (ctx && ctx->use_vm && k == 1 && MODE == 1) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);   \
-    return run_dev(ctx, n, [&] { k_multi_pair<MODE><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, (int)k, d_out); }); \
+    return run_dev(ctx, n, [&] { cudaError_t e_ = launch_multi_pair<MODE>(ctx->dev_slot, dP, dQ, n, (int)k, d_out, (cudaStream_t)stream); (void)e_; }); \
   }                                                                                                                        \
   int name(bn254_ctx* ctx, const void* P, const void* Q, size_t n, size_t k, OUT_T* out) {                                 \
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
@@ -513,7 +607,7 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
                     [kk, ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {                  \
                       if (ctx->use_vm && kk == 1 && MODE == 0) launch_vm<VmProgMiller>(ctx, a, b, c, o, cold, s);          \
                       else if (ctx->use_vm && kk == 1 && MODE == 1) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);       \
-                      else k_multi_pair<MODE><<<grid_for(c), kBlock, 0, s>>>(a, b, c, kk, o);                              \
+                      else launch_multi_pair<MODE>(ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0], a, b, c, kk, o, s);   \
                     });                                                                                                    \
   }
 MULTI_PAIR_ENTRY(bn254_miller_loop_batch, 0, BN254_GT_BYTES, void)
@@ -548,8 +642,24 @@ int bn254_g2_mul_batch_dev(bn254_ctx* ctx, const void* d_base, size_t stride, co
   }
 MUL_ENTRY(bn254_g1_mul_batch, G1Jac, G1Aff, BN254_G1_BYTES, false)
 MUL_ENTRY(bn254_g2_mul_batch, G2Jac, G2Aff, BN254_G2_BYTES, false)
-MUL_ENTRY(bn254_g1_mul_base_batch, G1Jac, G1Aff, BN254_G1_BYTES, true)
-MUL_ENTRY(bn254_g2_mul_base_batch, G2Jac, G2Aff, BN254_G2_BYTES, true)
+#define MUL_BASE_ENTRY(name, J, A, BYTES, G)                                                                          \
+  int name(bn254_ctx* ctx, const void* base, const void* scalars, size_t n, void* out) {                              \
+    if (!ctx || !base) return BN254_ERR_BAD_ARG;                                                                      \
+    if (n < kFixedMin)                                                                                                \
+      return run_host(ctx, {base, BYTES, true}, {scalars, BN254_SCALAR_BYTES, false}, out, BYTES, n,                  \
+                      [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) {                   \
+                        k_scalar_mul<J, A><<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o);                             \
+                      });                                                                                             \
+    int rc = ensure_fixed_table<J, A>(ctx, G, base);                                                                  \
+    if (rc) return rc;                                                                                                \
+    const A* table = static_cast<const A*>(ctx->fixed_table[G]);                                                      \
+    return run_host(ctx, {base, BYTES, true}, {scalars, BN254_SCALAR_BYTES, false}, out, BYTES, n,                    \
+                    [table](const void*, const void* b, size_t c, void* o, cudaStream_t s, uint4*) {                  \
+                      k_fixed_mul<J, A><<<grid_for(c), kBlock, 0, s>>>(table, b, c, o);                               \
+                    });                                                                                               \
+  }
+MUL_BASE_ENTRY(bn254_g1_mul_base_batch, G1Jac, G1Aff, BN254_G1_BYTES, 0)
+MUL_BASE_ENTRY(bn254_g2_mul_base_batch, G2Jac, G2Aff, BN254_G2_BYTES, 1)
 
 int bn254_g1_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_G1_BYTES, false}, {b, BN254_G1_BYTES, false}, out, BN254_G1_BYTES, n,

@@ -82,6 +82,81 @@ def main():
     # fixed by checking on the generator (1,2) in tests (tests/test_constants.py).
     beta_candidates = [pow(c, (P - 1) // 3, P) for c in (2, 3, 5, 7) if pow(c, (P - 1) // 3, P) != 1]
     beta = beta_candidates[0]
+    # ---- GLV: pick beta with phi(x,y) = (beta x, y) = [lam](x,y) on G1 and on the twist, by testing it
+    def ec_add(a, b, f_mul, f_sub, f_inv, f_zero):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        if a[0] == b[0]:
+            if f_sub(a[1], f_sub(f_zero, b[1])) == f_zero:
+                return None
+            three_x2 = f_mul(f_mul(a[0], a[0]), THREE[type(f_zero)])
+            lam_ = f_mul(three_x2, f_inv(f_mul(a[1], TWO[type(f_zero)])))
+        else:
+            lam_ = f_mul(f_sub(b[1], a[1]), f_inv(f_sub(b[0], a[0])))
+        x3 = f_sub(f_sub(f_mul(lam_, lam_), a[0]), b[0])
+        return (x3, f_sub(f_mul(lam_, f_sub(a[0], x3)), a[1]))
+
+    def ec_mul(pt, k, ops):
+        acc = None
+        while k:
+            if k & 1:
+                acc = ec_add(acc, pt, *ops)
+            pt = ec_add(pt, pt, *ops)
+            k >>= 1
+        return acc
+
+    THREE = {int: 3, tuple: (3, 0)}
+    TWO = {int: 2, tuple: (2, 0)}
+    fp_ops = (lambda a, b: a * b % P, lambda a, b: (a - b) % P, lambda a: pow(a, -1, P), 0)
+    fp2_ops = (f2mul, lambda a, b: ((a[0] - b[0]) % P, (a[1] - b[1]) % P), f2inv, (0, 0))
+    g1_lam = ec_mul((1, 2), lam, fp_ops)
+    beta_g1 = [b for b in (beta, beta * beta % P) if (b * 1 % P, 2) == g1_lam]
+    assert len(beta_g1) == 1
+    beta_g1 = beta_g1[0]
+    g2_lam = ec_mul((G2X, G2Y), lam, fp2_ops)
+    beta_g2 = [b for b in (beta, beta * beta % P) if ((G2X[0] * b % P, G2X[1] * b % P), G2Y) == g2_lam]
+    assert len(beta_g2) == 1
+    beta_g2 = beta_g2[0]
+    # short lattice basis of {(a,b): a + b*lam = 0 mod r} by the extended Euclidean algorithm
+    rows = [(R, 1, 0), (lam, 0, 1)]
+    while rows[-1][0] != 0:
+        q = rows[-2][0] // rows[-1][0]
+        rows.append(tuple(x - q * y for x, y in zip(rows[-2], rows[-1])))
+    import math
+    sq = math.isqrt(R)
+    l = max(i for i, row in enumerate(rows) if row[0] >= sq)
+    v1 = (rows[l + 1][0], -rows[l + 1][2])
+    cand = [(rows[l][0], -rows[l][2]), (rows[l + 2][0], -rows[l + 2][2])]
+    v2 = min(cand, key=lambda v: v[0] * v[0] + v[1] * v[1])
+    for a_, b_ in (v1, v2):
+        assert (a_ + b_ * lam) % R == 0
+    (a1, lb1), (a2, lb2) = v1, v2
+    det = a1 * lb2 - a2 * lb1
+    assert abs(det) == R
+    # k = c1 v1 + c2 v2 + (k1,k2):  c1 = round(k b2/det), c2 = round(-k b1/det); device uses floor(k*g/2^256)
+    sgn = 1 if det > 0 else -1
+    n1, n2 = sgn * lb2, -sgn * lb1          # c1 ~ k*n1/r, c2 ~ k*n2/r
+    g1c, g2c = (abs(n1) << 256) // R, (abs(n2) << 256) // R
+    M256 = (1 << 256) - 1
+    s1, s2 = (1 if n1 >= 0 else -1), (1 if n2 >= 0 else -1)
+    # k1 = k - c1 a1 - c2 a2 ; k2 = -c1 b1 - c2 b2, with c_i = s_i * floor(k*g_ic >> 256)
+    glv = {"G1C": g1c, "G2C": g2c, "K1_M1": (-s1 * a1) & M256, "K1_M2": (-s2 * a2) & M256,
+           "K2_M1": (-s1 * lb1) & M256, "K2_M2": (-s2 * lb2) & M256}
+    # self-check of the exact device formulas on many scalars
+    import random
+    rnd = random.Random(1)
+    worst = 0
+    for k in [0, 1, 2, R - 1, R - 2, R, R + 1, 1 << 128, lam, (1 << 256) - 1] + [rnd.randrange(1 << 256) for _ in range(20000)]:
+        c1, c2 = (k * g1c) >> 256, (k * g2c) >> 256
+        k1 = (k + c1 * glv["K1_M1"] + c2 * glv["K1_M2"]) & M256
+        k2 = (c1 * glv["K2_M1"] + c2 * glv["K2_M2"]) & M256
+        k1 = k1 - (1 << 256) if k1 >> 255 else k1
+        k2 = k2 - (1 << 256) if k2 >> 255 else k2
+        assert (k1 + k2 * lam - k) % R == 0
+        worst = max(worst, abs(k1).bit_length(), abs(k2).bit_length())
+    assert worst <= 131, worst
     ate_naf = naf(6 * X0 + 2)
     x0_naf3 = naf(X0, 3)
 
@@ -114,7 +189,11 @@ def main():
     w("BN_CONST Fp G1_GEN_Y = %s;" % fp_init(2))
     w("BN_CONST Fp2 G2_GEN_X = %s;" % fp2_init(G2X))
     w("BN_CONST Fp2 G2_GEN_Y = %s;" % fp2_init(G2Y))
-    w("BN_CONST Fp GLV_BETA = %s;" % fp_init(beta))
+    w("BN_CONST Fp GLV_BETA = %s;  // phi(x,y) = (beta x, y) = [lambda](x,y) on G1" % fp_init(beta_g1))
+    w("BN_CONST Fp GLV_BETA_G2 = %s;  // same on the twist (G2)" % fp_init(beta_g2))
+    for name, v in glv.items():
+        w("BN_CONST uint32_t GLV_%s[8] = {%s};" % (name, limbs32(v)))
+    w("static constexpr int GLV_MAX_BITS = %d;  // |k1|, |k2| < 2^GLV_MAX_BITS for every 256-bit scalar" % (worst + 1))
     w("static constexpr int ATE_NAF_LEN = %d;" % len(ate_naf))
     w("BN_CONST signed char ATE_NAF[%d] = {%s};" % (len(ate_naf), ",".join(map(str, ate_naf))))
     w("static constexpr int X0_NAF3_LEN = %d;" % len(x0_naf3))

@@ -1,0 +1,71 @@
+"""Scheme-shaped compositions of the engine's batch entry points (BASELINE configs 1/3).
+
+These are thin host-side drivers over the C ABI: they show how the reference's callers use the batch calls
+and give the benchmarks one call per scheme operation.  Nothing here is arithmetic -- all of it happens on
+the GPU through gopairingbasedcryptography_b200.bn254.Engine."""
+from __future__ import annotations
+
+import numpy as np
+
+from .bn254 import G1_BYTES, G2_BYTES, GT_BYTES, P_MOD
+
+
+def neg_fp(elems):
+    """Negate Montgomery-form Fp elements given as an (n, 32) uint8 array (v -> p - v, 0 -> 0) on the host."""
+    y = np.ascontiguousarray(elems).reshape(-1, 32).copy().view("<u8").reshape(-1, 4)
+    out = np.zeros_like(y)
+    p = [(P_MOD >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+    borrow = np.zeros(len(y), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(4):
+            pi = np.uint64(p[i])
+            out[:, i] = pi - y[:, i] - borrow
+            borrow = ((y[:, i] > pi) | ((y[:, i] == pi) & (borrow == 1))).astype(np.uint64)
+    out[~(y != 0).any(axis=1)] = 0
+    return out.view(np.uint8).reshape(-1, 32)
+
+
+def neg_g1(points):
+    """-(x, y) = (x, p - y) for an (n, 64) array of G1Affine in gnark layout; infinity stays infinity."""
+    pts = np.ascontiguousarray(points).reshape(-1, G1_BYTES).copy()
+    pts[:, 32:] = neg_fp(pts[:, 32:])
+    return pts
+
+
+def neg_g2(points):
+    """-(x, y) for an (n, 128) array of G2Affine (Y.A0 and Y.A1 negated)."""
+    pts = np.ascontiguousarray(points).reshape(-1, G2_BYTES).copy()
+    pts[:, 64:] = neg_fp(pts[:, 64:].reshape(-1, 32)).reshape(-1, 64)
+    return pts
+
+
+def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, deltas):
+    """Fused BSW07 decryption for n ciphertexts under ONE user key with m matched leaves
+    (reference: access/tree/access_tree_node.go:96-164 + cpabe/bsw07/bsw07_cpabe.go:172-195).
+
+    cy, cy_prime: (n, m, 64) G1 per ciphertext leaf;  dj, dj_prime: (m, 128) G2 of the key;  c: (n, 64);
+    d: (128,);  c_tilde: (n, 384);  deltas: (m, 32) Lagrange coefficients (regular-form LE scalars).
+    M = C~ * prod_i e([D_i]Cy_i, Dj_i) * e([D_i](-Cy'_i), Dj'_i) * e(-C, D): one (2m+1)-pair Miller product and
+    one final exponentiation per ciphertext, bit-exact with the reference's unfused formula."""
+    n, m = cy.shape[0], cy.shape[1]
+    sc = np.broadcast_to(np.ascontiguousarray(deltas).reshape(1, m, 32), (n, m, 32)).reshape(-1, 32)
+    a = engine.g1_mul_batch(np.ascontiguousarray(cy).reshape(-1, G1_BYTES), sc).reshape(n, m, G1_BYTES)
+    b = engine.g1_mul_batch(neg_g1(cy_prime), sc).reshape(n, m, G1_BYTES)
+    k = 2 * m + 1
+    P = np.concatenate([a, b, neg_g1(c).reshape(n, 1, G1_BYTES)], axis=1)
+    q1 = np.ascontiguousarray(dj).reshape(m, G2_BYTES)
+    q2 = np.ascontiguousarray(dj_prime).reshape(m, G2_BYTES)
+    qrow = np.concatenate([q1, q2, np.ascontiguousarray(d).reshape(1, G2_BYTES)], axis=0)
+    Q = np.broadcast_to(qrow.reshape(1, k, G2_BYTES), (n, k, G2_BYTES))
+    prod = engine.multi_pair_batch(P.reshape(-1), np.ascontiguousarray(Q).reshape(-1), k)
+    return engine.gt_mul_batch(np.ascontiguousarray(c_tilde).reshape(-1, GT_BYTES), prod)
+
+
+def bls_verify_batch(engine, pk, g1, hm, sigma_neg):
+    """n BLS verifications e(pk, H(m_i)) e(g1, -sigma_i) == 1 (signature/bls01_signature/bls_signature.go:71-89).
+    pk, g1: (64,) ; hm, sigma_neg: (n, 128)."""
+    n = hm.shape[0]
+    P = np.concatenate([np.tile(np.ascontiguousarray(pk).reshape(1, 64), (n, 1)),
+                        np.tile(np.ascontiguousarray(g1).reshape(1, 64), (n, 1))], axis=1)
+    Q = np.concatenate([np.ascontiguousarray(hm).reshape(n, 128), np.ascontiguousarray(sigma_neg).reshape(n, 128)], axis=1)
+    return engine.pairing_check_batch(P.reshape(-1), Q.reshape(-1), 2)

@@ -99,3 +99,19 @@ extern "C" void emu_fp2_mul(const void* a, const void* b, size_t n, void* z) {
   for (size_t i = 0; i < n; i++) st(z, i, fp2_mul_inl(ld<Fp2>(a, i), ld<Fp2>(b, i))); }
 extern "C" void emu_fp_mul_wide_redc(const void* a, const void* b, size_t n, void* z) {
   for (size_t i = 0; i < n; i++) { uint32_t t[16]; fp_mul_wide(t, ld<Fp>(a, i), ld<Fp>(b, i)); st(z, i, fp_redc(t)); } }
+extern "C" {
+void emu_g1_mul_glv(const void* base, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { G1Aff b = ld<G1Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32);
+    Fp beta = GLV_BETA; scalar_mul_glv<G1Jac, G1Aff>(r, b, k, beta); st(out, i, r); } }
+void emu_g2_mul_glv(const void* base, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32);
+    Fp beta = GLV_BETA_G2; scalar_mul_glv<G2Jac, G2Aff>(r, b, k, beta); st(out, i, r); } }
+// fixed base: table built with the GLV routine exactly as the engine does (scalars d << 8w)
+void emu_g1_mul_fixed(const void* base1, const void* s, size_t n, void* out) {
+  static G1Aff table[kFixedWindows * kFixedEntries];
+  G1Aff b = ld<G1Aff>(base1, 0); Fp beta = GLV_BETA;
+  for (int w = 0; w < kFixedWindows; w++) for (int d = 1; d <= kFixedEntries; d++) {
+    uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0}; k[w >> 2] = (uint32_t)d << ((w & 3) * 8);
+    scalar_mul_glv<G1Jac, G1Aff>(table[w * kFixedEntries + d - 1], b, k, beta); }
+  for (size_t i = 0; i < n; i++) { uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); G1Aff r; scalar_mul_fixed<G1Jac, G1Aff>(r, table, k); st(out, i, r); } }
+}

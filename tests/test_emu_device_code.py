@@ -173,3 +173,39 @@ def test_vmgen_python_evaluator_matches_oracle():
         out = [slots[s] for s in meta["out_slots"]]
         assert ((out[0], out[1], out[2]), (out[3], out[4], out[5])) == o.pair([Pt], [Qt])
         assert meta["nslots"] <= 48 and meta["ncold"] <= 64
+
+
+def test_glv_and_fixed_base_scalar_mul(emu):
+    """2-dimensional GLV (any 256-bit scalar, incl. >= r) and the 32x255 fixed-base window path."""
+    ks = common.scalars(24) + [(1 << 256) - 1, o.R, o.R + 1, o.LAMBDA_GLV - 1, o.LAMBDA_GLV + 1, 1 << 255]
+    n = len(ks)
+    sb = common.scalar_bytes(ks)
+    P, Q, _, _ = common.points(n, seed=31)
+    P[64 * 9:64 * 10] = 0
+    out = np.zeros(64 * n, np.uint8)
+    emu.emu_g1_mul_glv(vp(P), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == port.g1_mul_batch(P, sb, n)).all()
+    out = np.zeros(128 * n, np.uint8)
+    emu.emu_g2_mul_glv(vp(Q), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == port.g2_mul_batch(Q, sb, n)).all()
+    g1, _ = port.generators()
+    out = np.zeros(64 * n, np.uint8)
+    emu.emu_g1_mul_fixed(vp(g1), vp(sb), sz(n), vp(out))
+    assert (out == port.g1_mul_base_batch(g1, sb, n)).all()
+
+
+def test_lazy_fp2_product(emu):
+    rng = o.SplitMix64(3)
+    n = 400
+    A = [rng.fp() for _ in range(2 * n)]
+    B = [rng.fp() for _ in range(2 * n)]
+    for i in range(8):
+        A[i] = o.P - 1
+        B[i] = o.P - 1
+    A[8:12] = [0, 1, o.P - 1, 0]
+    enc = lambda v: np.frombuffer(b"".join(o.fp_to_mont_bytes(x) for x in v), dtype=np.uint8).copy()
+    a, b, z = enc(A), enc(B), np.zeros(64 * n, np.uint8)
+    emu.emu_fp2_mul_lazy(vp(a), vp(b), sz(n), vp(z))
+    for i in range(n):
+        r = o.fp2_mul((A[2 * i], A[2 * i + 1]), (B[2 * i], B[2 * i + 1]))
+        assert (o.fp_from_mont_bytes(z[64 * i:64 * i + 32].tobytes()), o.fp_from_mont_bytes(z[64 * i + 32:64 * i + 64].tobytes())) == r

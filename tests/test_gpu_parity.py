@@ -86,6 +86,34 @@ def test_multi_pair_and_check(engine, k):
     assert (engine.pairing_check_batch(P, Q, k) == port.pairing_check_batch(P, Q, n, k, 8).astype(bool)).all()
 
 
+def test_split_multi_pair_large_k(engine):
+    """k > 16 takes the split path (groups of 8 pairs per thread, then combine + one final exp)."""
+    n, k = 6, 37
+    P, Q, _, _ = common.points(n * k, seed=2024, threads=8)
+    P, Q = common.with_infinities(P, Q)
+    ref = port.multi_pair_batch(P, Q, n, k, 8)
+    assert (engine.multi_pair_batch(P, Q, k).reshape(-1) == ref).all()
+    assert (engine.final_exp_batch(engine.miller_loop_batch(P, Q, k)).reshape(-1) == ref).all()
+    # e(P,Q)^-1 appended k times makes the product 1 for item 0 only
+    ok = engine.pairing_check_batch(P, Q, k)
+    assert (ok == port.pairing_check_batch(P, Q, n, k, 8).astype(bool)).all()
+
+
+def test_fixed_base_tables(engine):
+    """>= 4096 scalars on one base switch to the cached 32x255 window table; the cache follows the base."""
+    n = 4096 + 5
+    ks = common.scalars(n) + [(1 << 256) - 1, o.R, o.R + 1]
+    n = len(ks)
+    sb = common.scalar_bytes(ks)
+    g1, g2 = port.generators()
+    assert (engine.g1_mul_base_batch(g1, sb).reshape(-1) == port.g1_mul_base_batch(g1, sb, n, 8)).all()
+    assert (engine.g2_mul_base_batch(g2, sb).reshape(-1) == port.g2_mul_base_batch(g2, sb, n, 8)).all()
+    P, Q, _, _ = common.points(2, seed=606)
+    assert (engine.g1_mul_base_batch(P[64:128], sb).reshape(-1) == port.g1_mul_base_batch(P[64:128], sb, n, 8)).all()
+    assert (engine.g1_mul_base_batch(g1, sb).reshape(-1) == port.g1_mul_base_batch(g1, sb, n, 8)).all()
+    assert (engine.g2_mul_base_batch(Q[:128], sb[:32 * 4100]).reshape(-1) == port.g2_mul_base_batch(Q[:128], sb[:32 * 4100], 4100, 8)).all()
+
+
 def test_bls_verify_batch(engine):
     """Config 1 shape (signature/bls01_signature/bls_signature.go:58-89), H(m) := [h_i]G2 synthetic hash:
     sign on the GPU, verify on the GPU, flip some messages -> those verify false."""
@@ -215,3 +243,56 @@ def test_device_pointer_entry_points(engine):
     engine.final_exp_batch_dev(dM.data_ptr(), n, dM.data_ptr(), s)
     torch.cuda.synchronize()
     assert torch.equal(dM, dO)
+
+
+def test_bsw07_fused_decrypt_matches_unfused_reference_formula(engine):
+    """Fused (2m+1)-pair product + one final exp vs the reference's unfused flow
+    (access/tree/access_tree_node.go:96-164: per leaf Pair/Pair/Div, GT.Exp by the Lagrange coefficient, Mul;
+    cpabe/bsw07/bsw07_cpabe.go:184-190: Pair, Div, Div), computed with the oracle."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    n, m = 3, 5
+    cyP, djQ, _, _ = common.points(n * m, seed=71, threads=8)
+    cypP, djpQ, _, _ = common.points(n * m, seed=72, threads=8)
+    cP, dQ, _, _ = common.points(n, seed=73)
+    cy = cyP.reshape(n, m, 64)
+    cyp = cypP.reshape(n, m, 64)
+    dj = djQ.reshape(n * m, 128)[:m]
+    djp = djpQ.reshape(n * m, 128)[:m]
+    d = dQ[:128]
+    c = cP.reshape(n, 64)
+    deltas = common.scalar_bytes(common.scalars(m, seed=74, edges=False)).reshape(m, 32)
+    ctil = engine.pair_batch(c, np.tile(d, n))  # any GT elements
+    got = schemes.bsw07_decrypt_batch(engine, cy, cyp, dj, djp, c, d, ctil, deltas)
+    for i in range(n):
+        A = None
+        for j in range(m):
+            e1 = port.pair_batch(cy[i, j], dj[j], 1)
+            e2 = port.pair_batch(cyp[i, j], djp[j], 1)
+            fz = port.gt_exp_batch(port.gt_div_batch(e1, e2, 1), deltas[j], 1)
+            A = fz if A is None else port.gt_mul_batch(A, fz, 1)
+        ecd = port.pair_batch(c[i], d, 1)
+        M = port.gt_div_batch(ctil[i], port.gt_div_batch(ecd, A, 1), 1)
+        assert (got[i] == M).all()
+
+
+def test_bls_verify_driver(engine):
+    from gopairingbasedcryptography_b200 import schemes
+
+    n = 64
+    g1, g2 = port.generators()
+    sk = 12345678901234567890
+    skb = common.scalar_bytes([sk])
+    pk = engine.g1_mul_base_batch(g1, skb)[0]
+    hm = engine.g2_mul_base_batch(g2, common.scalar_bytes(common.scalars(n, seed=9, edges=False)))
+    sigma = engine.g2_mul_batch(hm, np.tile(skb, n))
+    neg = sigma.copy().reshape(n, 4, 32)
+    for i in range(n):
+        for cidx in (2, 3):
+            v = int.from_bytes(neg[i, cidx].tobytes(), "little")
+            neg[i, cidx] = np.frombuffer(((o.P - v) % o.P).to_bytes(32, "little"), dtype=np.uint8)
+    ok = schemes.bls_verify_batch(engine, pk, g1, hm, neg.reshape(n, 128))
+    assert ok.all()
+    hm2 = hm.copy()
+    hm2[5] = hm[6]
+    assert not schemes.bls_verify_batch(engine, pk, g1, hm2, neg.reshape(n, 128))[5]
