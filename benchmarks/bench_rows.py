@@ -24,7 +24,8 @@ sys.path.insert(0, ROOT)
 
 MAC_PEAK = 9.24e12  # measured IMAD.WIDE rate, profiles/microbench/imad_peak_b200.json
 WORK = {  # SURVEY.md §8d limb-MACs per unit
-    "g1_var": 3.34e5, "g1_fixed": 4.9e4, "g2_var": 7.81e5, "gt_exp": 1.048e6, "bls_verify": 2.862e6, "bsw07_decrypt": 2.251e8,
+    "g1_var": 3.34e5, "g1_fixed": 4.9e4, "g2_var": 7.81e5, "gt_exp": 1.048e6, "gt_cyclo_exp": 1.048e6, "bls_verify": 2.862e6,
+    "bsw07_decrypt": 2.251e8, "waters05_encrypt": 1.577e6, "afp25_decrypt": 3.45e8,
 }
 
 
@@ -97,13 +98,17 @@ def main():
     assert (out[:cs].reshape(-1) == ref).all()
     row("g2_var", "scalar-mults/s", n, sec, cpu, "%d mults" % cs, "G2Affine.ScalarMultiplication (BLS sign), 2-dim GLV")
     # GT exp
-    ng = 1 << (12 if args.quick else 15)
+    ng = 1 << (12 if args.quick else 17)
     gt = eng.pair_batch(Pn[:ng], Qn[:ng])
     sec, out = timed(lambda: eng.gt_exp_batch(gt, sb[:ng]), 2)
     cg = 256
     t0 = time.perf_counter(); ref = port.gt_exp_batch(gt[:cg].reshape(-1), sb[:cg], cg, T); cpu = cg / (time.perf_counter() - t0)
     assert (out[:cg].reshape(-1) == ref).all()
     row("gt_exp", "exps/s", ng, sec, cpu, "%d exps" % cg, "GT.Exp generic 254-bit square-and-multiply")
+    sec, out2 = timed(lambda: eng.gt_cyclo_exp_batch(gt, sb[:ng]), 2)
+    assert (out2[:cg].reshape(-1) == ref).all()
+    row("gt_cyclo_exp", "exps/s", ng, sec, cpu, "%d exps (generic ladder, as gnark's GT.Exp)" % cg,
+        "GT.Exp for pairing outputs: Granger-Scott squarings + signed window")
     # ---- config 1: BLS verify ---------------------------------------------------------------------
     nb = 1 << (12 if args.quick else 16)
     skb = sb[:1]
@@ -122,7 +127,7 @@ def main():
         "config 1 (hash-to-G2 excluded: H(m) := [h]G2 synthetic hash, SURVEY 8d-1)")
     # ---- config 3: BSW07 100-attribute decrypt ---------------------------------------------------
     m = 100
-    nd = 64 if args.quick else 512
+    nd = 64 if args.quick else 2048
     cy = Pn[: nd * m].reshape(nd, m, 64)
     cyp = Pn[nd * m: 2 * nd * m].reshape(nd, m, 64)
     dj, djp = Qn[:m], Qn[m: 2 * m]
@@ -147,6 +152,62 @@ def main():
     cpu = cdn / (time.perf_counter() - t0)
     row("bsw07_decrypt", "decryptions/s", nd, sec, cpu, "%d decryptions, unfused reference flow without its debug pairing" % cdn,
         "config 3: 200 G1 GLV mults + 201-pair Miller product + 1 final exp per decryption")
+    # ---- config 4: Waters05 encrypt -------------------------------------------------------------------
+    import hashlib
+    nw = 1 << (12 if args.quick else 16)
+    U = Qn[:257]
+    e_const = gt[0]
+    ids = np.stack([np.frombuffer(hashlib.sha256(b"id-%d" % i).digest(), dtype=np.uint8) for i in range(nw)])
+    ts = sb[:nw]
+
+    def waters_encrypt():
+        c1 = eng.gt_mul_batch(eng.gt_cyclo_exp_base_batch(e_const, ts), gt[:nw] if nw <= ng else np.tile(gt, (nw // ng + 1, 1))[:nw])
+        c2 = eng.g1_mul_base_batch(g1, ts)
+        H = eng.g2_subset_sum_batch(U, ids)
+        c3 = eng.g2_mul_batch(H, ts)
+        return c1, c2, c3
+
+    sec, (c1, c2, c3) = timed(waters_encrypt, 1)
+    cw = 64
+    t0 = time.perf_counter()
+    e1 = port.gt_exp_base_batch(e_const, ts[:cw].reshape(-1), cw, T)
+    r2 = port.g1_mul_base_batch(g1, ts[:cw].reshape(-1), cw, T)
+    Hc = np.zeros((cw, 128), np.uint8)
+    for i in range(cw):
+        acc = U[0].copy()
+        for j in range(256):
+            if (ids[i, j >> 3] >> (7 - (j & 7))) & 1:
+                acc = port.g2_add_batch(acc, U[j + 1], 1)
+        Hc[i] = acc
+    r3 = port.g2_mul_batch(Hc.reshape(-1), ts[:cw].reshape(-1), cw, T)
+    cpu = cw / (time.perf_counter() - t0)
+    assert (c2[:cw].reshape(-1) == r2).all() and (c3[:cw].reshape(-1) == r3).all()
+    assert (c1[:cw].reshape(-1) == port.gt_mul_batch(e1, (gt[:cw]).reshape(-1), cw, T)).all()
+    row("waters05_encrypt", "encryptions/s", nw, sec, cpu, "%d encryptions (Add loop single-threaded as in the reference)" % cw,
+        "config 4: GT exp of the constant pairing + fixed-base G1 + Waters hash subset sum + G2 GLV mult")
+    # ---- config 5: AFP25 decrypt shape (B-term G1 MSM + 3-pair product) ---------------------------------
+    B = 1024
+    nc = 8 if args.quick else 64
+    tau = Pn[:B]
+    coef = sb[: nc * B] if nc * B <= n else np.tile(sb, (nc * B // n + 1, 1))[: nc * B]
+
+    def afp25():
+        terms = eng.g1_mul_batch(np.tile(tau, (nc, 1)), coef)
+        pi = eng.g1_sum_batch(terms, B)
+        Pp = np.concatenate([pi.reshape(nc, 1, 64), Pn[B:B + nc].reshape(nc, 1, 64), Pn[2 * B:2 * B + nc].reshape(nc, 1, 64)], axis=1)
+        Qp = np.tile(Qn[:3].reshape(1, 3, 128), (nc, 1, 1))
+        return pi, eng.multi_pair_batch(Pp, Qp, 3)
+
+    sec, (pi, prod) = timed(afp25, 1)
+    t0 = time.perf_counter()
+    tr = port.g1_mul_batch(tau.reshape(-1), coef[:B].reshape(-1), B, T)
+    acc = np.zeros(64, np.uint8)
+    for j in range(B):
+        acc = port.g1_add_batch(acc, tr[64 * j:64 * j + 64], 1)
+    cpu = 1 / (time.perf_counter() - t0)
+    assert (pi[0] == acc).all()
+    row("afp25_decrypt", "decryptions/s", nc, sec, cpu, "1 decryption's 1024-term MSM (mults on %d threads, Add chain serial as in the reference)" % T,
+        "config 5 shape: 1024-term G1 MSM (GLV + segment sums) + 3-pair product per ciphertext; O(B^2) Fr polynomial stays on the host")
     print(json.dumps({"summary": {r["row"]: r["value"] for r in rows}, "launches": eng.launches}))
 
 

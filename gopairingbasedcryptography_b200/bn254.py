@@ -99,10 +99,14 @@ class Engine:
             raise ValueError("invalid inputs sizes")
         raise EngineError("%s: %s" % (_ERRORS.get(rc, rc), self._lib.bn254_last_error(self._h).decode()))
 
-    def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8):
+    def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8, pre_sizes=None, mid_sizes=None):
         out = np.empty(n * out_bytes, dtype=np.uint8)
         fn = getattr(self._lib, name)
-        args = [self._h] + [b.ctypes.data_as(ctypes.c_void_p) for b in bufs] + [ctypes.c_size_t(s) for s in sizes]
+        if pre_sizes is not None:  # (ctx, buf0, size..., buf1, size..., out) argument order
+            args = [self._h, bufs[0].ctypes.data_as(ctypes.c_void_p)] + [ctypes.c_size_t(s) for s in pre_sizes]
+            args += [bufs[1].ctypes.data_as(ctypes.c_void_p)] + [ctypes.c_size_t(s) for s in mid_sizes]
+        else:
+            args = [self._h] + [b.ctypes.data_as(ctypes.c_void_p) for b in bufs] + [ctypes.c_size_t(s) for s in sizes]
         args.append(out.ctypes.data_as(ctypes.c_void_p))
         fn.restype = ctypes.c_int
         self._check(fn(*args))
@@ -176,6 +180,38 @@ class Engine:
     def g2_add_batch(self, a, b):
         return self._binary("bn254_g2_add_batch", a, b, G2_BYTES)
 
+    def _subset_sum(self, name, U, sel, pt_bytes):
+        U = _u8(U, pt_bytes, "U")
+        m = U.size // pt_bytes - 1
+        if m <= 0:
+            raise ValueError("invalid inputs sizes")
+        row = (m + 7) // 8
+        sel = _u8(sel, row, "sel")
+        n = sel.size // row
+        return self._call(name, [U, sel], [], pt_bytes, n, pre_sizes=[m], mid_sizes=[n]).reshape(n, pt_bytes)
+
+    def g1_subset_sum_batch(self, U, sel):
+        """out[i] = U[0] + sum_{bit j of sel[i]} U[j+1]; sel rows are MSB-first bit strings of ceil(m/8) bytes."""
+        return self._subset_sum("bn254_g1_subset_sum_batch", U, sel, G1_BYTES)
+
+    def g2_subset_sum_batch(self, U, sel):
+        return self._subset_sum("bn254_g2_subset_sum_batch", U, sel, G2_BYTES)
+
+    def _segment_sum(self, name, pts, length, pt_bytes):
+        pts = _u8(pts, pt_bytes, "points")
+        length = int(length)
+        if length <= 0 or (pts.size // pt_bytes) % length:
+            raise ValueError("invalid inputs sizes")
+        groups = pts.size // pt_bytes // length
+        return self._call(name, [pts], [groups, length], pt_bytes, groups).reshape(groups, pt_bytes)
+
+    def g1_sum_batch(self, pts, length):
+        """Sum every `length` consecutive points -> (groups, 64)."""
+        return self._segment_sum("bn254_g1_sum_batch", pts, length, G1_BYTES)
+
+    def g2_sum_batch(self, pts, length):
+        return self._segment_sum("bn254_g2_sum_batch", pts, length, G2_BYTES)
+
     # ---- GT -------------------------------------------------------------------------------
     def gt_exp_batch(self, x, k):
         x, k = _u8(x, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
@@ -190,6 +226,21 @@ class Engine:
         if x1.size != GT_BYTES:
             raise ValueError("invalid inputs sizes")
         return self._call("bn254_gt_exp_base_batch", [x1, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    def gt_cyclo_exp_batch(self, x, k):
+        """x[i]^k[i] for x in the cyclotomic subgroup (pairing outputs and their products/powers)."""
+        x, k = _u8(x, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
+        n = k.size // SCALAR_BYTES
+        if x.size // GT_BYTES != n:
+            raise ValueError("invalid inputs sizes")
+        return self._call("bn254_gt_cyclo_exp_batch", [x, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+
+    def gt_cyclo_exp_base_batch(self, x1, k):
+        x1, k = _u8(x1, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
+        n = k.size // SCALAR_BYTES
+        if x1.size != GT_BYTES:
+            raise ValueError("invalid inputs sizes")
+        return self._call("bn254_gt_cyclo_exp_base_batch", [x1, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
 
     def gt_mul_batch(self, a, b):
         return self._binary("bn254_gt_mul_batch", a, b, GT_BYTES)

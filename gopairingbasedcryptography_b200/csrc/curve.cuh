@@ -224,4 +224,48 @@ BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
   out = acc;
 }
 
+// GT.Exp for bases in the cyclotomic subgroup (every pairing output and any product / quotient / power of
+// pairing outputs -- all GT.Exp call sites of the reference): Granger-Scott squarings and a
+// width-3 signed window where the inverse is a conjugation.  ~8.3k Fp-mul instead of ~23k for the generic ladder.
+BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
+  // signed width-3 digits of the 256-bit exponent, LSB first (257 digits max)
+  signed char dg[260];
+  uint32_t t[9];
+  for (int i = 0; i < 8; i++) t[i] = k[i];
+  t[8] = 0;
+  int n = 0;
+  bool nz = false;
+  for (int i = 0; i < 9; i++) nz |= t[i] != 0;
+  while (nz) {
+    int d = 0;
+    if (t[0] & 1u) {
+      d = (int)(t[0] & 7u);
+      if (d > 4) d -= 8;
+      // t -= d
+      if (d > 0) { uint64_t b = (uint64_t)d; for (int i = 0; i < 9 && b; i++) { uint64_t v = (uint64_t)t[i] - b; t[i] = (uint32_t)v; b = (v >> 63) & 1u; } }
+      else { uint64_t c = (uint64_t)(-d); for (int i = 0; i < 9 && c; i++) { c += t[i]; t[i] = (uint32_t)c; c >>= 32; } }
+    }
+    dg[n++] = (signed char)d;
+    for (int i = 0; i < 8; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    t[8] >>= 1;
+    nz = false;
+    for (int i = 0; i < 9; i++) nz |= t[i] != 0;
+  }
+  if (n == 0) { fp12_set_one(out); return; }
+  Fp12 x3, acc, m;
+  fp12_cyclo_sqr(x3, x); fp12_mul(x3, x3, x);
+  bool started = false;
+  for (int i = n - 1; i >= 0; i--) {
+    if (started) fp12_cyclo_sqr(acc, acc);
+    int d = dg[i];
+    if (d) {
+      int ad = d < 0 ? -d : d;
+      if (ad == 1) m = x; else m = x3;
+      if (d < 0) fp12_conj(m, m);
+      if (started) fp12_mul(acc, acc, m); else { acc = m; started = true; }
+    }
+  }
+  out = acc;
+}
+
 }  // namespace bn254

@@ -144,6 +144,55 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_aff_add(const void
   aff_add<J, A>(r, x, y);
   store_struct(out, i, r);
 }
+// out[i] = U[0] + sum_{j < m, bit j of sel_i set} U[j+1]   (Waters hash: ibe/waters05_ibe/waters05_ibe.go:227-233).
+// Bit j is bit (7 - j%8) of byte j/8 -- the MSB-first order of waters05_ibe.go:302-313.  The m+1 public
+// points are staged in shared memory once per CTA; the sum runs in Jacobian form with ONE inversion at the end
+// (the reference pays one inversion per Add).
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum(const A* U, int m, const uint8_t* sel, size_t n, void* out) {
+  extern __shared__ uint4 su_raw[];
+  A* su = reinterpret_cast<A*>(su_raw);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(U);
+    int words = (m + 1) * (int)(sizeof(A) / 16);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) su_raw[w] = __ldg(src + w);
+  }
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* bits = sel + i * (size_t)((m + 7) / 8);
+  J acc;
+  if (aff_is_inf(su[0])) { f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z); }
+  else { acc.x = su[0].x; acc.y = su[0].y; f_set_one(acc.z); }
+  for (int j = 0; j < m; j++) {
+    if ((bits[j >> 3] >> (7 - (j & 7))) & 1) {
+      A e = su[j + 1];
+      if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+    }
+  }
+  A r;
+  jac_to_aff(r, acc);
+  store_struct(out, i, r);
+}
+// out[g] = sum of the `len` consecutive points of group g, processed as ceil(len/32)-way partial sums per pass
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const void* pts, size_t groups, int len, int chunk, void* out) {
+  int nch = (len + chunk - 1) / chunk;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= groups * (size_t)nch) return;
+  size_t g = t / nch;
+  int c = (int)(t % nch);
+  int first = c * chunk, cnt = min(chunk, len - first);
+  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
+  for (int j = 0; j < cnt; j++) {
+    A e; load_struct(e, pts, g * (size_t)len + first + j);
+    if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+  }
+  A r;
+  jac_to_aff(r, acc);
+  store_struct(out, t, r);
+}
+template <int CYCLO>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -153,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void*
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
   s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
   Fp12 r;
-  gt_exp(r, b, s);
+  if (CYCLO) gt_cyclo_exp(r, b, s); else gt_exp(r, b, s);
   store_struct(out, i, r);
 }
 // mode 0: a*b ; mode 1: a/b
@@ -661,6 +710,61 @@ MUL_ENTRY(bn254_g2_mul_batch, G2Jac, G2Aff, BN254_G2_BYTES, false)
 MUL_BASE_ENTRY(bn254_g1_mul_base_batch, G1Jac, G1Aff, BN254_G1_BYTES, 0)
 MUL_BASE_ENTRY(bn254_g2_mul_base_batch, G2Jac, G2Aff, BN254_G2_BYTES, 1)
 
+// ---- subset sums and segment sums -----------------------------------------------------------------
+#define SUBSET_SUM_ENTRY(name, J, A, BYTES)                                                                              \
+  int name(bn254_ctx* ctx, const void* U, size_t m, const void* sel, size_t n, void* out) {                              \
+    if (!ctx || !U || m == 0 || (m + 1) * BYTES > 200 * 1024) return fail(ctx, BN254_ERR_BAD_ARG, "bad subset-sum arguments"); \
+    size_t smem = (m + 1) * BYTES;                                                                                       \
+    { std::lock_guard<std::mutex> lk(ctx->mu); CU(cudaSetDevice(ctx->device));                                          \
+      CU(cudaFuncSetAttribute(k_subset_sum<J, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }           \
+    int mm = (int)m;                                                                                                     \
+    return run_host(ctx, {U, (m + 1) * BYTES, true}, {sel, (m + 7) / 8, false}, out, BYTES, n,                           \
+                    [mm, smem](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) {                \
+                      k_subset_sum<J, A><<<grid_for(c), kBlock, smem, s>>>(static_cast<const A*>(a), mm,                 \
+                                                                            static_cast<const uint8_t*>(b), c, o);        \
+                    });                                                                                                  \
+  }
+SUBSET_SUM_ENTRY(bn254_g1_subset_sum_batch, G1Jac, G1Aff, BN254_G1_BYTES)
+SUBSET_SUM_ENTRY(bn254_g2_subset_sum_batch, G2Jac, G2Aff, BN254_G2_BYTES)
+
+// out[g] = sum of points[g*len .. g*len+len): passes of 32-way partial sums, all on the device
+#define SEGMENT_SUM_ENTRY(name, J, A, BYTES)                                                                             \
+  int name(bn254_ctx* ctx, const void* pts, size_t groups, size_t len, void* out) {                                      \
+    if (!ctx || !pts || !out || len == 0 || len > (1u << 24)) return fail(ctx, BN254_ERR_BAD_ARG, "bad segment-sum arguments"); \
+    if (groups == 0) return BN254_OK;                                                                                    \
+    std::lock_guard<std::mutex> lk(ctx->mu);                                                                             \
+    CU(cudaSetDevice(ctx->device));                                                                                      \
+    Slot& s = ctx->slot[0];                                                                                              \
+    const int chunk = 32;                                                                                                \
+    size_t per_group = len * BYTES + ((len + chunk - 1) / chunk) * BYTES + 512;                                          \
+    size_t gmax = (ctx->slot_bytes - 4096) / per_group;                                                                  \
+    if (gmax == 0) return fail(ctx, BN254_ERR_BAD_ARG, "segment too long for staging");                                  \
+    for (size_t g0 = 0; g0 < groups; g0 += gmax) {                                                                       \
+      size_t gc = std::min(gmax, groups - g0);                                                                           \
+      size_t in_bytes = gc * len * BYTES;                                                                                \
+      memcpy(s.h, static_cast<const char*>(pts) + g0 * len * BYTES, in_bytes);                                           \
+      CU(cudaMemcpyAsync(s.d, s.h, in_bytes, cudaMemcpyHostToDevice, s.stream));                                         \
+      char* cur = s.d;                                                                                                   \
+      char* nxt = s.d + ((in_bytes + 255) & ~size_t(255));                                                               \
+      size_t cur_len = len;                                                                                              \
+      while (true) {                                                                                                     \
+        int nch = (int)((cur_len + chunk - 1) / chunk);                                                                  \
+        k_segment_sum<J, A><<<grid_for(gc * (size_t)nch), kBlock, 0, s.stream>>>(cur, gc, (int)cur_len, chunk, nxt);     \
+        ctx->launches++;                                                                                                 \
+        CU(cudaGetLastError());                                                                                          \
+        std::swap(cur, nxt);                                                                                             \
+        cur_len = (size_t)nch;                                                                                           \
+        if (nch == 1) break;                                                                                             \
+      }                                                                                                                  \
+      CU(cudaMemcpyAsync(s.h, cur, gc * BYTES, cudaMemcpyDeviceToHost, s.stream));                                       \
+      CU(cudaStreamSynchronize(s.stream));                                                                               \
+      memcpy(static_cast<char*>(out) + g0 * BYTES, s.h, gc * BYTES);                                                     \
+    }                                                                                                                    \
+    return BN254_OK;                                                                                                     \
+  }
+SEGMENT_SUM_ENTRY(bn254_g1_sum_batch, G1Jac, G1Aff, BN254_G1_BYTES)
+SEGMENT_SUM_ENTRY(bn254_g2_sum_batch, G2Jac, G2Aff, BN254_G2_BYTES)
+
 int bn254_g1_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_G1_BYTES, false}, {b, BN254_G1_BYTES, false}, out, BN254_G1_BYTES, n,
                   [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_aff_add<G1Jac, G1Aff><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
@@ -672,15 +776,23 @@ int bn254_g2_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, v
 
 // ---- GT ---------------------------------------------------------------------------------------
 int bn254_gt_exp_batch_dev(bn254_ctx* ctx, const void* d_x, size_t stride, const void* d_k, size_t n, void* d_out, void* stream) {
-  return run_dev(ctx, n, [&] { k_gt_exp<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_x, stride, d_k, n, d_out); });
+  return run_dev(ctx, n, [&] { k_gt_exp<0><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_x, stride, d_k, n, d_out); });
 }
 int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+}
+int bn254_gt_cyclo_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
+  return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+}
+int bn254_gt_cyclo_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
+  return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
 }
 int bn254_gt_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,

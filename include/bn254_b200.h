@@ -100,12 +100,27 @@ int bn254_g2_mul_batch_dev(bn254_ctx*, const void* d_base, size_t base_stride_el
 int bn254_g1_add_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 int bn254_g2_add_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 
+/* Waters hash  out[i] = U[0] + sum_{j<m : bit j of sel_i} U[j+1]  for n selector strings of ceil(m/8) bytes, bit j =
+ * bit (7 - j%8) of byte j/8 (the identity-vector order of ibe/waters05_ibe/waters05_ibe.go:302-313).  Replaces the
+ * loop of affine Adds at waters05_ibe.go:227-233 (one inversion per Add) by one Jacobian sum per identity. */
+int bn254_g1_subset_sum_batch(bn254_ctx*, const void* U_m_plus_1, size_t m, const void* sel, size_t n, void* out);
+int bn254_g2_subset_sum_batch(bn254_ctx*, const void* U_m_plus_1, size_t m, const void* sel, size_t n, void* out);
+/* out[g] = points[g*len] + ... + points[g*len+len-1]: the Add chain of bibe/afp25_bibe/afp25_bibe_utils.go:45-55
+ * (after bn254_g1_mul_batch on the terms) and of gwww25's G2-side MSM. */
+int bn254_g1_sum_batch(bn254_ctx*, const void* points, size_t groups, size_t len, void* out);
+int bn254_g2_sum_batch(bn254_ctx*, const void* points, size_t groups, size_t len, void* out);
+
 /* (*GT).Exp(x[i], k[i]) with k >= 0 (the Go shim inverts x for negative k as gnark does); generic
  * Fp12 exponentiation, no subgroup assumption; k == 0 -> 1
  * [access/tree/access_tree_node.go:156; waters05_ibe.go:219; bsw07_cpabe.go:80,146] */
 int bn254_gt_exp_batch(bn254_ctx*, const void* x, const void* k, size_t n, void* out);
 int bn254_gt_exp_base_batch(bn254_ctx*, const void* x1, const void* k, size_t n, void* out);
 int bn254_gt_exp_batch_dev(bn254_ctx*, const void* d_x, size_t x_stride_elems, const void* d_k, size_t n, void* d_out, void* stream);
+/* Same result as bn254_gt_exp_batch when x lies in the cyclotomic subgroup (any Pair output, or a product,
+ * quotient or power of Pair outputs -- every GT.Exp base in the reference's non-test code):
+ * Granger-Scott squarings + signed windows, ~2.8x less work.  Undefined for other Fp12 elements. */
+int bn254_gt_cyclo_exp_batch(bn254_ctx*, const void* x, const void* k, size_t n, void* out);
+int bn254_gt_cyclo_exp_base_batch(bn254_ctx*, const void* x1, const void* k, size_t n, void* out);
 /* (*GT).Mul / (*GT).Div  [access_tree_node.go:114,157; bsw07_cpabe.go:189-190] */
 int bn254_gt_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 int bn254_gt_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);

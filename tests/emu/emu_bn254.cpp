@@ -115,3 +115,5 @@ void emu_g1_mul_fixed(const void* base1, const void* s, size_t n, void* out) {
     scalar_mul_glv<G1Jac, G1Aff>(table[w * kFixedEntries + d - 1], b, k, beta); }
   for (size_t i = 0; i < n; i++) { uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); G1Aff r; scalar_mul_fixed<G1Jac, G1Aff>(r, table, k); st(out, i, r); } }
 }
+extern "C" void emu_gt_cyclo_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); gt_cyclo_exp(r, b, k); st(out, i, r); } }

@@ -296,3 +296,106 @@ def test_bls_verify_driver(engine):
     hm2 = hm.copy()
     hm2[5] = hm[6]
     assert not schemes.bls_verify_batch(engine, pk, g1, hm2, neg.reshape(n, 128))[5]
+
+
+def test_gt_cyclotomic_exp(engine):
+    n = 40
+    P, Q, _, _ = common.points(n, seed=56, threads=8)
+    gt = engine.pair_batch(P, Q)
+    ks = common.scalars(n - 4) + [(1 << 256) - 1, 1 << 255, 3, 4]
+    sb = common.scalar_bytes(ks)
+    ref = port.gt_exp_batch(gt.reshape(-1), sb, n, 8)
+    assert (engine.gt_cyclo_exp_batch(gt, sb).reshape(-1) == ref).all()
+    assert (engine.gt_exp_batch(gt, sb).reshape(-1) == ref).all()
+    assert (engine.gt_cyclo_exp_base_batch(gt[3], sb).reshape(-1) == port.gt_exp_base_batch(gt[3], sb, n, 8)).all()
+
+
+def test_subset_and_segment_sums(engine):
+    m, n = 256, 33
+    U1, U2, _, _ = common.points(m + 1, seed=91, threads=8)
+    rng = np.random.default_rng(5)
+    sel = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sel[0] = 0
+    sel[1] = 255
+    got2 = engine.g2_subset_sum_batch(U2, sel)
+    got1 = engine.g1_subset_sum_batch(U1, sel)
+    for i in (0, 1, 2, n - 1):
+        a1, a2 = U1[:64].copy(), U2[:128].copy()
+        for j in range(m):
+            if (sel[i, j >> 3] >> (7 - (j & 7))) & 1:
+                a1 = port.g1_add_batch(a1, U1[64 * (j + 1):64 * (j + 2)], 1)
+                a2 = port.g2_add_batch(a2, U2[128 * (j + 1):128 * (j + 2)], 1)
+        assert (got1[i] == a1).all() and (got2[i] == a2).all()
+    # segment sums incl. infinity members, a cancelling pair and non-power-of-two lengths
+    for length in (1, 5, 37, 100):
+        groups = 7
+        pts, qts, _, _ = common.points(groups * length, seed=300 + length, threads=8)
+        pts[:64] = 0
+        if length >= 5:
+            neg = o.g1_to_bytes(o.g1_neg(o.g1_from_bytes(pts[64 * 2:64 * 3].tobytes())))
+            pts[64 * 3:64 * 4] = np.frombuffer(neg, dtype=np.uint8)
+        s1 = engine.g1_sum_batch(pts, length)
+        s2 = engine.g2_sum_batch(qts, length)
+        for g in (0, groups - 1):
+            a1, a2 = np.zeros(64, np.uint8), np.zeros(128, np.uint8)
+            for j in range(length):
+                k = g * length + j
+                a1 = port.g1_add_batch(a1, pts[64 * k:64 * k + 64], 1)
+                a2 = port.g2_add_batch(a2, qts[128 * k:128 * k + 128], 1)
+            assert (s1[g] == a1).all() and (s2[g] == a2).all()
+
+
+def test_waters05_encrypt_decrypt_round_trip(engine):
+    """Config 4 shape (ibe/waters05_ibe/waters05_ibe.go:206-279) on the batch entry points: fixed-base G1,
+    GT exponentiation of the constant e(g1^alpha, g2), Waters hash as one subset sum, G2 variable-base mult;
+    decryption M = c1 * e(d2, c3) / e(c2, d1) recovers the message for every identity."""
+    import hashlib
+    from gopairingbasedcryptography_b200 import schemes
+
+    n, m = 48, 256
+    g1, g2 = port.generators()
+    sb = common.scalar_bytes
+    alpha = 0x1234567890ABCDEF1234567890ABCDEF % o.R
+    us = common.scalars(m + 1, seed=505, edges=False)
+    U = engine.g2_mul_base_batch(g2, sb(us))  # U', U_1..U_m
+    g1a = engine.g1_mul_base_batch(g1, sb([alpha]))[0]
+    e_const = engine.pair_batch(g1a, g2)[0]
+    ids = np.stack([np.frombuffer(hashlib.sha256(b"id-%d" % i).digest(), dtype=np.uint8) for i in range(n)])
+    H = engine.g2_subset_sum_batch(U, ids)
+    ts = sb(common.scalars(n, seed=506, edges=False)).reshape(n, 32)
+    rs = sb(common.scalars(n, seed=507, edges=False)).reshape(n, 32)
+    msgs = engine.gt_cyclo_exp_base_batch(e_const, sb(common.scalars(n, seed=508, edges=False)))
+    # encrypt
+    c1 = engine.gt_mul_batch(engine.gt_cyclo_exp_base_batch(e_const, ts), msgs)
+    c2 = engine.g1_mul_base_batch(g1, ts)
+    c3 = engine.g2_mul_batch(H, ts)
+    # key generation: d1 = [alpha]g2 + [r]H(id), d2 = [r]g1
+    d1 = engine.g2_add_batch(np.tile(engine.g2_mul_base_batch(g2, sb([alpha])), (n, 1)), engine.g2_mul_batch(H, rs))
+    d2 = engine.g1_mul_base_batch(g1, rs)
+    # decrypt: one 2-pair product e(d2, c3) * e(-c2, d1) per ciphertext
+    P = np.concatenate([d2.reshape(n, 1, 64), schemes.neg_g1(c2).reshape(n, 1, 64)], axis=1)
+    Q = np.concatenate([c3.reshape(n, 1, 128), d1.reshape(n, 1, 128)], axis=1)
+    rec = engine.gt_mul_batch(c1, engine.multi_pair_batch(P, Q, 2))
+    assert (rec == msgs).all()
+    # the Waters hash agrees with the reference's Add loop (oracle) for one identity
+    acc = U[0].copy()
+    for j in range(m):
+        if (ids[7, j >> 3] >> (7 - (j & 7))) & 1:
+            acc = port.g2_add_batch(acc, U[j + 1], 1)
+    assert (H[7] == acc).all()
+
+
+def test_afp25_shaped_msm(engine):
+    """Config 5 shape (bibe/afp25_bibe/afp25_bibe_utils.go:45-55): result = sum_j [coef_j] tauPowers_j for several
+    coefficient vectors over the SAME points: n*len variable-base mults + segment sums."""
+    length, n = 64, 5
+    pts, _, _, _ = common.points(length, seed=808, threads=8)
+    coef = common.scalar_bytes(common.scalars(n * length, seed=809, edges=False))
+    terms = engine.g1_mul_batch(np.tile(pts, n), coef)
+    got = engine.g1_sum_batch(terms, length)
+    for i in (0, n - 1):
+        acc = np.zeros(64, np.uint8)
+        t = port.g1_mul_batch(pts, coef[32 * i * length:32 * (i + 1) * length], length, 8)
+        for j in range(length):
+            acc = port.g1_add_batch(acc, t[64 * j:64 * j + 64], 1)
+        assert (got[i] == acc).all()
