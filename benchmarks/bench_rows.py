@@ -128,8 +128,9 @@ def main():
     # ---- config 3: BSW07 100-attribute decrypt ---------------------------------------------------
     m = 100
     nd = 64 if args.quick else 2048
-    cy = Pn[: nd * m].reshape(nd, m, 64)
-    cyp = Pn[nd * m: 2 * nd * m].reshape(nd, m, 64)
+    big = np.tile(Pn, (2 * nd * m // n + 1, 1))
+    cy = big[: nd * m].reshape(nd, m, 64)
+    cyp = big[nd * m: 2 * nd * m].reshape(nd, m, 64)
     dj, djp = Qn[:m], Qn[m: 2 * m]
     c, d = Pn[-nd:], Qn[-1]
     ctil = gt[:nd] if nd <= ng else np.tile(gt, (nd // ng + 1, 1))[:nd]

@@ -209,62 +209,78 @@ BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
   jac_to_aff(out, acc);
 }
 
-// GT.Exp: generic Fp12 square-and-multiply (no subgroup assumption), k = 256-bit LE; k == 0 -> 1
+// x * conj(y) without materialising conj(y) = (y0, -y1)
+BN_NOINLINE void fp12_mul_conj(Fp12& z, const Fp12& x, const Fp12& y) {
+  Fp6 a, b, s, t;
+  fp6_mul(a, x.c0, y.c0);
+  fp6_mul(b, x.c1, y.c1);
+  fp6_add(s, x.c0, x.c1); fp6_sub(t, y.c0, y.c1);
+  fp6_mul(s, s, t);
+  fp6_sub(s, s, a); fp6_add(z.c1, s, b);
+  fp6_mul_v(b, b); fp6_sub(z.c0, a, b);
+}
+
+// GT.Exp, generic Fp12 (no subgroup assumption), k = 256-bit LE, k == 0 -> 1.  FIXED 2-bit windows (gnark's
+// E12.Exp shape): every lane of a warp multiplies at the same 128 positions, so the SIMT lanes never diverge on
+// the exponent bits -- a bit-serial or sliding-window ladder would make every warp pay for the union of its
+// lanes' multiplications.
 BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
-  Fp12 acc; fp12_set_one(acc);
-  int top = 255;
-  while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1u)) top--;
-  if (top >= 0) {
-    acc = x;
-    for (int i = top - 1; i >= 0; i--) {
-      fp12_sqr(acc, acc);
-      if ((k[i >> 5] >> (i & 31)) & 1u) fp12_mul(acc, acc, x);
+  Fp12 tab[3];  // x, x^2, x^3
+  tab[0] = x;
+  fp12_sqr(tab[1], x);
+  fp12_mul(tab[2], tab[1], x);
+  Fp12 acc;
+  bool started = false;
+  for (int w = 127; w >= 0; w--) {
+    if (started) { fp12_sqr(acc, acc); fp12_sqr(acc, acc); }
+    int d = (int)((k[w >> 4] >> ((w & 15) * 2)) & 3u);
+    if (d) {
+      if (started) fp12_mul(acc, acc, tab[d - 1]);
+      else { acc = tab[d - 1]; started = true; }
     }
   }
+  if (!started) fp12_set_one(acc);
   out = acc;
 }
 
 // GT.Exp for bases in the cyclotomic subgroup (every pairing output and any product / quotient / power of
-// pairing outputs -- all GT.Exp call sites of the reference): Granger-Scott squarings and a
-// width-3 signed window where the inverse is a conjugation.  ~8.3k Fp-mul instead of ~23k for the generic ladder.
+// pairing outputs -- all GT.Exp call sites of the reference): Granger-Scott squarings, FIXED
+// 3-bit signed windows (digits -4..3, inverse = conjugate), table x..x^4: 258 cyclotomic squarings + <= 86
+// products at lane-uniform positions.
 BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
-  // signed width-3 digits of the 256-bit exponent, LSB first (257 digits max)
-  signed char dg[260];
-  uint32_t t[9];
-  for (int i = 0; i < 8; i++) t[i] = k[i];
-  t[8] = 0;
-  int n = 0;
-  bool nz = false;
-  for (int i = 0; i < 9; i++) nz |= t[i] != 0;
-  while (nz) {
-    int d = 0;
-    if (t[0] & 1u) {
-      d = (int)(t[0] & 7u);
-      if (d > 4) d -= 8;
-      // t -= d
-      if (d > 0) { uint64_t b = (uint64_t)d; for (int i = 0; i < 9 && b; i++) { uint64_t v = (uint64_t)t[i] - b; t[i] = (uint32_t)v; b = (v >> 63) & 1u; } }
-      else { uint64_t c = (uint64_t)(-d); for (int i = 0; i < 9 && c; i++) { c += t[i]; t[i] = (uint32_t)c; c >>= 32; } }
+  Fp12 tab[4];  // x, x^2, x^3, x^4
+  tab[0] = x;
+  fp12_cyclo_sqr(tab[1], x);
+  fp12_mul(tab[2], tab[1], x);
+  fp12_cyclo_sqr(tab[3], tab[1]);
+  // recode: k = sum d_i 8^i with d_i in [-4, 3]; 86 digits cover 258 bits (a carry may reach digit 85)
+  signed char dg[87];
+  int carry = 0;
+  for (int i = 0; i < 86; i++) {
+    int bit = 3 * i;
+    int v = carry;
+    if (bit < 256) {
+      uint32_t lo = k[bit >> 5] >> (bit & 31);
+      if ((bit & 31) > 29 && (bit >> 5) + 1 < 8) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+      v += (int)(lo & 7u);  // at bit 255 only one bit exists: lo = k[7] >> 31
     }
-    dg[n++] = (signed char)d;
-    for (int i = 0; i < 8; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 31);
-    t[8] >>= 1;
-    nz = false;
-    for (int i = 0; i < 9; i++) nz |= t[i] != 0;
+    if (v > 3) { v -= 8; carry = 1; } else carry = 0;
+    dg[i] = (signed char)v;
   }
-  if (n == 0) { fp12_set_one(out); return; }
-  Fp12 x3, acc, m;
-  fp12_cyclo_sqr(x3, x); fp12_mul(x3, x3, x);
+  Fp12 acc;
   bool started = false;
-  for (int i = n - 1; i >= 0; i--) {
-    if (started) fp12_cyclo_sqr(acc, acc);
+  for (int i = 85; i >= 0; i--) {
+    if (started) { fp12_cyclo_sqr(acc, acc); fp12_cyclo_sqr(acc, acc); fp12_cyclo_sqr(acc, acc); }
     int d = dg[i];
-    if (d) {
-      int ad = d < 0 ? -d : d;
-      if (ad == 1) m = x; else m = x3;
-      if (d < 0) fp12_conj(m, m);
-      if (started) fp12_mul(acc, acc, m); else { acc = m; started = true; }
+    if (d > 0) {
+      if (started) fp12_mul(acc, acc, tab[d - 1]);
+      else { acc = tab[d - 1]; started = true; }
+    } else if (d < 0) {
+      if (started) fp12_mul_conj(acc, acc, tab[-d - 1]);
+      else { fp12_conj(acc, tab[-d - 1]); started = true; }
     }
   }
+  if (!started) fp12_set_one(acc);
   out = acc;
 }
 

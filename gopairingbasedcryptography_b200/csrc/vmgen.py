@@ -747,7 +747,7 @@ def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, par
 
 
 WINDOW = {1: 0, 2: 20, 3: 30, 4: 40, 6: 60}
-COLD_LIFETIME = 60  # rounds; longer-lived values go to the cold (global, L2-resident) slot space
+COLD_LIFETIME = int(os.environ.get("VM_COLD_LIFETIME", "60"))  # rounds; longer-lived values go to the cold (global, L2-resident) slot space
 
 
 def mont32(v):

@@ -209,3 +209,24 @@ def test_lazy_fp2_product(emu):
     for i in range(n):
         r = o.fp2_mul((A[2 * i], A[2 * i + 1]), (B[2 * i], B[2 * i + 1]))
         assert (o.fp_from_mont_bytes(z[64 * i:64 * i + 32].tobytes()), o.fp_from_mont_bytes(z[64 * i + 32:64 * i + 64].tobytes())) == r
+
+
+def test_gt_exp_fixed_windows(emu):
+    """Lane-uniform fixed-window ladders: generic (2-bit) and cyclotomic (signed 3-bit) vs the oracle's ladder."""
+    ks = common.scalars(12) + [(1 << 256) - 1, 1 << 255, (1 << 255) + 1, 5, 7, 3, 4, 8, (1 << 256) - 8,
+                               int("7" * 64, 16), int("4" * 64, 16), int("c" * 64, 16), int("b6d" * 21 + "b", 16)]
+    n = len(ks)
+    sb = common.scalar_bytes(ks)
+    P, Q, _, _ = common.points(n, seed=55)
+    gt = port.pair_batch(P, Q, n)
+    ref = port.gt_exp_batch(gt, sb, n)
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_gt_cyclo_exp(vp(gt), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == ref).all()
+    emu.emu_gt_exp(vp(gt), sz(1), vp(sb), sz(n), vp(out))
+    assert (out == ref).all()
+    # generic ladder on an element outside the cyclotomic subgroup
+    rng = o.SplitMix64(99)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(12)), dtype=np.uint8).copy()
+    emu.emu_gt_exp(vp(x), sz(0), vp(sb), sz(4), vp(out))
+    assert (out[:384 * 4] == port.gt_exp_base_batch(x, sb[:128], 4)).all()
