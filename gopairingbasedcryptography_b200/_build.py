@@ -14,6 +14,9 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "inline_255": [],
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
+    "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
+    "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],
+    "byval_b4": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_BYVAL_LEAVES"],
     **{"k%dw%d" % (k, w): DEFAULT + ["-DBN254_VM_K=%d" % k, "-DBN254_VM_WARPS=%d" % w]
        for k in (1, 2, 3, 4, 6) for w in (1, 2, 3, 4, 6, 8)},
     "b3": ["-DBN254_MIN_BLOCKS=3"],

@@ -52,6 +52,18 @@ BN_HD Fp2 fp2_mul_xi_i(const Fp2& a) {
   z.a1 = fp_add(fp_add(e1, a.a1), a.a0);
   return z;
 }
+#ifdef BN254_BYVAL_LEAVES
+// operands and results travel in registers across the out-of-line call: Fp2 temporaries of the callers no
+// longer have to live in local memory (ncu: CALL / IADD3 stalls were ~60-95% long-scoreboard on LDL)
+BN_LEAF Fp2 fp2_add(Fp2 a, Fp2 b) { return fp2_add_i(a, b); }
+BN_LEAF Fp2 fp2_sub(Fp2 a, Fp2 b) { return fp2_sub_i(a, b); }
+BN_LEAF Fp2 fp2_dbl(Fp2 a) { return fp2_dbl_i(a); }
+BN_LEAF Fp2 fp2_neg(Fp2 a) { return fp2_neg_i(a); }
+BN_LEAF Fp2 fp2_conj(Fp2 a) { return fp2_conj_i(a); }
+BN_LEAF Fp2 fp2_half(Fp2 a) { return fp2_half_i(a); }
+BN_LEAF Fp2 fp2_mul_fp(Fp2 a, Fp k) { return fp2_mul_fp_i(a, k); }
+BN_LEAF Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_i(a); }
+#else
 BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { return fp2_add_i(a, b); }
 BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return fp2_sub_i(a, b); }
 BN_LEAF Fp2 fp2_dbl(const Fp2& a) { return fp2_dbl_i(a); }
@@ -60,6 +72,7 @@ BN_LEAF Fp2 fp2_conj(const Fp2& a) { return fp2_conj_i(a); }
 BN_LEAF Fp2 fp2_half(const Fp2& a) { return fp2_half_i(a); }
 BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return fp2_mul_fp_i(a, k); }
 BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(a); }
+#endif
 // Karatsuba: 3 Fp products
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
   Fp t0 = FP_MUL(a.a0, b.a0);
@@ -109,8 +122,15 @@ BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_inl(a, b); }
 BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_lazy(a, b); }
 #endif
 // out-of-line bodies shared by every tower routine
+#ifdef BN254_BYVAL_LEAVES
+BN_NOINLINE Fp2 fp2_mul_bv(Fp2 a, Fp2 b) { return fp2_mul_best(a, b); }
+BN_NOINLINE Fp2 fp2_sqr_bv(Fp2 a) { return fp2_sqr_inl(a); }
+BN_HD void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_bv(a, b); }
+BN_HD void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_bv(a); }
+#else
 BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_best(a, b); }
 BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_inl(a); }
+#endif
 BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
 BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
   Fp n = fp_add(fp_sqr(a.a0), fp_sqr(a.a1));
