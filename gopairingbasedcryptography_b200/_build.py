@@ -14,6 +14,7 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "inline_255": [],
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
+    "vmA": DEFAULT, "vmB": DEFAULT, "vmC": DEFAULT, "vmD": DEFAULT,
     "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
     "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],
     "byval_b4": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_BYVAL_LEAVES"],

@@ -111,7 +111,14 @@ BN_HD bool exec_op(const SlotFile& f, uint64_t w, int& dst, Fp2& out) {
     case OP_INV: fp2_inv(out, A); break;
     default: return false;
   }
-  if (do_mul) out = fp2_mul_best(A, B);
+  if (do_mul) {
+    out = fp2_mul_best(A, B);
+    if (op == OP_MUL) {  // fused Karatsuba recombination: (a+a2)(b+b2) - c - e
+      int c = imm, e = (int)((w >> 56) & 0xFF);
+      if (c != SLOT_NONE) out = fp2_sub_i(out, ld_slot(f, c));
+      if (e != SLOT_NONE) out = fp2_sub_i(out, ld_slot(f, e));
+    }
+  }
   return true;
 }
 

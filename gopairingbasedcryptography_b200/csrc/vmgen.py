@@ -113,6 +113,7 @@ class Tracer:
         self.outputs = []
 
     def _mk(self, op, src, imm=0):
+        src = tuple(src) + (None,) * (6 - len(src))  # (a, a2, b, b2, c, e): MUL computes (a+a2)(b+b2) - c - e
         key = (op, tuple(s.id if s is not None else -1 for s in src), imm)
         if op not in (None,) and key in self.cse:
             return self.cse[key]
@@ -197,7 +198,7 @@ class Tracer:
         return self._mk(INV, (a, None, None, None))
 
     def mov(self, a, cold=False):
-        n = Node(len(self.nodes), MOV, (a, None, None, None), 0)  # never CSE'd: used to pin outputs / park values
+        n = Node(len(self.nodes), MOV, (a, None, None, None, None, None), 0)  # never CSE'd: pins outputs / parks values
         n.cold = cold
         self.nodes.append(n)
         a.users.append(n)
@@ -484,6 +485,38 @@ def flat12(x):
 
 
 # ----------------------------------------------------------------------------------------- scheduling
+FUSE_MUL_SUB = os.environ.get("VM_FUSE", "1") == "1"
+
+
+def fuse_mul_sub(t):
+    """Peephole on the DAG: SUB2(m, x, y) / SUB(m, x) where m is a MUL used nowhere else becomes ONE MUL with the
+    subtraction(s) folded in (the Karatsuba cross terms (a1+a2)(b1+b2) - v1 - v2)."""
+    outs = set(v.id for v, _ in t.outputs)
+    fused = 0
+    for n in t.nodes:
+        if n.op not in (SUB, SUB2):
+            continue
+        m = n.src[0]
+        if m is None or m.op != MUL or m.id in outs or len(m.users) != 1 or m.src[4] is not None:
+            continue
+        c = n.src[2]
+        e = n.src[3] if n.op == SUB2 else None
+        if c is m or e is m:
+            continue
+        # rewrite n in place as the fused MUL; m dies (no users)
+        for s_ in n.src:
+            if s_ is not None and n in s_.users:
+                s_.users.remove(n)
+        n.op = MUL
+        n.src = (m.src[0], m.src[1], m.src[2], m.src[3], c, e)
+        for s_ in n.src:
+            if s_ is not None:
+                s_.users.append(n)
+        m.users = []
+        fused += 1
+    return fused
+
+
 def schedule(t, K, window=400):
     """List-schedule into rounds of <= K ops of one opcode.  Returns list of rounds (lists of nodes).
     Ops are taken in trace order (the natural depth-first order of the formulas, which keeps few values
@@ -539,6 +572,14 @@ def schedule(t, K, window=400):
         take = [x for x in lst if x.id <= limit][:K]
         tk = set(x.id for x in take)
         ready[best_op] = [x for x in lst if x.id not in tk]
+        if MIX_ALU and len(take) < K and best_op in ALU_SET:
+            # top up an under-filled add-type round with other eligible add-type ops (cheap divergence)
+            extra = sorted((x for op2, l2 in ready.items() if op2 in ALU_SET and op2 != best_op for x in l2 if x.id <= limit),
+                           key=lambda x: -x.prio)[: K - len(take)]
+            for x in extra:
+                ready[x.op].remove(x)
+                take.append(x)
+                tk.add(x.id)
         scheduled.update(tk)
         r = len(rounds)
         for n in take:
@@ -560,6 +601,10 @@ def schedule(t, K, window=400):
 
 
 COLD_BASE = 160  # slot ids >= COLD_BASE live in global memory (parked values)
+
+
+ALU_SET = {ADD, SUB, SUB2, DBL, NEG, CONJ, MULXI, HALF, MOV, ADDXI, TRIPLE, LDC, SUBXI}
+MIX_ALU = os.environ.get("VM_MIX", "0") == "1"  # measured slower: divergent add-type rounds cost more than the fill they gain
 
 
 def auto_cold(t, rounds, min_lifetime):
@@ -640,7 +685,10 @@ def encode(rounds, K):
             if j < len(ops):
                 n = ops[j]
                 f = [s.slot if s is not None else NONE for s in n.src]
-                w = n.op | (n.slot << 8) | (f[0] << 16) | (f[1] << 24) | (f[2] << 32) | (f[3] << 40) | (n.imm << 48)
+                if n.op == MUL:  # bits 48-55 / 56-63: slots subtracted from the product (NONE = absent)
+                    w = n.op | (n.slot << 8) | (f[0] << 16) | (f[1] << 24) | (f[2] << 32) | (f[3] << 40) | (f[4] << 48) | (f[5] << 56)
+                else:
+                    w = n.op | (n.slot << 8) | (f[0] << 16) | (f[1] << 24) | (f[2] << 32) | (f[3] << 40) | (n.imm << 48)
             else:
                 w = NOP
             words.append(w)
@@ -668,6 +716,11 @@ def evaluate(words, K, nslots, slots_init):
                 B = f2add(B, slots[b2])
             if op == MUL:
                 v = f2mul(A, B)
+                c, e = (w >> 48) & 0xFF, (w >> 56) & 0xFF
+                if c != NONE:
+                    v = f2sub(v, slots[c])
+                if e != NONE:
+                    v = f2sub(v, slots[e])
             elif op == SQR:
                 v = f2mul(A, A)
             elif op == ADD:
@@ -729,6 +782,8 @@ def build_pair_program(K, with_miller=True, with_final_exp=True, window=400, par
     outs = [t.mov(v) for v in flat12(f)]
     for i, v in enumerate(outs):
         t.output(v, "out%d" % i)
+    if FUSE_MUL_SUB:
+        fuse_mul_sub(t)
     rounds = schedule(t, K, window)
     if cold_lifetime:
         auto_cold(t, rounds, cold_lifetime)
