@@ -8,12 +8,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # Default flags = the measured best of the profiles/r1 sweep: out-of-line add-type leaves and Montgomery
-# product (instruction footprint 380 KB -> 100 KB) and 3 CTAs/SM (168 registers): 1.30M -> 2.03M pairings/s.
-DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"]
+# product (instruction footprint 380 KB -> 100 KB), 3 CTAs/SM (168 registers): 1.30M -> 2.03M pairings/s, and the
+# innermost Fp6 temporaries in a per-thread shared-memory scratch: -> 2.11M.
+DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "inline_255": [],
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
+    "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "vmA": DEFAULT, "vmB": DEFAULT, "vmC": DEFAULT, "vmD": DEFAULT,
     "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
     "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],

@@ -24,7 +24,12 @@ constexpr int kBlock = 128;
 #ifndef BN254_MIN_BLOCKS
 #define BN254_MIN_BLOCKS 1
 #endif
-constexpr int kPairChunk = 4;  // pairs per shared-squaring pass inside one thread
+constexpr int kPairChunk = 4;
+#ifdef BN254_SMEM_SCRATCH
+constexpr size_t kTowerSmem = (size_t)kBlock * kScratchStride;  // per-thread Fp2 scratch of the tower routines
+#else
+constexpr size_t kTowerSmem = 0;
+#endif  // pairs per shared-squaring pass inside one thread
 
 template <typename T>
 __device__ __forceinline__ void load_struct(T& dst, const void* base, size_t idx) {
@@ -505,7 +510,7 @@ int run_dev_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out
 // multi-pairing launch: single kernel for small k, split + combine for large k
 template <int MODE>
 cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
-  if (k <= 2 * kMpChunk) { k_multi_pair<MODE><<<grid_for(n), kBlock, 0, s>>>(a, b, n, k, o); return cudaSuccess; }
+  if (k <= 2 * kMpChunk) { k_multi_pair<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, k, o); return cudaSuccess; }
   int nchunks = (k + kMpChunk - 1) / kMpChunk;
   size_t need = n * (size_t)nchunks * BN254_GT_BYTES;
   if (sl.mp_scratch_bytes < need) {
@@ -514,8 +519,8 @@ cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, 
     if (e != cudaSuccess) return e;
     sl.mp_scratch_bytes = need;
   }
-  k_mp_partial<<<grid_for(n * (size_t)nchunks), kBlock, 0, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
-  k_mp_combine<MODE><<<grid_for(n), kBlock, 0, s>>>(sl.mp_scratch, n, nchunks, o);
+  k_mp_partial<<<grid_for(n * (size_t)nchunks), kBlock, kTowerSmem, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
+  k_mp_combine<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(sl.mp_scratch, n, nchunks, o);
   return cudaSuccess;
 }
 // One base, n scalars.  Small batches run the GLV kernel on the broadcast base; from kFixedMin scalars on a
@@ -578,6 +583,15 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
       return BN254_ERR_OOM;
     }
   }
+#ifdef BN254_SMEM_SCRATCH
+  {
+    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
+                                   (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
+                                   (const void*)k_final_exp, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
+    for (const void* k : tower_kernels)
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTowerSmem) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
+  }
+#endif
   const char* impl = getenv("BN254_IMPL");
   ctx->use_vm = impl && std::string(impl) == "vm";  // default: one-thread-per-pairing kernels (faster so far)
   ctx->sms = prop.multiProcessorCount;
@@ -633,13 +647,13 @@ void bn254_generators(void* g1, void* g2) {
 // ---- pairings -------------------------------------------------------------------------------
 int bn254_pair_batch_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, void* d_out, void* stream) {
   if (ctx && ctx->use_vm) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);
-  return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
+  return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
 }
 int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, void* out) {
   return run_host(ctx, {P, BN254_G1_BYTES, false}, {Q, BN254_G2_BYTES, false}, out, BN254_GT_BYTES, n,
                   [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {
                     if (ctx->use_vm) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);
-                    else k_pair<<<grid_for(c), kBlock, 0, s>>>(a, b, c, o);
+                    else k_pair<<<grid_for(c), kBlock, kTowerSmem, s>>>(a, b, c, o);
                   });
 }
 #define MULTI_PAIR_ENTRY(name, MODE, OUT_BYTES, OUT_T)                                                                     \
@@ -665,13 +679,13 @@ MULTI_PAIR_ENTRY(bn254_pairing_check_batch, 2, 1, uint8_t)
 
 int bn254_final_exp_batch_dev(bn254_ctx* ctx, const void* d_in, size_t n, void* d_out, void* stream) {
   if (ctx && ctx->use_vm) return run_dev_vm<VmProgFinalExp>(ctx, d_in, nullptr, n, d_out, (cudaStream_t)stream);
-  return run_dev(ctx, n, [&] { k_final_exp<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_in, n, d_out); });
+  return run_dev(ctx, n, [&] { k_final_exp<<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(d_in, n, d_out); });
 }
 int bn254_final_exp_batch(bn254_ctx* ctx, const void* in, size_t n, void* out) {
   return run_host(ctx, {in, BN254_GT_BYTES, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
                   [ctx](const void* a, const void*, size_t c, void* o, cudaStream_t s, uint4* cold) {
                     if (ctx->use_vm) launch_vm<VmProgFinalExp>(ctx, a, nullptr, c, o, cold, s);
-                    else k_final_exp<<<grid_for(c), kBlock, 0, s>>>(a, c, o);
+                    else k_final_exp<<<grid_for(c), kBlock, kTowerSmem, s>>>(a, c, o);
                   });
 }
 
@@ -776,31 +790,31 @@ int bn254_g2_add_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, v
 
 // ---- GT ---------------------------------------------------------------------------------------
 int bn254_gt_exp_batch_dev(bn254_ctx* ctx, const void* d_x, size_t stride, const void* d_k, size_t n, void* d_out, void* stream) {
-  return run_dev(ctx, n, [&] { k_gt_exp<0><<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(d_x, stride, d_k, n, d_out); });
+  return run_dev(ctx, n, [&] { k_gt_exp<0><<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(d_x, stride, d_k, n, d_out); });
 }
 int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
 }
 int bn254_gt_cyclo_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, 0, s>>>(a, 1, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_cyclo_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, 0, s>>>(a, 0, b, c, o); });
+                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
 }
 int bn254_gt_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<0><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(x, y, c, o); });
 }
 int bn254_gt_div_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<1><<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+                  [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_mul<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(x, y, c, o); });
 }
 int bn254_fp_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, 32, false}, {b, 32, false}, out, 32, n,

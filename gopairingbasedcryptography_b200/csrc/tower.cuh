@@ -15,6 +15,28 @@ namespace bn254 {
 struct Fp6 { Fp2 b0, b1, b2; };
 struct Fp12 { Fp6 c0, c1; };
 
+// 128-bit operand access for the out-of-line leaves: their reference parameters are generic pointers (local
+// stack or the shared-memory scratch); word-wise generic loads cost 4x the LSU instructions and 4-way bank
+// conflicts on the 592-byte scratch stride.
+#if defined(__CUDACC__)
+BN_D Fp2 fp2_ld(const Fp2& r) {
+  Fp2 v;
+  const uint4* p = reinterpret_cast<const uint4*>(&r);
+  uint4* d = reinterpret_cast<uint4*>(&v);
+  d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+  return v;
+}
+BN_D void fp2_st(Fp2& r, const Fp2& v) {
+  uint4* p = reinterpret_cast<uint4*>(&r);
+  const uint4* d = reinterpret_cast<const uint4*>(&v);
+  p[0] = d[0]; p[1] = d[1]; p[2] = d[2]; p[3] = d[3];
+}
+BN_D Fp fp_ld(const Fp& r) { Fp v; const uint4* p = reinterpret_cast<const uint4*>(&r); uint4* d = reinterpret_cast<uint4*>(&v); d[0] = p[0]; d[1] = p[1]; return v; }
+#else
+BN_D Fp2 fp2_ld(const Fp2& r) { return r; }
+BN_D void fp2_st(Fp2& r, const Fp2& v) { r = v; }
+BN_D Fp fp_ld(const Fp& r) { return r; }
+#endif
 // Add-type Fp2 leaves: inline by default; -DBN254_OOL_ADDS makes them out-of-line calls, trading
 // call overhead for a much smaller instruction footprint (ncu: k_pair v1 stalls on no_instruction).
 #ifdef BN254_OOL_ADDS
@@ -64,14 +86,14 @@ BN_LEAF Fp2 fp2_half(Fp2 a) { return fp2_half_i(a); }
 BN_LEAF Fp2 fp2_mul_fp(Fp2 a, Fp k) { return fp2_mul_fp_i(a, k); }
 BN_LEAF Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_i(a); }
 #else
-BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { return fp2_add_i(a, b); }
-BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return fp2_sub_i(a, b); }
-BN_LEAF Fp2 fp2_dbl(const Fp2& a) { return fp2_dbl_i(a); }
-BN_LEAF Fp2 fp2_neg(const Fp2& a) { return fp2_neg_i(a); }
-BN_LEAF Fp2 fp2_conj(const Fp2& a) { return fp2_conj_i(a); }
-BN_LEAF Fp2 fp2_half(const Fp2& a) { return fp2_half_i(a); }
-BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return fp2_mul_fp_i(a, k); }
-BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(a); }
+BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { return fp2_add_i(fp2_ld(a), fp2_ld(b)); }
+BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return fp2_sub_i(fp2_ld(a), fp2_ld(b)); }
+BN_LEAF Fp2 fp2_dbl(const Fp2& a) { return fp2_dbl_i(fp2_ld(a)); }
+BN_LEAF Fp2 fp2_neg(const Fp2& a) { return fp2_neg_i(fp2_ld(a)); }
+BN_LEAF Fp2 fp2_conj(const Fp2& a) { return fp2_conj_i(fp2_ld(a)); }
+BN_LEAF Fp2 fp2_half(const Fp2& a) { return fp2_half_i(fp2_ld(a)); }
+BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return fp2_mul_fp_i(fp2_ld(a), fp_ld(k)); }
+BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(fp2_ld(a)); }
 #endif
 // Karatsuba: 3 Fp products
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
@@ -128,8 +150,8 @@ BN_NOINLINE Fp2 fp2_sqr_bv(Fp2 a) { return fp2_sqr_inl(a); }
 BN_HD void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_bv(a, b); }
 BN_HD void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_bv(a); }
 #else
-BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_best(a, b); }
-BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_inl(a); }
+BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { fp2_st(z, fp2_mul_best(fp2_ld(a), fp2_ld(b))); }
+BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { fp2_st(z, fp2_sqr_inl(fp2_ld(a))); }
 #endif
 BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
 BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
@@ -139,6 +161,19 @@ BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
   z = r;
 }
 
+// -DBN254_SMEM_SCRATCH: the Fp2 temporaries of the innermost composite routines (fp6_mul, fp6_mul_01,
+// fp12_cyclo_sqr) live in a per-thread slice of dynamic shared memory instead of the local-memory stack
+// (ncu: the 7 KB/thread stack drives 3 TB/s of DRAM traffic and a third of all stall samples).  9 slots of
+// 64 B, thread stride 592 B = 16 B x 37 (odd) so 128-bit accesses of a quarter-warp hit distinct bank quads.
+constexpr int kScratchSlots = 9;
+constexpr int kScratchStride = 592;
+#if defined(BN254_SMEM_SCRATCH) && defined(__CUDACC__)
+extern __shared__ uint4 bn_dyn_smem[];
+BN_D Fp2* bn_scratch() { return reinterpret_cast<Fp2*>(reinterpret_cast<char*>(bn_dyn_smem) + threadIdx.x * kScratchStride); }
+#define BN_SCRATCH_DECL Fp2* sc_ = bn_scratch();
+#else
+#define BN_SCRATCH_DECL Fp2 sc_[kScratchSlots];
+#endif
 // ------------------------------------------------------------------------------------------ Fp6
 BN_HD void fp6_add(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_add(x.b0, y.b0); z.b1 = fp2_add(x.b1, y.b1); z.b2 = fp2_add(x.b2, y.b2); }
 BN_HD void fp6_sub(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_sub(x.b0, y.b0); z.b1 = fp2_sub(x.b1, y.b1); z.b2 = fp2_sub(x.b2, y.b2); }
@@ -146,17 +181,21 @@ BN_HD void fp6_neg(Fp6& z, const Fp6& x) { z.b0 = fp2_neg(x.b0); z.b1 = fp2_neg(
 BN_HD void fp6_mul_v(Fp6& z, const Fp6& x) { Fp2 t = fp2_mul_xi(x.b2); z.b2 = x.b1; z.b1 = x.b0; z.b0 = t; }
 // Karatsuba, 6 Fp2 products.  z may alias x or y.
 BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
-  Fp2 v0, v1, v2, t, u0, u1, u2;
+  BN_SCRATCH_DECL
+  Fp2 &v0 = sc_[0], &v1 = sc_[1], &v2 = sc_[2], &t = sc_[3], &u0 = sc_[4], &u1 = sc_[5], &s1 = sc_[6], &s2 = sc_[7];
   fp2_mul(v0, x.b0, y.b0);
   fp2_mul(v1, x.b1, y.b1);
   fp2_mul(v2, x.b2, y.b2);
-  fp2_mul(t, fp2_add(x.b1, x.b2), fp2_add(y.b1, y.b2));
+  s1 = fp2_add(x.b1, x.b2); s2 = fp2_add(y.b1, y.b2);
+  fp2_mul(t, s1, s2);
   u0 = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(t, v1), v2)), v0);
-  fp2_mul(t, fp2_add(x.b0, x.b1), fp2_add(y.b0, y.b1));
+  s1 = fp2_add(x.b0, x.b1); s2 = fp2_add(y.b0, y.b1);
+  fp2_mul(t, s1, s2);
   u1 = fp2_add(fp2_sub(fp2_sub(t, v0), v1), fp2_mul_xi(v2));
-  fp2_mul(t, fp2_add(x.b0, x.b2), fp2_add(y.b0, y.b2));
-  u2 = fp2_add(fp2_sub(fp2_sub(t, v0), v2), v1);
-  z.b0 = u0; z.b1 = u1; z.b2 = u2;
+  s1 = fp2_add(x.b0, x.b2); s2 = fp2_add(y.b0, y.b2);
+  fp2_mul(t, s1, s2);
+  z.b2 = fp2_add(fp2_sub(fp2_sub(t, v0), v2), v1);  // x, y are fully consumed: z may alias them
+  z.b0 = u0; z.b1 = u1;
 }
 BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
   Fp2 r0, r1, r2;
@@ -165,16 +204,20 @@ BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
 }
 // x * (c0 + c1 v), 5 Fp2 products
 BN_NOINLINE void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& c0, const Fp2& c1) {
-  Fp2 a, b, t, r0, r1, r2;
+  BN_SCRATCH_DECL
+  Fp2 &a = sc_[0], &b = sc_[1], &t = sc_[2], &r0 = sc_[3], &r2 = sc_[4], &s1 = sc_[5], &s2 = sc_[6];
   fp2_mul(a, x.b0, c0);
   fp2_mul(b, x.b1, c1);
-  fp2_mul(t, fp2_add(x.b1, x.b2), c1);
+  s1 = fp2_add(x.b1, x.b2);
+  fp2_mul(t, s1, c1);
   r0 = fp2_add(fp2_mul_xi(fp2_sub(t, b)), a);
-  fp2_mul(t, fp2_add(x.b0, x.b2), c0);
+  s1 = fp2_add(x.b0, x.b2);
+  fp2_mul(t, s1, c0);
   r2 = fp2_add(fp2_sub(t, a), b);
-  fp2_mul(t, fp2_add(x.b0, x.b1), fp2_add(c0, c1));
-  r1 = fp2_sub(fp2_sub(t, a), b);
-  z.b0 = r0; z.b1 = r1; z.b2 = r2;
+  s1 = fp2_add(x.b0, x.b1); s2 = fp2_add(c0, c1);
+  fp2_mul(t, s1, s2);
+  z.b1 = fp2_sub(fp2_sub(t, a), b);
+  z.b0 = r0; z.b2 = r2;
 }
 BN_NOINLINE void fp6_inv(Fp6& z, const Fp6& x) {
   Fp2 t0, t1, t2, s, n;
@@ -240,26 +283,28 @@ BN_NOINLINE void fp12_frob(Fp12& z, const Fp12& x, int k) {
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
 // exponentiation).  Fp12 = Fp4[w]/(w^3 - s), s = w^3, s^2 = xi; z = A + B w + C w^2 with
 // A=(g0,g3) B=(g1,g4) C=(g2,g5):  z^2 = (3A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.
-BN_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b) {
-  Fp2 a2, b2, s;
+BN_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b, Fp2* tmp) {
+  Fp2 &a2 = tmp[0], &b2 = tmp[1], &s = tmp[2];
   fp2_sqr(a2, a); fp2_sqr(b2, b);
-  fp2_sqr(s, fp2_add(a, b));
+  s = fp2_add(a, b);
+  fp2_sqr(s, s);
   r1 = fp2_sub(fp2_sub(s, a2), b2);
   r0 = fp2_add(a2, fp2_mul_xi(b2));
 }
 BN_NOINLINE void fp12_cyclo_sqr(Fp12& z, const Fp12& x) {
-  Fp2 a0, a1, b0, b1, c0, c1;
-  fp4_sqr(a0, a1, x.c0.b0, x.c1.b1);
-  fp4_sqr(b0, b1, x.c1.b0, x.c0.b2);
-  fp4_sqr(c0, c1, x.c0.b1, x.c1.b2);
+  BN_SCRATCH_DECL
+  Fp2 &a0 = sc_[0], &a1 = sc_[1], &b0 = sc_[2], &b1 = sc_[3], &c0 = sc_[4], &c1 = sc_[5];
+  fp4_sqr(a0, a1, x.c0.b0, x.c1.b1, sc_ + 6);
+  fp4_sqr(b0, b1, x.c1.b0, x.c0.b2, sc_ + 6);
+  fp4_sqr(c0, c1, x.c0.b1, x.c1.b2, sc_ + 6);
   c1 = fp2_mul_xi(c1);
-  Fp2 g0 = x.c0.b0, g1 = x.c1.b0, g2 = x.c0.b1, g3 = x.c1.b1, g4 = x.c0.b2, g5 = x.c1.b2;
-  z.c0.b0 = fp2_add(fp2_dbl(fp2_sub(a0, g0)), a0);  // 3 a0 - 2 g0
-  z.c1.b1 = fp2_add(fp2_dbl(fp2_add(a1, g3)), a1);  // 3 a1 + 2 g3
-  z.c0.b1 = fp2_add(fp2_dbl(fp2_sub(b0, g2)), b0);
-  z.c1.b2 = fp2_add(fp2_dbl(fp2_add(b1, g5)), b1);
-  z.c1.b0 = fp2_add(fp2_dbl(fp2_add(c1, g1)), c1);  // 3 xi c1 + 2 g1
-  z.c0.b2 = fp2_add(fp2_dbl(fp2_sub(c0, g4)), c0);  // 3 c0 - 2 g4
+  // every g_i of x is read only by its own output coefficient, so z may alias x without copies
+  z.c0.b0 = fp2_add(fp2_dbl(fp2_sub(a0, x.c0.b0)), a0);  // 3 a0 - 2 g0
+  z.c1.b1 = fp2_add(fp2_dbl(fp2_add(a1, x.c1.b1)), a1);  // 3 a1 + 2 g3
+  z.c0.b1 = fp2_add(fp2_dbl(fp2_sub(b0, x.c0.b1)), b0);
+  z.c1.b2 = fp2_add(fp2_dbl(fp2_add(b1, x.c1.b2)), b1);
+  z.c1.b0 = fp2_add(fp2_dbl(fp2_add(c1, x.c1.b0)), c1);  // 3 xi c1 + 2 g1
+  z.c0.b2 = fp2_add(fp2_dbl(fp2_sub(c0, x.c0.b2)), c0);  // 3 c0 - 2 g4
 }
 // z *= l0 + l1 w + l3 w^3  (sparse "034" line), 13 Fp2 products
 BN_NOINLINE void fp12_mul_034(Fp12& z, const Fp2& l0, const Fp2& l1, const Fp2& l3) {
