@@ -16,6 +16,7 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "inline_255": [],
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
+    "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH"],
     "vmA": DEFAULT, "vmB": DEFAULT, "vmC": DEFAULT, "vmD": DEFAULT,
     "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
     "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],

@@ -108,8 +108,18 @@ BN_HD Fp fp_sub(const Fp& a, const Fp& b) {
   t.l[0] = sub_cc(a.l[0], b.l[0]); t.l[1] = subc_cc(a.l[1], b.l[1]); t.l[2] = subc_cc(a.l[2], b.l[2]); t.l[3] = subc_cc(a.l[3], b.l[3]);
   t.l[4] = subc_cc(a.l[4], b.l[4]); t.l[5] = subc_cc(a.l[5], b.l[5]); t.l[6] = subc_cc(a.l[6], b.l[6]); t.l[7] = subc_cc(a.l[7], b.l[7]);
   uint32_t borrow = subc(0u, 0u);  // all-ones iff a < b
+#if defined(__CUDACC__)
+  // add p back under a predicate: 8 predicated adds instead of 8 masks + 8 adds
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %8, 0;\n\t"
+      "@q add.cc.u32 %0, %0, %9;\n\t@q addc.cc.u32 %1, %1, %10;\n\t@q addc.cc.u32 %2, %2, %11;\n\t@q addc.cc.u32 %3, %3, %12;\n\t"
+      "@q addc.cc.u32 %4, %4, %13;\n\t@q addc.cc.u32 %5, %5, %14;\n\t@q addc.cc.u32 %6, %6, %15;\n\t@q addc.u32 %7, %7, %16;\n\t}"
+      : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]), "+r"(t.l[7])
+      : "r"(borrow), "r"(P0), "r"(P1), "r"(P2), "r"(P3), "r"(P4), "r"(P5), "r"(P6), "r"(P7));
+#else
   t.l[0] = add_cc(t.l[0], P0 & borrow); t.l[1] = addc_cc(t.l[1], P1 & borrow); t.l[2] = addc_cc(t.l[2], P2 & borrow); t.l[3] = addc_cc(t.l[3], P3 & borrow);
   t.l[4] = addc_cc(t.l[4], P4 & borrow); t.l[5] = addc_cc(t.l[5], P5 & borrow); t.l[6] = addc_cc(t.l[6], P6 & borrow); t.l[7] = addc(t.l[7], P7 & borrow);
+#endif
   return t;
 }
 BN_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }  // -0 = 0 (borrow never set)

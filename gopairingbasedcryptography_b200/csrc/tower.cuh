@@ -99,7 +99,7 @@ BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(fp2_ld(a)); }
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
   Fp t0 = FP_MUL(a.a0, b.a0);
   Fp t1 = FP_MUL(a.a1, b.a1);
-  Fp m = FP_MUL(fp_add(a.a0, a.a1), fp_add(b.a0, b.a1));
+  Fp m = FP_MUL(fp_add_noreduce(a.a0, a.a1), fp_add_noreduce(b.a0, b.a1));  // operands < 2p are fine for the product
   Fp2 z;
   z.a0 = fp_sub(t0, t1);
   z.a1 = fp_sub(fp_sub(m, t0), t1);
@@ -133,7 +133,7 @@ BN_HD Fp2 fp2_mul_lazy(const Fp2& a, const Fp2& b) {
 BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
   Fp m = FP_MUL(a.a0, a.a1);
   Fp2 z;
-  z.a0 = FP_MUL(fp_add(a.a0, a.a1), fp_sub(a.a0, a.a1));
+  z.a0 = FP_MUL(fp_add_noreduce(a.a0, a.a1), fp_sub(a.a0, a.a1));
   z.a1 = fp_dbl(m);
   return z;
 }
