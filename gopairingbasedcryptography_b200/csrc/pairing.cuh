@@ -24,7 +24,8 @@ BN_HD bool g2_is_inf(const G2Aff& q) { return fp2_is_zero(q.x) && fp2_is_zero(q.
 //   X3 = XY/2 (Y^2 - 3E), Y3 = ((Y^2+3E)/2)^2 - 3E^2, Z3 = 2Y^3Z
 //   line (times a subfield factor) = (-2YZ) yP + (3X^2) xP w + (E - Y^2) w^3
 BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
-  Fp2 A, B, C, E, F, G, H, J, t;
+  BN_SCRATCH_DECL
+  Fp2 &A = sc_[0], &B = sc_[1], &C = sc_[2], &E = sc_[3], &F = sc_[4], &G = sc_[5], &H = sc_[6], &J = sc_[7], &t = sc_[8];
   fp2_mul(A, T.x, T.y); A = fp2_half(A);
   fp2_sqr(B, T.y);
   fp2_sqr(C, T.z);
@@ -45,7 +46,9 @@ BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
 // Chord through T and affine Q, T <- T + Q.  O = Y1 - y2 Z1, L = X1 - x2 Z1:
 //   line = L yP - O xP w + (O x2 - L y2) w^3
 BN_NOINLINE void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, bool update) {
-  Fp2 O, L, C, D, E, F, G, H, t, t1;
+  BN_SCRATCH_DECL
+  Fp2 &O = sc_[0], &L = sc_[1], &C = sc_[2], &D = sc_[3], &E = sc_[4], &F = sc_[5], &G = sc_[6], &H = sc_[7], &t = sc_[8];
+  Fp2 t1;
   fp2_mul(t, Q.y, T.z); O = fp2_sub(T.y, t);
   fp2_mul(t, Q.x, T.z); L = fp2_sub(T.x, t);
   fp2_mul(t, L, Q.y); fp2_mul(t1, Q.x, O);
