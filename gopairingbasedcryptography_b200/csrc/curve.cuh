@@ -179,17 +179,18 @@ BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& be
   p2.x = f_mul_beta(base.x, beta); p2.y = base.y;
   if (n1) p1.y = f_neg(p1.y);
   if (n2) p2.y = f_neg(p2.y);
-  J p3; p3.x = p1.x; p3.y = p1.y; f_set_one(p3.z);
-  jac_add_aff(p3, p3, p2);
+  // table {P1, P2, P1+P2} in Jacobian form, indexed by the joint bit pair: every lane of a warp runs the SAME
+  // doubling + one Jacobian addition per bit (a data-dependent choice between three addition paths would make
+  // each warp execute all of them)
+  J tab[3];
+  tab[0].x = p1.x; tab[0].y = p1.y; f_set_one(tab[0].z);
+  tab[1].x = p2.x; tab[1].y = p2.y; f_set_one(tab[1].z);
+  jac_add_aff(tab[2], tab[0], p2);
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
-  int top = GLV_MAX_BITS - 1;
-  while (top >= 0 && !(((k1[top >> 5] | k2[top >> 5]) >> (top & 31)) & 1u)) top--;
-  for (int i = top; i >= 0; i--) {
+  for (int i = GLV_MAX_BITS - 1; i >= 0; i--) {
     jac_dbl(acc, acc);
     int b = (int)((k1[i >> 5] >> (i & 31)) & 1u) | ((int)((k2[i >> 5] >> (i & 31)) & 1u) << 1);
-    if (b == 1) jac_add_aff(acc, acc, p1);
-    else if (b == 2) jac_add_aff(acc, acc, p2);
-    else if (b == 3) jac_add(acc, acc, p3);
+    if (b) jac_add(acc, acc, tab[b - 1]);
   }
   jac_to_aff(out, acc);
 }
