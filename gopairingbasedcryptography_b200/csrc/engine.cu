@@ -56,8 +56,12 @@ __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t fir
   for (int base = 0; base < k; base += kPairChunk) {
     int c = min(kPairChunk, k - base);
     for (int j = 0; j < c; j++) { load_struct(p[j], P, first + base + j); load_struct(q[j], Q, first + base + j); }
-    if (!have) { miller_loop(f, p, q, T, c); have = true; }
-    else { Fp12 g; miller_loop(g, p, q, T, c); fp12_mul(f, f, g); }
+    Fp12 g;
+    Fp12& dst = have ? g : f;
+    if (c == kPairChunk) miller_loop_t<kPairChunk>(dst, p, q, T, c);  // full passes: compile-time pair count
+    else miller_loop_t<0>(dst, p, q, T, c);
+    if (have) fp12_mul(f, f, g);
+    have = true;
   }
 }
 
@@ -70,6 +74,20 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P
   miller_loop(f, &p, &q, &T, 1);
   final_exp(f, f);
   store_struct(out, i, f);
+}
+// small products with a compile-time pair count (BLS verify: KC = 2): the pair loop unrolls
+template <int MODE, int KC>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair_c(const void* P, const void* Q, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Aff p[KC]; G2Aff q[KC]; G2Proj T[KC];
+#pragma unroll
+  for (int j = 0; j < KC; j++) { load_struct(p[j], P, i * KC + j); load_struct(q[j], Q, i * KC + j); }
+  Fp12 f;
+  miller_loop_t<KC>(f, p, q, T, KC);
+  if (MODE >= 1) final_exp(f, f);
+  if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
+  else store_struct(out, i, f);
 }
 // mode 0: Miller product only; 1: + final exponentiation; 2: pairing check (writes one byte)
 template <int MODE>
@@ -510,6 +528,9 @@ int run_dev_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out
 // multi-pairing launch: single kernel for small k, split + combine for large k
 template <int MODE>
 cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
+  if (k == 1) { k_multi_pair_c<MODE, 1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
+  if (k == 2) { k_multi_pair_c<MODE, 2><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
+  if (k == 3) { k_multi_pair_c<MODE, 3><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
   if (k <= 2 * kMpChunk) { k_multi_pair<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, k, o); return cudaSuccess; }
   int nchunks = (k + kMpChunk - 1) / kMpChunk;
   size_t need = n * (size_t)nchunks * BN254_GT_BYTES;
@@ -585,7 +606,9 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
 #ifdef BN254_SMEM_SCRATCH
   {
-    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
+    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_multi_pair_c<0, 1>, (const void*)k_multi_pair_c<1, 1>, (const void*)k_multi_pair_c<2, 1>,
+                                   (const void*)k_multi_pair_c<0, 2>, (const void*)k_multi_pair_c<1, 2>, (const void*)k_multi_pair_c<2, 2>,
+                                   (const void*)k_multi_pair_c<0, 3>, (const void*)k_multi_pair_c<1, 3>, (const void*)k_multi_pair_c<2, 3>, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
                                    (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
                                    (const void*)k_final_exp, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
     for (const void* k : tower_kernels)

@@ -71,37 +71,38 @@ BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, con
   fp12_mul_034(f, fp2_mul_fp(r0, P.y), fp2_mul_fp(r1, P.x), r2);
 }
 
-// f *= Miller function of one pair.  Used with f = running product: the caller squares f between
-// NAF digits.  For the single-pair and small-k paths we run the digits inside (shared squarings).
-// P, Q: k pairs (pairs containing infinity are skipped).  T: scratch of k projective points.
-BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
+// Product of the Miller functions of k pairs with shared squarings (pairs containing infinity are skipped).
+// KC > 0: k == KC is a compile-time constant (loops over the pairs unroll, T[j] indexing is static);
+// KC == 0: run-time k.  T: scratch of k projective points.
+template <int KC>
+BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k_rt) {
+  const int k = KC > 0 ? KC : k_rt;
   fp12_set_one(f);
-  int live = 0;
+  unsigned skip = 0;  // bit j set: pair j contains the point at infinity
   for (int j = 0; j < k; j++) {
-    bool skip = g1_is_inf(P[j]) || g2_is_inf(Q[j]);
-    T[j].x = Q[j].x; T[j].y = Q[j].y;
-    T[j].z = skip ? fp2_zero() : fp2_one();  // z == 0 marks a skipped pair
-    live += skip ? 0 : 1;
+    if (g1_is_inf(P[j]) || g2_is_inf(Q[j])) skip |= 1u << j;
+    T[j].x = Q[j].x; T[j].y = Q[j].y; T[j].z = fp2_one();
   }
-  if (live == 0) return;
+  if (skip == (k >= 32 ? 0xffffffffu : ((1u << k) - 1u))) return;
   Fp2 r0, r1, r2;
   for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
     if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
     int d = ATE_NAF[i];
+#pragma unroll
     for (int j = 0; j < k; j++) {
-      if (fp2_is_zero(T[j].z)) continue;
+      if ((skip >> j) & 1u) continue;
       g2_dbl_step(T[j], r0, r1, r2);
       apply_line(f, P[j], r0, r1, r2);
       if (d) {
-        G2Aff q = Q[j];
-        if (d < 0) q.y = fp2_neg(q.y);
-        g2_add_step(T[j], q, r0, r1, r2, true);
+        if (d > 0) g2_add_step(T[j], Q[j], r0, r1, r2, true);
+        else { G2Aff q; q.x = Q[j].x; q.y = fp2_neg(Q[j].y); g2_add_step(T[j], q, r0, r1, r2, true); }
         apply_line(f, P[j], r0, r1, r2);
       }
     }
   }
+#pragma unroll
   for (int j = 0; j < k; j++) {
-    if (fp2_is_zero(T[j].z)) continue;
+    if ((skip >> j) & 1u) continue;
     G2Aff q1, q2;
     fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
     fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
@@ -111,6 +112,10 @@ BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k
     g2_add_step(T[j], q2, r0, r1, r2, false);
     apply_line(f, P[j], r0, r1, r2);
   }
+}
+BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
+  if (k == 1) miller_loop_t<1>(f, P, Q, T, 1);
+  else miller_loop_t<0>(f, P, Q, T, k);
 }
 
 // z^(d'), d' = 2x0(6x0^2+3x0+1)(p^12-1)/r.  Returns 1 early when the easy part is 1 (gnark behaviour).
