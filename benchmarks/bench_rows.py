@@ -153,6 +153,12 @@ def main():
     cpu = cdn / (time.perf_counter() - t0)
     row("bsw07_decrypt", "decryptions/s", nd, sec, cpu, "%d decryptions, unfused reference flow without its debug pairing" % cdn,
         "config 3: 200 G1 GLV mults + 201-pair Miller product + 1 final exp per decryption")
+    key = schemes.bsw07_key_lines(eng, dj, djp, d)
+    sec, out_l = timed(lambda: schemes.bsw07_decrypt_batch(eng, cy, cyp, dj, djp, c, d, ctil, deltas, lines=key), 1)
+    assert (out_l == out).all()
+    WORK["bsw07_decrypt_lines"] = WORK["bsw07_decrypt"]
+    row("bsw07_decrypt_lines", "decryptions/s", nd, sec, cpu, "same CPU sample as bsw07_decrypt",
+        "config 3 with the user key's 201 G2 points as precomputed line tables (no G2 arithmetic per ciphertext)")
     # ---- config 4: Waters05 encrypt -------------------------------------------------------------------
     import hashlib
     nw = 1 << (12 if args.quick else 16)

@@ -12,7 +12,8 @@ SYMBOLS = [
     "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_device_count", "bn254_host_alloc",
     "bn254_host_free", "bn254_launch_count", "bn254_generators",
     "bn254_pair_batch", "bn254_pair_batch_dev", "bn254_multi_pair_batch", "bn254_multi_pair_batch_dev",
-    "bn254_pairing_check_batch", "bn254_pairing_check_batch_dev", "bn254_miller_loop_batch",
+    "bn254_pairing_check_batch", "bn254_pairing_check_batch_dev", "bn254_g2_lines_create", "bn254_g2_lines_destroy",
+    "bn254_g2_lines_count", "bn254_multi_pair_lines_batch", "bn254_miller_loop_batch",
     "bn254_final_exp_batch", "bn254_miller_loop_batch_dev", "bn254_final_exp_batch_dev",
     "bn254_g1_mul_batch", "bn254_g2_mul_batch", "bn254_g1_mul_base_batch", "bn254_g2_mul_base_batch",
     "bn254_g1_mul_batch_dev", "bn254_g2_mul_batch_dev", "bn254_g1_add_batch", "bn254_g2_add_batch", "bn254_g1_subset_sum_batch", "bn254_g2_subset_sum_batch",

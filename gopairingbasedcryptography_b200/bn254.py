@@ -142,6 +142,29 @@ class Engine:
         out, n = self._kpairs("bn254_pairing_check_batch", P, Q, k, 1)
         return out.astype(bool)
 
+    def g2_lines_create(self, Q):
+        """Precompute the Miller-loop line tables of m fixed G2 points (kept on the GPU); returns a handle."""
+        Q = _u8(Q, G2_BYTES, "Q")
+        m = Q.size // G2_BYTES
+        h = ctypes.c_void_p()
+        fn = self._lib.bn254_g2_lines_create
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, Q.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(m), ctypes.byref(h)))
+        return G2Lines(self, h, m)
+
+    def multi_pair_lines_batch(self, P, lines):
+        """n products of m pairings against the m table points: P is (n*m, 64) -> (n, 384)."""
+        P = _u8(P, G1_BYTES, "P")
+        m = lines.m
+        if lines.engine is not self or (P.size // G1_BYTES) % m:
+            raise ValueError("invalid inputs sizes")
+        n = P.size // G1_BYTES // m
+        out = np.empty(n * GT_BYTES, dtype=np.uint8)
+        fn = self._lib.bn254_multi_pair_lines_batch
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, P.ctypes.data_as(ctypes.c_void_p), lines.handle, ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(n, GT_BYTES)
+
     def final_exp_batch(self, f):
         f = _u8(f, GT_BYTES, "f")
         n = f.size // GT_BYTES
@@ -288,6 +311,27 @@ class Engine:
     def gt_exp_batch_dev(self, d_x, stride, d_k, n, d_out, stream=0):
         self._dev("bn254_gt_exp_batch_dev", ctypes.c_void_p(d_x), ctypes.c_size_t(stride), ctypes.c_void_p(d_k),
                   ctypes.c_size_t(n), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+
+class G2Lines:
+    """Handle of a device-resident line table (bn254_lines)."""
+
+    def __init__(self, engine, handle, m):
+        self.engine, self.handle, self.m = engine, handle, m
+
+    def close(self):
+        if self.handle:
+            fn = self.engine._lib.bn254_g2_lines_destroy
+            fn.argtypes = [ctypes.c_void_p]
+            fn.restype = None
+            fn(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default = None

@@ -125,6 +125,49 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_combine(const v
   if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
   else store_struct(out, i, f);
 }
+// ---- precomputed G2 lines (fixed G2 points: user keys / public parameters) ---------------------------------
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_g2_lines(const void* Q, size_t m, Fp2* table, uint8_t* qskip) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  G2Aff q; load_struct(q, Q, j);
+  bool inf = g2_is_inf(q);
+  qskip[j] = inf ? 1 : 0;
+  if (!inf) g2_precompute_lines(q, table + j * (size_t)kLinesPerPoint * 3);
+}
+// Partial Miller products from line tables.  Grid: x = blocks of kBlock items, y = groups of kMpChunk pairs.
+// Every thread of a CTA walks the SAME pairs, so each line read is one warp-uniform (broadcast) load of 192 B
+// served by L1; P[i][j] is the only per-thread operand.  out: partial[i * nchunks + chunk].
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const void* P, const Fp2* __restrict__ table, const uint8_t* __restrict__ qskip,
+                                                                          size_t n, int m, int nchunks, void* partial) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int ci = blockIdx.y;
+  if (i >= n) return;
+  int first = ci * kMpChunk, cnt = min(kMpChunk, m - first);
+  G1Aff p[kMpChunk];
+  unsigned skip = 0;
+  for (int j = 0; j < cnt; j++) {
+    load_struct(p[j], P, i * (size_t)m + first + j);
+    if (g1_is_inf(p[j]) || qskip[first + j]) skip |= 1u << j;
+  }
+  Fp12 f;
+  fp12_set_one(f);
+  int s = 0;
+  for (int it = ATE_NAF_LEN - 2; it >= -2; it--) {
+    // it >= 0: tangent (+ chord if the digit is non-zero); it == -1, -2: the two Frobenius lines
+    if (it >= 0 && it != ATE_NAF_LEN - 2) fp12_sqr(f, f);
+    int reps = (it >= 0 && ATE_NAF[it]) ? 2 : 1;
+    for (int r = 0; r < reps; r++, s++) {
+      for (int j = 0; j < cnt; j++) {
+        if ((skip >> j) & 1u) continue;
+        const Fp2* L = table + ((size_t)(first + j) * kLinesPerPoint + s) * 3;
+        Fp2 r0, r1, r2;
+        load_struct(r0, L, 0); load_struct(r1, L, 1); load_struct(r2, L, 2);
+        apply_line(f, p[j], r0, r1, r2);
+      }
+    }
+  }
+  store_struct(partial, i * (size_t)nchunks + ci, f);
+}
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const void* in, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -606,7 +649,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
 #ifdef BN254_SMEM_SCRATCH
   {
-    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_multi_pair_c<0, 1>, (const void*)k_multi_pair_c<1, 1>, (const void*)k_multi_pair_c<2, 1>,
+    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_g2_lines, (const void*)k_miller_lines, (const void*)k_multi_pair_c<0, 1>, (const void*)k_multi_pair_c<1, 1>, (const void*)k_multi_pair_c<2, 1>,
                                    (const void*)k_multi_pair_c<0, 2>, (const void*)k_multi_pair_c<1, 2>, (const void*)k_multi_pair_c<2, 2>,
                                    (const void*)k_multi_pair_c<0, 3>, (const void*)k_multi_pair_c<1, 3>, (const void*)k_multi_pair_c<2, 3>, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
                                    (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
@@ -699,6 +742,65 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
 MULTI_PAIR_ENTRY(bn254_miller_loop_batch, 0, BN254_GT_BYTES, void)
 MULTI_PAIR_ENTRY(bn254_multi_pair_batch, 1, BN254_GT_BYTES, void)
 MULTI_PAIR_ENTRY(bn254_pairing_check_batch, 2, 1, uint8_t)
+
+// ---- line tables --------------------------------------------------------------------------------------
+struct bn254_lines {
+  bn254_ctx* ctx;
+  size_t m;
+  Fp2* table;      // m x kLinesPerPoint x 3 Fp2 on the device
+  uint8_t* qskip;  // m flags: point at infinity
+};
+int bn254_g2_lines_create(bn254_ctx* ctx, const void* Q, size_t m, bn254_lines** out) {
+  if (!ctx || !Q || !out || m == 0) return fail(ctx, BN254_ERR_BAD_ARG, "bad lines arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (m * BN254_G2_BYTES > ctx->slot_bytes) return fail(ctx, BN254_ERR_BAD_ARG, "too many points for one table");
+  bn254_lines* L = new bn254_lines{ctx, m, nullptr, nullptr};
+  size_t bytes = m * (size_t)kLinesPerPoint * 3 * sizeof(Fp2);
+  if (cudaMalloc((void**)&L->table, bytes) != cudaSuccess || cudaMalloc((void**)&L->qskip, m) != cudaSuccess) {
+    if (L->table) cudaFree(L->table);
+    delete L;
+    return fail(ctx, BN254_ERR_OOM, "line table allocation");
+  }
+  Slot& s = ctx->slot[0];
+  memcpy(s.h, Q, m * BN254_G2_BYTES);
+  CU(cudaMemcpyAsync(s.d, s.h, m * BN254_G2_BYTES, cudaMemcpyHostToDevice, s.stream));
+  k_g2_lines<<<grid_for(m), kBlock, kTowerSmem, s.stream>>>(s.d, m, L->table, L->qskip);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s.stream));
+  *out = L;
+  return BN254_OK;
+}
+void bn254_g2_lines_destroy(bn254_lines* L) {
+  if (!L) return;
+  cudaSetDevice(L->ctx->device);
+  cudaFree(L->table);
+  cudaFree(L->qskip);
+  delete L;
+}
+size_t bn254_g2_lines_count(const bn254_lines* L) { return L ? L->m : 0; }
+// out[i] = FinalExponentiation(prod_j Miller(P[i*m + j], Q_j)) for the m table points: n products of m pairs
+int bn254_multi_pair_lines_batch(bn254_ctx* ctx, const void* P, const bn254_lines* L, size_t n, void* out) {
+  if (!ctx || !L || L->ctx != ctx) return fail(ctx, BN254_ERR_BAD_ARG, "line table belongs to another context");
+  const int m = (int)L->m;
+  const int nchunks = (m + kMpChunk - 1) / kMpChunk;
+  const Fp2* table = L->table;
+  const uint8_t* qskip = L->qskip;
+  return run_host(ctx, {P, BN254_G1_BYTES * (size_t)m, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
+                  [=](const void* a, const void*, size_t c, void* o, cudaStream_t s, uint4* cold) {
+                    Slot& sl = ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0];
+                    size_t need = c * (size_t)nchunks * BN254_GT_BYTES;
+                    if (sl.mp_scratch_bytes < need) {
+                      if (sl.mp_scratch) { cudaStreamSynchronize(s); cudaFree(sl.mp_scratch); sl.mp_scratch = nullptr; sl.mp_scratch_bytes = 0; }
+                      if (cudaMalloc(&sl.mp_scratch, need) != cudaSuccess) return;
+                      sl.mp_scratch_bytes = need;
+                    }
+                    dim3 grid(grid_for(c), (unsigned)nchunks);
+                    k_miller_lines<<<grid, kBlock, kTowerSmem, s>>>(a, table, qskip, c, m, nchunks, sl.mp_scratch);
+                    k_mp_combine<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(sl.mp_scratch, c, nchunks, o);
+                  });
+}
 
 int bn254_final_exp_batch_dev(bn254_ctx* ctx, const void* d_in, size_t n, void* d_out, void* stream) {
   if (ctx && ctx->use_vm) return run_dev_vm<VmProgFinalExp>(ctx, d_in, nullptr, n, d_out, (cudaStream_t)stream);

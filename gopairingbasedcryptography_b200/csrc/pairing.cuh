@@ -118,6 +118,29 @@ BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k
   else miller_loop_t<0>(f, P, Q, T, k);
 }
 
+// ---- precomputed G2 line tables (north_star: fixed public-parameter / user-key G2 points) -----------------
+// The (r0, r1, r2) coefficients of every line of the Miller schedule depend on Q only.  For a fixed Q they are
+// computed once (g2_precompute_lines) and every later pairing against Q costs per line: 2 Fp2 x Fp products
+// (evaluation at P) + one sparse 034 multiply -- no G2 arithmetic, no T state.
+// Order: for i = 64..0 { tangent line; chord line if NAF digit != 0 }, then the two Frobenius lines.
+static constexpr int kLinesPerPoint = 65 + 21 + 2;
+BN_HD void g2_precompute_lines(const G2Aff& Q, Fp2* out /* kLinesPerPoint x 3 */) {
+  G2Proj T; T.x = Q.x; T.y = Q.y; T.z = fp2_one();
+  G2Aff qn; qn.x = Q.x; qn.y = fp2_neg(Q.y);
+  int s = 0;
+  for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
+    g2_dbl_step(T, out[3 * s], out[3 * s + 1], out[3 * s + 2]); s++;
+    int d = ATE_NAF[i];
+    if (d) { g2_add_step(T, d > 0 ? Q : qn, out[3 * s], out[3 * s + 1], out[3 * s + 2], true); s++; }
+  }
+  G2Aff q1, q2;
+  fp2_mul(q1.x, fp2_conj(Q.x), GAMMA1[2]);
+  fp2_mul(q1.y, fp2_conj(Q.y), GAMMA1[3]);
+  q2.x = fp2_mul_fp(Q.x, GAMMA2[2]); q2.y = Q.y;
+  g2_add_step(T, q1, out[3 * s], out[3 * s + 1], out[3 * s + 2], true); s++;
+  g2_add_step(T, q2, out[3 * s], out[3 * s + 1], out[3 * s + 2], false); s++;
+}
+
 // z^(d'), d' = 2x0(6x0^2+3x0+1)(p^12-1)/r.  Returns 1 early when the easy part is 1 (gnark behaviour).
 // z == 0 is mapped to 0 by the inversion convention inv(0) = 0.
 BN_NOINLINE void final_exp(Fp12& out, const Fp12& in) {

@@ -39,7 +39,15 @@ def neg_g2(points):
     return pts
 
 
-def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, deltas):
+def bsw07_key_lines(engine, dj, dj_prime, d):
+    """Line tables of one user key (2m+1 fixed G2 points) for bsw07_decrypt_batch(..., lines=...)."""
+    m = np.ascontiguousarray(dj).reshape(-1, G2_BYTES).shape[0]
+    qrow = np.concatenate([np.ascontiguousarray(dj).reshape(m, G2_BYTES), np.ascontiguousarray(dj_prime).reshape(m, G2_BYTES),
+                           np.ascontiguousarray(d).reshape(1, G2_BYTES)], axis=0)
+    return engine.g2_lines_create(qrow)
+
+
+def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, deltas, lines=None):
     """Fused BSW07 decryption for n ciphertexts under ONE user key with m matched leaves
     (reference: access/tree/access_tree_node.go:96-164 + cpabe/bsw07/bsw07_cpabe.go:172-195).
 
@@ -53,6 +61,9 @@ def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, delta
     b = engine.g1_mul_batch(neg_g1(cy_prime), sc).reshape(n, m, G1_BYTES)
     k = 2 * m + 1
     P = np.concatenate([a, b, neg_g1(c).reshape(n, 1, G1_BYTES)], axis=1)
+    if lines is not None:  # the key's G2 points are fixed: Miller product from precomputed line tables
+        prod = engine.multi_pair_lines_batch(P.reshape(-1), lines)
+        return engine.gt_mul_batch(np.ascontiguousarray(c_tilde).reshape(-1, GT_BYTES), prod)
     q1 = np.ascontiguousarray(dj).reshape(m, G2_BYTES)
     q2 = np.ascontiguousarray(dj_prime).reshape(m, G2_BYTES)
     qrow = np.concatenate([q1, q2, np.ascontiguousarray(d).reshape(1, G2_BYTES)], axis=0)

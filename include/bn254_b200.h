@@ -71,6 +71,18 @@ int bn254_pair_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, v
 int bn254_multi_pair_batch(bn254_ctx*, const void* P, const void* Q, size_t n, size_t k, void* out_gt);
 int bn254_multi_pair_batch_dev(bn254_ctx*, const void* dP, const void* dQ, size_t n, size_t k, void* d_out_gt, void* stream);
 
+/* Precomputed G2 line tables for FIXED G2 points (a user key: bsw07 usk.dj / usk.djPrime / usk.d,
+ * cpabe/bsw07/bsw07_cpabe.go:97-131; public parameters of the IBE schemes).  gnark's analogue is
+ * PrecomputeLines / MillerLoopFixedQ.  create() runs the G2 side of the Miller schedule once per point
+ * (88 lines x 192 B each, kept on the GPU); bn254_multi_pair_lines_batch then computes, for n rows of m G1 points,
+ * out[i] = Pair(P[i*m .. i*m+m), Q[0..m)) with no G2 arithmetic and one final exponentiation per row --
+ * bit-identical to bn254_multi_pair_batch on the same operands. */
+typedef struct bn254_lines bn254_lines;
+int bn254_g2_lines_create(bn254_ctx*, const void* Q, size_t m, bn254_lines** out);
+void bn254_g2_lines_destroy(bn254_lines*);
+size_t bn254_g2_lines_count(const bn254_lines*);
+int bn254_multi_pair_lines_batch(bn254_ctx*, const void* P, const bn254_lines* lines, size_t n, void* out_gt);
+
 /* n x bn254.PairingCheck(P[i*k..], Q[i*k..]) -> ok[i] in {0,1}
  * [signature/bls01_signature/bls_signature.go:81-84] */
 int bn254_pairing_check_batch(bn254_ctx*, const void* P, const void* Q, size_t n, size_t k, uint8_t* ok);

@@ -117,3 +117,27 @@ void emu_g1_mul_fixed(const void* base1, const void* s, size_t n, void* out) {
 }
 extern "C" void emu_gt_cyclo_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
   for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); gt_cyclo_exp(r, b, k); st(out, i, r); } }
+// line tables: precompute for the m points of Q, then out[i] = FE(prod_j lines_j evaluated at P[i*m+j])
+extern "C" void emu_multi_pair_lines(const void* P, const void* Q, size_t n, size_t m, void* out) {
+  Fp2* table = new Fp2[m * kLinesPerPoint * 3];
+  unsigned char* qs = new unsigned char[m];
+  for (size_t j = 0; j < m; j++) { G2Aff q = ld<G2Aff>(Q, j); qs[j] = g2_is_inf(q); if (!qs[j]) g2_precompute_lines(q, table + j * kLinesPerPoint * 3); }
+  for (size_t i = 0; i < n; i++) {
+    Fp12 f; fp12_set_one(f);
+    int s = 0;
+    for (int it = ATE_NAF_LEN - 2; it >= -2; it--) {
+      if (it >= 0 && it != ATE_NAF_LEN - 2) fp12_sqr(f, f);
+      int reps = (it >= 0 && ATE_NAF[it]) ? 2 : 1;
+      for (int r = 0; r < reps; r++, s++)
+        for (size_t j = 0; j < m; j++) {
+          G1Aff p = ld<G1Aff>(P, i * m + j);
+          if (g1_is_inf(p) || qs[j]) continue;
+          const Fp2* L = table + (j * kLinesPerPoint + s) * 3;
+          apply_line(f, p, L[0], L[1], L[2]);
+        }
+    }
+    final_exp(f, f);
+    st(out, i, f);
+  }
+  delete[] table; delete[] qs;
+}

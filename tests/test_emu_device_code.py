@@ -230,3 +230,16 @@ def test_gt_exp_fixed_windows(emu):
     x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(12)), dtype=np.uint8).copy()
     emu.emu_gt_exp(vp(x), sz(0), vp(sb), sz(4), vp(out))
     assert (out[:384 * 4] == port.gt_exp_base_batch(x, sb[:128], 4)).all()
+
+
+def test_precomputed_g2_lines(emu):
+    """Line tables of fixed G2 points + line-based Miller product == the ordinary multi-pairing (incl. infinity)."""
+    n, m = 3, 5
+    _, Q, _, _ = common.points(m, seed=401)
+    P, _, _, _ = common.points(n * m, seed=402)
+    Q[128 * 2:128 * 3] = 0   # an infinity G2 point in the key
+    P[64 * 7:64 * 8] = 0     # and an infinity G1 operand
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_multi_pair_lines(vp(P), vp(Q), sz(n), sz(m), vp(out))
+    ref = port.multi_pair_batch(P, np.tile(Q, n), n, m)
+    assert (out == ref).all()

@@ -399,3 +399,32 @@ def test_afp25_shaped_msm(engine):
         for j in range(length):
             acc = port.g1_add_batch(acc, t[64 * j:64 * j + 64], 1)
         assert (got[i] == acc).all()
+
+
+def test_precomputed_g2_line_tables(engine):
+    """bn254_g2_lines_create + bn254_multi_pair_lines_batch == bn254_multi_pair_batch, bit for bit; the BSW07 driver
+    gives the same plaintexts with and without the key's line tables."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    for n, m in ((5, 3), (130, 21)):
+        _, Q, _, _ = common.points(m, seed=411 + m, threads=8)
+        P, _, _, _ = common.points(n * m, seed=412 + m, threads=8)
+        Q[128:256] = 0
+        P[64 * 4:64 * 5] = 0
+        lines = engine.g2_lines_create(Q)
+        got = engine.multi_pair_lines_batch(P, lines)
+        assert (got.reshape(-1) == port.multi_pair_batch(P, np.tile(Q, n), n, m, 8)).all()
+        assert (got == engine.multi_pair_batch(P, np.tile(Q, n), m)).all()
+        lines.close()
+    n, m = 4, 6
+    cyP, djQ, _, _ = common.points(n * m, seed=81, threads=8)
+    cypP, djpQ, _, _ = common.points(n * m, seed=82, threads=8)
+    cP, dQ, _, _ = common.points(n, seed=83)
+    cy, cyp = cyP.reshape(n, m, 64), cypP.reshape(n, m, 64)
+    dj, djp, d, c = djQ.reshape(-1, 128)[:m], djpQ.reshape(-1, 128)[:m], dQ[:128], cP.reshape(n, 64)
+    deltas = common.scalar_bytes(common.scalars(m, seed=84, edges=False)).reshape(m, 32)
+    ctil = engine.pair_batch(c, np.tile(d, n))
+    a = schemes.bsw07_decrypt_batch(engine, cy, cyp, dj, djp, c, d, ctil, deltas)
+    key = schemes.bsw07_key_lines(engine, dj, djp, d)
+    b = schemes.bsw07_decrypt_batch(engine, cy, cyp, dj, djp, c, d, ctil, deltas, lines=key)
+    assert (a == b).all()
