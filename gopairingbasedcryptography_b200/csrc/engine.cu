@@ -271,6 +271,27 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void*
   if (CYCLO) gt_cyclo_exp(r, b, s); else gt_exp(r, b, s);
   store_struct(out, i, r);
 }
+// fixed-base GT exponentiation: out = prod_w table[w][byte_w(k)] -- 32 Fp12 products, no squarings.  The table
+// (32 x 255 x 384 B = 3.1 MB, L2-resident) is built once per base with k_gt_exp on the scalars d << 8w.
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const Fp12* table, const void* k, size_t n, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(k) + i * 32);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  Fp12 acc, e;
+  bool started = false;
+  for (int w = 0; w < kFixedWindows; w++) {
+    int d = (int)((s[w >> 2] >> ((w & 3) * 8)) & 0xFFu);
+    if (d) {
+      load_struct(e, table, (size_t)w * kFixedEntries + d - 1);
+      if (started) fp12_mul(acc, acc, e); else { acc = e; started = true; }
+    }
+  }
+  if (!started) fp12_set_one(acc);
+  store_struct(out, i, acc);
+}
 // mode 0: a*b ; mode 1: a/b
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
@@ -444,6 +465,9 @@ struct bn254_ctx {
   void* fixed_table[2] = {nullptr, nullptr};
   unsigned char fixed_base[2][BN254_G2_BYTES] = {};
   bool fixed_valid[2] = {false, false};
+  Fp12* gt_table = nullptr;  // fixed-base GT table of the last base used with >= kFixedMin exponents
+  unsigned char gt_base[BN254_GT_BYTES] = {};
+  bool gt_valid = false;
   cudaEvent_t vm_dev_done = nullptr;
 };
 
@@ -568,6 +592,39 @@ int run_dev_vm(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out
 }
 
 
+
+// fixed-base GT table: entries x^(d << 8w) computed with the generic ladder (valid for any Fp12 base)
+int ensure_gt_table(bn254_ctx* ctx, const void* base) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->gt_valid && memcmp(ctx->gt_base, base, BN254_GT_BYTES) == 0) return BN254_OK;
+  const size_t entries = (size_t)kFixedWindows * kFixedEntries;
+  if (!ctx->gt_table) CU(cudaMalloc((void**)&ctx->gt_table, entries * sizeof(Fp12)));
+  Slot& s = ctx->slot[0];
+  unsigned char* h = reinterpret_cast<unsigned char*>(s.h);
+  memcpy(h, base, BN254_GT_BYTES);
+  unsigned char* hs = h + 512;
+  memset(hs, 0, entries * 32);
+  for (int w = 0; w < kFixedWindows; w++)
+    for (int d = 1; d <= kFixedEntries; d++) hs[((size_t)w * kFixedEntries + d - 1) * 32 + w] = (unsigned char)d;
+  CU(cudaMemcpyAsync(s.d, s.h, 512 + entries * 32, cudaMemcpyHostToDevice, s.stream));
+  k_gt_exp<0><<<grid_for(entries), kBlock, kTowerSmem, s.stream>>>(s.d, 0, s.d + 512, entries, ctx->gt_table);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s.stream));
+  memcpy(ctx->gt_base, base, BN254_GT_BYTES);
+  ctx->gt_valid = true;
+  return BN254_OK;
+}
+int gt_fixed_exp(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
+  int rc = ensure_gt_table(ctx, x1);
+  if (rc) return rc;
+  const Fp12* table = ctx->gt_table;
+  return run_host(ctx, {k, BN254_SCALAR_BYTES, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
+                  [table](const void* a, const void*, size_t c, void* o, cudaStream_t s, uint4*) {
+                    k_gt_fixed_exp<<<grid_for(c), kBlock, kTowerSmem, s>>>(table, a, c, o);
+                  });
+}
 // multi-pairing launch: single kernel for small k, split + combine for large k
 template <int MODE>
 cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
@@ -649,7 +706,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
 #ifdef BN254_SMEM_SCRATCH
   {
-    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_g2_lines, (const void*)k_miller_lines, (const void*)k_multi_pair_c<0, 1>, (const void*)k_multi_pair_c<1, 1>, (const void*)k_multi_pair_c<2, 1>,
+    const void* tower_kernels[] = {(const void*)k_pair, (const void*)k_gt_fixed_exp, (const void*)k_g2_lines, (const void*)k_miller_lines, (const void*)k_multi_pair_c<0, 1>, (const void*)k_multi_pair_c<1, 1>, (const void*)k_multi_pair_c<2, 1>,
                                    (const void*)k_multi_pair_c<0, 2>, (const void*)k_multi_pair_c<1, 2>, (const void*)k_multi_pair_c<2, 2>,
                                    (const void*)k_multi_pair_c<0, 3>, (const void*)k_multi_pair_c<1, 3>, (const void*)k_multi_pair_c<2, 3>, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
                                    (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
@@ -685,6 +742,7 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
   if (ctx->dev_slot.mp_scratch) { cudaFree(ctx->dev_slot.mp_scratch); }
   if (ctx->vm_cold_dev) cudaFree(ctx->vm_cold_dev);
   for (int g = 0; g < 2; g++) if (ctx->fixed_table[g]) cudaFree(ctx->fixed_table[g]);
+  if (ctx->gt_table) cudaFree(ctx->gt_table);
   if (ctx->vm_dev_done) cudaEventDestroy(ctx->vm_dev_done);
   delete ctx;
 }
@@ -922,6 +980,7 @@ int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, v
                   [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
+  if (ctx && x1 && n >= kFixedMin) return gt_fixed_exp(ctx, x1, k, n, out);
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
                   [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
 }
@@ -930,6 +989,7 @@ int bn254_gt_cyclo_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_
                   [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
 }
 int bn254_gt_cyclo_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
+  if (ctx && x1 && n >= kFixedMin) return gt_fixed_exp(ctx, x1, k, n, out);
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
                   [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
 }

@@ -428,3 +428,23 @@ def test_precomputed_g2_line_tables(engine):
     key = schemes.bsw07_key_lines(engine, dj, djp, d)
     b = schemes.bsw07_decrypt_batch(engine, cy, cyp, dj, djp, c, d, ctil, deltas, lines=key)
     assert (a == b).all()
+
+
+def test_gt_fixed_base_table(engine):
+    """>= 4096 exponents on one base use the cached 32x255 GT window table (built with the generic ladder, so it is
+    valid for ANY Fp12 base, not only pairing outputs)."""
+    n = 4096 + 3
+    ks = common.scalars(n - 3) + [0, (1 << 256) - 1, 1 << 255]
+    sb = common.scalar_bytes(ks)
+    P, Q, _, _ = common.points(2, seed=515)
+    gt = engine.pair_batch(P, Q)
+    idx = [0, 1, 2, 3, 4, 5, 6, n - 3, n - 2, n - 1, 777]
+    sel = np.concatenate([sb[32 * i:32 * i + 32] for i in idx])
+    out = engine.gt_cyclo_exp_base_batch(gt[0], sb)
+    assert (out[idx].reshape(-1) == port.gt_exp_base_batch(gt[0], sel, len(idx), 8)).all()
+    rng = o.SplitMix64(4)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(12)), dtype=np.uint8).copy()
+    out = engine.gt_exp_base_batch(x, sb)          # generic element: the cache must switch bases
+    assert (out[idx].reshape(-1) == port.gt_exp_base_batch(x, sel, len(idx), 8)).all()
+    out = engine.gt_exp_base_batch(gt[1], sb)
+    assert (out[idx].reshape(-1) == port.gt_exp_base_batch(gt[1], sel, len(idx), 8)).all()
