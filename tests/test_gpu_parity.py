@@ -448,3 +448,60 @@ def test_gt_fixed_base_table(engine):
     assert (out[idx].reshape(-1) == port.gt_exp_base_batch(x, sel, len(idx), 8)).all()
     out = engine.gt_exp_base_batch(gt[1], sb)
     assert (out[idx].reshape(-1) == port.gt_exp_base_batch(gt[1], sel, len(idx), 8)).all()
+
+
+def test_lane_group_vm_implementation():
+    """The alternative pairing implementation (K=3 lane groups, tower VM; BN254_IMPL=vm, read at context creation)
+    through the same C ABI: pair / miller / final-exp parity incl. ragged sizes and infinity operands."""
+    from gopairingbasedcryptography_b200 import bn254
+
+    old = os.environ.get("BN254_IMPL")
+    os.environ["BN254_IMPL"] = "vm"
+    try:
+        eng = bn254.Engine(0)
+    finally:
+        if old is None:
+            del os.environ["BN254_IMPL"]
+        else:
+            os.environ["BN254_IMPL"] = old
+    n = 10 * 13 + 7  # not a multiple of the 10 pairings a warp owns
+    P, Q, _, _ = common.points(n, seed=909, threads=8)
+    P, Q = common.with_infinities(P, Q)
+    ref = port.pair_batch(P, Q, n, 8)
+    assert (eng.pair_batch(P, Q).reshape(-1) == ref).all()
+    ml = eng.miller_loop_batch(P, Q, 1)
+    assert (eng.final_exp_batch(ml).reshape(-1) == ref).all()
+    rng = o.SplitMix64(12)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(24)), dtype=np.uint8).copy()
+    assert (eng.final_exp_batch(x).reshape(-1) == port.final_exp_batch(x, 2)).all()
+    eng.close()
+
+
+def test_error_contract(engine):
+    """gnark's only error ("invalid inputs sizes") and the ABI's argument checks; nothing else validates input."""
+    import ctypes
+    from gopairingbasedcryptography_b200 import bn254, _native
+
+    P, Q, _, _ = common.points(2, seed=5)
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        engine.multi_pair_batch(P, Q[:128], 2)
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        engine.pairing_check_batch(P, Q, 0)
+    with pytest.raises(ValueError, match="invalid inputs sizes"):
+        bn254.PairingCheck([bn254.G1Affine()], [])
+    lib = _native.lib()
+    lib.bn254_pair_batch.restype = ctypes.c_int
+    out = np.zeros(384, np.uint8)
+    rc = lib.bn254_pair_batch(engine.handle, None, None, ctypes.c_size_t(1), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == -4 and b"null" in lib.bn254_last_error(engine.handle)
+    lib.bn254_multi_pair_batch.restype = ctypes.c_int
+    rc = lib.bn254_multi_pair_batch(engine.handle, P.ctypes.data_as(ctypes.c_void_p), Q.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_size_t(1), ctypes.c_size_t(0), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == -1
+    # points that are not on the curve are processed without complaint, like gnark (no validation): just no crash
+    junk = np.arange(64, dtype=np.uint8)
+    engine.pair_batch(junk, Q[:128])
+    # a second context on the same GPU works concurrently with the first
+    e2 = bn254.Engine(0)
+    assert (e2.pair_batch(P, Q) == engine.pair_batch(P, Q)).all()
+    e2.close()
