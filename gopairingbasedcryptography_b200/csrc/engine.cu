@@ -65,15 +65,58 @@ __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t fir
   }
 }
 
+// Coalesced CTA-wide staging: the kBlock operands of a CTA are contiguous in the caller's AoS arrays, so the CTA
+// copies them with unit-stride 128-bit accesses (every warp instruction touches one contiguous 512-byte span)
+// through the dynamic shared memory that later serves as the tower scratch, and each thread then picks its own
+// element out of shared memory.  Same for the 384-byte results on the way out.
+template <typename T>
+__device__ __forceinline__ void cta_load(T& dst, const void* base, size_t first, size_t n_left, uint4* stage) {
+  constexpr int Q4 = (int)(sizeof(T) / 16);
+  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(base) + first * sizeof(T));
+  int total = (int)min((size_t)kBlock, n_left) * Q4;
+  for (int w = threadIdx.x; w < total; w += kBlock) stage[w] = __ldg(src + w);
+  __syncthreads();
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+  if ((size_t)threadIdx.x < n_left) {
+#pragma unroll
+    for (int c = 0; c < Q4; c++) d[c] = stage[threadIdx.x * Q4 + c];
+  }
+  __syncthreads();
+}
+template <typename T>
+__device__ __forceinline__ void cta_store(void* base, size_t first, size_t n_left, const T& src, uint4* stage) {
+  constexpr int Q4 = (int)(sizeof(T) / 16);
+  __syncthreads();  // the scratch is free again: every thread is past its last tower routine
+  const uint4* sv = reinterpret_cast<const uint4*>(&src);
+  if ((size_t)threadIdx.x < n_left) {
+#pragma unroll
+    for (int c = 0; c < Q4; c++) stage[threadIdx.x * Q4 + c] = sv[c];
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(base) + first * sizeof(T));
+  int total = (int)min((size_t)kBlock, n_left) * Q4;
+  for (int w = threadIdx.x; w < total; w += kBlock) dst[w] = stage[w];
+}
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P, const void* Q, size_t n, void* out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t first = (size_t)blockIdx.x * blockDim.x;
+  size_t i = first + threadIdx.x;
   G1Aff p; G2Aff q; G2Proj T;
-  load_struct(p, P, i); load_struct(q, Q, i);
   Fp12 f;
+#ifdef BN254_SMEM_SCRATCH
+  cta_load(p, P, first, n - first, bn_dyn_smem);
+  cta_load(q, Q, first, n - first, bn_dyn_smem);
+  if (i < n) {
+    miller_loop(f, &p, &q, &T, 1);
+    final_exp(f, f);
+  }
+  cta_store(out, first, n - first, f, bn_dyn_smem);
+#else
+  if (i >= n) return;
+  load_struct(p, P, i); load_struct(q, Q, i);
   miller_loop(f, &p, &q, &T, 1);
   final_exp(f, f);
   store_struct(out, i, f);
+#endif
 }
 // small products with a compile-time pair count (BLS verify: KC = 2): the pair loop unrolls
 template <int MODE, int KC>
