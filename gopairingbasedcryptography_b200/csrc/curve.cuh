@@ -210,17 +210,6 @@ BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
   jac_to_aff(out, acc);
 }
 
-// x * conj(y) without materialising conj(y) = (y0, -y1)
-BN_NOINLINE void fp12_mul_conj(Fp12& z, const Fp12& x, const Fp12& y) {
-  Fp6 a, b, s, t;
-  fp6_mul(a, x.c0, y.c0);
-  fp6_mul(b, x.c1, y.c1);
-  fp6_add(s, x.c0, x.c1); fp6_sub(t, y.c0, y.c1);
-  fp6_mul(s, s, t);
-  fp6_sub(s, s, a); fp6_add(z.c1, s, b);
-  fp6_mul_v(b, b); fp6_sub(z.c0, a, b);
-}
-
 // GT.Exp, generic Fp12 (no subgroup assumption), k = 256-bit LE, k == 0 -> 1.  FIXED 2-bit windows (gnark's
 // E12.Exp shape): every lane of a warp multiplies at the same 128 positions, so the SIMT lanes never diverge on
 // the exponent bits -- a bit-serial or sliding-window ladder would make every warp pay for the union of its
