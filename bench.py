@@ -31,6 +31,10 @@ METRIC = "bn254_pairings_per_sec"
 UNIT = "pairings/s"
 MACS_PER_PAIRING = 2.081e6  # SURVEY.md §8d Model-M: 15300 Fp-mul equivalents x 136 limb-MACs
 BYTES_PER_PAIRING = 64 + 128 + 384
+# dram__bytes_read.sum + dram__bytes_write.sum of k_pair from the committed ncu --set full capture
+# (profiles/r1/ncu_k_pair_final_summary.txt: 30.8 + 157.7 GB for 2^18 pairings): the local-memory stack of the
+# one-thread-per-pairing kernel, ~1250x the algorithmic 576 B -- the first thing round 2 has to remove.
+NCU_DRAM_BYTES_PER_PAIRING = (30.817529e9 + 157.676779e9) / (1 << 18)
 
 
 def host_threads():
@@ -266,9 +270,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 192, "d2h_bytes_per_step": n * 384},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T limb-MAC/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PAIRING * n,
                          "note": "algorithmic 2.081e6 32x32->64 MACs per pairing (SURVEY 8d) x %d per launch / %.1f ms kernel; "
-                                 "peak = IMAD.WIDE rate %s; HBM: %.2f GB/s of %.0f measured (not the bound)"
+                                 "peak = IMAD.WIDE rate %s; algorithmic HBM: %.2f GB/s of %.0f measured (not the bound); traffic = DRAM bytes per launch "
+                                 "scaled from the ncu capture at 2^18 (local-memory stack spill, see profiles/r1)"
                                  % (n, kernel_ms, peak_how, BYTES_PER_PAIRING * n / (kernel_ms * 1e-3) / 1e9, 6472.1)},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d pairings on %d threads, oracle C restatement (gnark cannot run here: no Go)" % (sample, threads)},
