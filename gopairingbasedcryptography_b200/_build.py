@@ -17,6 +17,9 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH"],
+    "blk64": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=6", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=64"],
+    "blk96": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=96"],
+    "blk192": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=192"],
     "vmA": DEFAULT, "vmB": DEFAULT, "vmC": DEFAULT, "vmD": DEFAULT,
     "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
     "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],

@@ -20,7 +20,10 @@ using namespace bn254;
 // =============================================================================================
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef BN254_BLOCK
+#define BN254_BLOCK 128
+#endif
+constexpr int kBlock = BN254_BLOCK;
 #ifndef BN254_MIN_BLOCKS
 #define BN254_MIN_BLOCKS 1
 #endif
