@@ -80,3 +80,43 @@ def bls_verify_batch(engine, pk, g1, hm, sigma_neg):
                         np.tile(np.ascontiguousarray(g1).reshape(1, 64), (n, 1))], axis=1)
     Q = np.concatenate([np.ascontiguousarray(hm).reshape(n, 128), np.ascontiguousarray(sigma_neg).reshape(n, 128)], axis=1)
     return engine.pairing_check_batch(P.reshape(-1), Q.reshape(-1), 2)
+
+
+def sw05_fibe_decrypt_batch(engine, di, ei, e_prime, deltas):
+    """Fused SW05 fuzzy-IBE decryption (fibe/sw05_fibe_common.go:284-331) for n ciphertexts with |S| = m matched
+    attributes each:  M = e' / prod_i e(D_i, E_i)^{Delta_i}  ==  e' * Pair([-Delta_i] D_i, E_i) as ONE m-pair product.
+    di: (n, m, 64) key components, ei: (n, m, 128) ciphertext components, e_prime: (n, 384), deltas: (n, m, 32)."""
+    n, m = di.shape[0], di.shape[1]
+    scaled = engine.g1_mul_batch(neg_g1(di), np.ascontiguousarray(deltas).reshape(-1, 32)).reshape(n, m, G1_BYTES)
+    prod = engine.multi_pair_batch(scaled.reshape(-1), np.ascontiguousarray(ei).reshape(-1), m)
+    return engine.gt_mul_batch(np.ascontiguousarray(e_prime).reshape(-1, GT_BYTES), prod)
+
+
+def bb04_ibe_decrypt_batch(engine, a, b, c, d0, dj):
+    """Fused BB04 full-IBE decryption (ibe/bb04_ibe/bb04_ibe.go:210-241): M = a * prod_j e(d_j, c_j) / e(b, d0) as ONE
+    (k+1)-pair product per ciphertext.  a: (n, 384); b: (n, 64); c: (n, k, 128); d0: (n, 128) or (128,); dj: (n, k, 64)
+    or (k, 64) when one key decrypts the whole batch."""
+    n, k = c.shape[0], c.shape[1]
+    dj = np.broadcast_to(np.ascontiguousarray(dj).reshape(-1, k, G1_BYTES), (n, k, G1_BYTES))
+    d0 = np.broadcast_to(np.ascontiguousarray(d0).reshape(-1, 1, G2_BYTES), (n, 1, G2_BYTES))
+    P = np.concatenate([dj, neg_g1(b).reshape(n, 1, G1_BYTES)], axis=1)
+    Q = np.concatenate([np.ascontiguousarray(c).reshape(n, k, G2_BYTES), d0], axis=1)
+    prod = engine.multi_pair_batch(np.ascontiguousarray(P).reshape(-1), np.ascontiguousarray(Q).reshape(-1), k + 1)
+    return engine.gt_mul_batch(np.ascontiguousarray(a).reshape(-1, GT_BYTES), prod)
+
+
+def g2_msm_batch(engine, points, coeffs):
+    """n MSMs over the SAME B G2 points (bibe/gwww25_bibe/gwww25_bibe_utils.go:40-50: sum_j [coef_j] tauPowersG2_j).
+    points: (B, 128); coeffs: (n, B, 32) -> (n, 128)."""
+    n, B = coeffs.shape[0], coeffs.shape[1]
+    terms = engine.g2_mul_batch(np.tile(np.ascontiguousarray(points).reshape(B, G2_BYTES), (n, 1)),
+                                np.ascontiguousarray(coeffs).reshape(-1, 32))
+    return engine.g2_sum_batch(terms, B)
+
+
+def g1_msm_batch(engine, points, coeffs):
+    """n MSMs over the SAME B G1 points (bibe/afp25_bibe/afp25_bibe_utils.go:45-55)."""
+    n, B = coeffs.shape[0], coeffs.shape[1]
+    terms = engine.g1_mul_batch(np.tile(np.ascontiguousarray(points).reshape(B, G1_BYTES), (n, 1)),
+                                np.ascontiguousarray(coeffs).reshape(-1, 32))
+    return engine.g1_sum_batch(terms, B)

@@ -505,3 +505,52 @@ def test_error_contract(engine):
     e2 = bn254.Engine(0)
     assert (e2.pair_batch(P, Q) == engine.pair_batch(P, Q)).all()
     e2.close()
+
+
+def test_sw05_bb04_gwww25_fused_drivers(engine):
+    """§8f-3 callers: SW05 FIBE (fibe/sw05_fibe_common.go:305-323), BB04-IBE (ibe/bb04_ibe/bb04_ibe.go:213-236) and the
+    GWWW25 G2-side MSM (bibe/gwww25_bibe/gwww25_bibe_utils.go:40-50): fused batch drivers vs the reference's unfused
+    formulas evaluated with the oracle."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    # SW05: M = e' / prod_i e(D_i, E_i)^Delta_i
+    n, m = 3, 4
+    D, E, _, _ = common.points(n * m, seed=601, threads=8)
+    di, ei = D.reshape(n, m, 64), E.reshape(n, m, 128)
+    deltas = common.scalar_bytes(common.scalars(n * m, seed=602, edges=False)).reshape(n, m, 32)
+    P0, Q0, _, _ = common.points(n, seed=603)
+    eprime = engine.pair_batch(P0, Q0)
+    got = schemes.sw05_fibe_decrypt_batch(engine, di, ei, eprime, deltas)
+    for i in range(n):
+        den = None
+        for j in range(m):
+            t = port.gt_exp_batch(port.pair_batch(di[i, j], ei[i, j], 1), deltas[i, j], 1)
+            den = t if den is None else port.gt_mul_batch(den, t, 1)
+        assert (got[i] == port.gt_div_batch(eprime[i], den, 1)).all()
+    # BB04-IBE: M = a * prod_j e(d_j, c_j) / e(b, d0), one key for the batch, k = 9 here (256 in the reference)
+    n, k = 3, 9
+    dj, _, _, _ = common.points(k, seed=611)
+    _, C, _, _ = common.points(n * k, seed=612, threads=8)
+    B_, D0, _, _ = common.points(n, seed=613)
+    c = C.reshape(n, k, 128)
+    b, d0 = B_.reshape(n, 64), D0[:128]
+    a = eprime
+    got = schemes.bb04_ibe_decrypt_batch(engine, a, b, c, d0, dj.reshape(k, 64))
+    for i in range(n):
+        prod = None
+        for j in range(k):
+            t = port.pair_batch(dj[64 * j:64 * j + 64], c[i, j], 1)
+            prod = t if prod is None else port.gt_mul_batch(prod, t, 1)
+        mref = port.gt_div_batch(port.gt_mul_batch(a[i], prod, 1), port.pair_batch(b[i], d0, 1), 1)
+        assert (got[i] == mref).all()
+    # GWWW25: sum_j [coef_j] tauPowersG2_j
+    Bn, n = 17, 3
+    _, tau2, _, _ = common.points(Bn, seed=621, threads=8)
+    coef = common.scalar_bytes(common.scalars(n * Bn, seed=622, edges=False)).reshape(n, Bn, 32)
+    got = schemes.g2_msm_batch(engine, tau2.reshape(Bn, 128), coef)
+    for i in range(n):
+        acc = np.zeros(128, np.uint8)
+        t = port.g2_mul_batch(tau2, coef[i].reshape(-1), Bn, 8)
+        for j in range(Bn):
+            acc = port.g2_add_batch(acc, t[128 * j:128 * j + 128], 1)
+        assert (got[i] == acc).all()
