@@ -420,6 +420,19 @@ class G1Affine(_Point):
     NBYTES = G1_BYTES
     _mul, _add = "g1_mul_batch", "g1_add_batch"
 
+    def Bytes(self):
+        from . import wire
+        return wire.g1_bytes(self.raw)
+
+    def Marshal(self):
+        from . import wire
+        return wire.g1_marshal(self.raw)
+
+    def Unmarshal(self, b):
+        from . import wire
+        self.raw = wire.g1_unmarshal(bytes(b))
+        return self
+
     def ScalarMultiplicationBase(self, s):
         return self.ScalarMultiplication(Generators()[2], s)
 
@@ -427,6 +440,19 @@ class G1Affine(_Point):
 class G2Affine(_Point):
     NBYTES = G2_BYTES
     _mul, _add = "g2_mul_batch", "g2_add_batch"
+
+    def Bytes(self):
+        from . import wire
+        return wire.g2_bytes(self.raw)
+
+    def Marshal(self):
+        from . import wire
+        return wire.g2_marshal(self.raw)
+
+    def Unmarshal(self, b):
+        from . import wire
+        self.raw = wire.g2_unmarshal(bytes(b))
+        return self
 
     def ScalarMultiplicationBase(self, s):
         return self.ScalarMultiplication(Generators()[3], s)
@@ -480,6 +506,17 @@ class GT:
 
     def Inverse(self, a):
         self.raw = default_engine().gt_div_batch(_gt_one_raw(), a.raw).tobytes()
+        return self
+
+    def Bytes(self):
+        from . import wire
+        return wire.gt_bytes(self.raw)
+
+    Marshal = Bytes
+
+    def Unmarshal(self, b):
+        from . import wire
+        self.raw = wire.gt_from_bytes(bytes(b))
         return self
 
     def Exp(self, x, k):
