@@ -13,6 +13,12 @@ CSRC = os.path.join(HERE, "csrc")
 DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
+    "staged": DEFAULT + ["-DBN254_STAGED"],
+    "staged_ls": DEFAULT + ["-DBN254_STAGED", "-DBN254_CTA_LOCKSTEP"],
+    "staged_ls_ilp": DEFAULT + ["-DBN254_STAGED", "-DBN254_CTA_LOCKSTEP", "-DBN254_ILP_MUL"],
+    "ilp": DEFAULT + ["-DBN254_ILP_MUL"],
+    "ls": DEFAULT + ["-DBN254_CTA_LOCKSTEP"],
+    "staged_inl": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_STAGED"],
     "inline_255": [],
     "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],

@@ -260,7 +260,7 @@ BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
   Fp12 acc;
   bool started = false;
   for (int i = 85; i >= 0; i--) {
-    if (started) { fp12_cyclo_sqr(acc, acc); fp12_cyclo_sqr(acc, acc); fp12_cyclo_sqr(acc, acc); }
+    if (started) fp12_cyclo_sqr_n(acc, acc, 3);
     int d = dg[i];
     if (d > 0) {
       if (started) fp12_mul(acc, acc, tab[d - 1]);

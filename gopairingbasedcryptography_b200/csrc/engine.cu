@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P
 #ifdef BN254_SMEM_SCRATCH
   cta_load(p, P, first, n - first, bn_dyn_smem);
   cta_load(q, Q, first, n - first, bn_dyn_smem);
+  // lockstep (BN254_CTA_LOCKSTEP) only when all threads of the CTA take the same path: full CTA, no infinity
+  bool plain = i < n && !g1_is_inf(p) && !g2_is_inf(q);
+  cta_lockstep_set(__syncthreads_and(plain) != 0);
   if (i < n) {
     miller_loop(f, &p, &q, &T, 1);
     final_exp(f, f);
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P
 // small products with a compile-time pair count (BLS verify: KC = 2): the pair loop unrolls
 template <int MODE, int KC>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair_c(const void* P, const void* Q, size_t n, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   G1Aff p[KC]; G2Aff q[KC]; G2Proj T[KC];
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair_c(const
 // mode 0: Miller product only; 1: + final exponentiation; 2: pairing check (writes one byte)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const void* P, const void* Q, size_t n, int k, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f;
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const v
 // partial Miller values of a product and finishes with ONE final exponentiation / check.
 constexpr int kMpChunk = 8;
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_partial(const void* P, const void* Q, size_t n, int k, int nchunks, void* partial) {
+  cta_lockstep_set(false);
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * (size_t)nchunks) return;
   size_t i = t / nchunks;
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_partial(const v
 }
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_combine(const void* partial, size_t n, int nchunks, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f, g;
@@ -173,6 +180,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_combine(const v
 }
 // ---- precomputed G2 lines (fixed G2 points: user keys / public parameters) ---------------------------------
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_g2_lines(const void* Q, size_t m, Fp2* table, uint8_t* qskip) {
+  cta_lockstep_set(false);
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   G2Aff q; load_struct(q, Q, j);
@@ -185,6 +193,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_g2_lines(const voi
 // served by L1; P[i][j] is the only per-thread operand.  out: partial[i * nchunks + chunk].
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const void* P, const Fp2* __restrict__ table, const uint8_t* __restrict__ qskip,
                                                                           size_t n, int m, int nchunks, void* partial) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int ci = blockIdx.y;
   if (i >= n) return;
@@ -215,6 +224,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
   store_struct(partial, i * (size_t)nchunks + ci, f);
 }
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const void* in, size_t n, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f; load_struct(f, in, i);
@@ -306,6 +316,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const 
 }
 template <int CYCLO>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 b; load_struct(b, x, i * x_stride);
@@ -320,6 +331,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void*
 // fixed-base GT exponentiation: out = prod_w table[w][byte_w(k)] -- 32 Fp12 products, no squarings.  The table
 // (32 x 255 x 384 B = 3.1 MB, L2-resident) is built once per base with k_gt_exp on the scalars d << 8w.
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const Fp12* table, const void* k, size_t n, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
@@ -341,6 +353,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const
 // mode 0: a*b ; mode 1: a/b
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
+  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 x, y; load_struct(x, a, i); load_struct(y, b, i);

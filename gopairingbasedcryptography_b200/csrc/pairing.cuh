@@ -20,11 +20,137 @@ struct G2Proj { Fp2 x, y, z; };
 BN_HD bool g1_is_inf(const G1Aff& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
 BN_HD bool g2_is_inf(const G2Aff& q) { return fp2_is_zero(q.x) && fp2_is_zero(q.y); }
 
+#ifdef BN254_STAGED
+// Staged G2 steps (see tower_staged.cuh): T is copied into the scratch once (one local-memory round trip), every
+// Fp2 product then runs out of shared memory, the new T goes straight back to memory and the raw line
+// (r0, r1, r2) is LEFT in sc[3..5], where apply_line_sc consumes it -- the coefficients never visit local memory.
+//
+// Tangent at T (homogeneous projective), T <- 2T.  With E = 3b'Z^2:
+//   X3 = XY/2 (Y^2 - 3E), Y3 = ((Y^2+3E)/2)^2 - 3E^2, Z3 = 2Y^3Z
+//   line (times a subfield factor) = (-2YZ) yP + (3X^2) xP w + (E - Y^2) w^3
+BN_NOINLINE void g2_dbl_step_sc(G2Proj& T, Fp2* sc) {
+  BN_SC_REBIND(sc)
+  BN_CTA_SYNC();
+  stage6(sc, reinterpret_cast<const Fp6&>(T));  // X, Y, Z
+  fp2_sqr(sc[3], sc[1]);                        // B = Y^2
+  fp2_sqr(sc[4], sc[2]);                        // C = Z^2
+  sc[8] = fp2_add(sc[1], sc[2]);
+  fp2_sqr(sc[8], sc[8]);
+  sc[8] = fp2_sub2(sc[8], sc[3], sc[4]);        // H = (Y+Z)^2 - B - C
+  fp2_sqr(sc[6], sc[0]);                        // J = X^2
+  fp2_mul(sc[7], sc[0], sc[1]);
+  sc[7] = fp2_half(sc[7]);                      // A = XY/2
+  fp2_mul(sc[4], sc[4], TWIST_3B);              // E = 3b' C
+  sc[0] = fp2_triple(sc[4]);                    // F = 3E
+  sc[1] = fp2_sub(sc[3], sc[0]);
+  fp2_mul(T.x, sc[7], sc[1]);                   // X3 = A (B - F)
+  sc[1] = fp2_add_half(sc[3], sc[0]);           // G = (B + F)/2
+  fp2_sqr(sc[1], sc[1]);
+  fp2_sqr(sc[2], sc[4]);                        // E^2
+  T.y = fp2_sub_triple(sc[1], sc[2]);           // Y3 = G^2 - 3E^2
+  fp2_mul(T.z, sc[3], sc[8]);                   // Z3 = B H
+  sc[5] = fp2_sub(sc[4], sc[3]);                // r2 = E - B
+  sc[3] = fp2_neg(sc[8]);                       // r0 = -H
+  sc[4] = fp2_triple(sc[6]);                    // r1 = 3J
+}
+// Chord through T and affine Q (negated when neg), T <- T + Q.  O = Y1 - y2 Z1, L = X1 - x2 Z1:
+//   line = L yP - O xP w + (O x2 - L y2) w^3
+BN_NOINLINE void g2_stage_tq(Fp2* sc, const G2Proj& T, const G2Aff& Q, bool neg) {
+  Fp2 x = fp2_ld(T.x), y = fp2_ld(T.y), z = fp2_ld(T.z), qx = fp2_ld(Q.x), qy = fp2_ld(Q.y);
+  if (neg) qy = fp2_neg_i(qy);
+  fp2_st(sc[0], x); fp2_st(sc[1], y); fp2_st(sc[2], z); fp2_st(sc[6], qx); fp2_st(sc[7], qy);
+}
+BN_NOINLINE void g2_add_step_sc(G2Proj& T, const G2Aff& Q, bool neg, bool update, Fp2* sc) {
+  BN_SC_REBIND(sc)
+  BN_CTA_SYNC();
+  g2_stage_tq(sc, T, Q, neg);
+  fp2_mul_rsub(sc[8], sc[7], sc[2], sc[1]);     // O = Y - y2 Z
+  fp2_mul_rsub(sc[3], sc[6], sc[2], sc[0]);     // L = X - x2 Z            (r0)
+  fp2_mul(sc[5], sc[6], sc[8]);
+  fp2_mul_rsub(sc[5], sc[3], sc[7], sc[5]);     // r2 = x2 O - L y2
+  sc[4] = fp2_neg(sc[8]);                       // r1 = -O
+  if (!update) return;
+  fp2_sqr(sc[6], sc[8]);                        // C = O^2
+  fp2_sqr(sc[7], sc[3]);                        // D = L^2
+  fp2_mul(sc[6], sc[2], sc[6]);                 // F = Z C
+  fp2_mul(sc[0], sc[0], sc[7]);                 // G = X D
+  fp2_mul(sc[7], sc[3], sc[7]);                 // E = L D
+  sc[6] = fp2_add_sub_dbl(sc[7], sc[6], sc[0]); // H = E + F - 2G
+  fp2_mul(T.x, sc[3], sc[6]);                   // X3 = L H
+  fp2_mul(sc[1], sc[1], sc[7]);                 // Y E
+  sc[0] = fp2_sub(sc[0], sc[6]);
+  fp2_mul(sc[0], sc[0], sc[8]);                 // (G - H) O
+  T.y = fp2_sub(sc[0], sc[1]);
+  fp2_mul(T.z, sc[7], sc[2]);                   // Z3 = E Z
+}
+// f *= line(P), raw line in sc[3..5]
+BN_NOINLINE void apply_line_sc(Fp12& f, const G1Aff& P, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc); }
+// line coefficients given in memory (line tables)
+BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, const Fp2& r2) {
+  BN_SCRATCH_DECL
+  {
+    Fp2 a = fp2_ld(r0), b = fp2_ld(r1), c = fp2_ld(r2);
+    fp2_st(sc_[3], a); fp2_st(sc_[4], b); fp2_st(sc_[5], c);
+  }
+  apply_line_sc(f, P, sc_);
+}
+// compatibility forms writing the line to memory (line-table precomputation)
+BN_HD void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
+  BN_SCRATCH_DECL
+  g2_dbl_step_sc(T, sc_);
+  r0 = sc_[3]; r1 = sc_[4]; r2 = sc_[5];
+}
+BN_HD void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, bool update) {
+  BN_SCRATCH_DECL
+  g2_add_step_sc(T, Q, false, update, sc_);
+  r0 = sc_[3]; r1 = sc_[4]; r2 = sc_[5];
+}
+
+template <int KC>
+BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k_rt) {
+  BN_SCRATCH_DECL
+  const int k = KC > 0 ? KC : k_rt;
+  fp12_set_one(f);
+  unsigned skip = 0;  // bit j set: pair j contains the point at infinity
+  for (int j = 0; j < k; j++) {
+    if (g1_is_inf(P[j]) || g2_is_inf(Q[j])) skip |= 1u << j;
+    T[j].x = Q[j].x; T[j].y = Q[j].y; T[j].z = fp2_one();
+  }
+  if (skip == (k >= 32 ? 0xffffffffu : ((1u << k) - 1u))) return;
+  for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
+    int d = ATE_NAF[i];
+#pragma unroll
+    for (int j = 0; j < k; j++) {
+      if ((skip >> j) & 1u) continue;
+      g2_dbl_step_sc(T[j], sc_);
+      apply_line_sc(f, P[j], sc_);
+      if (d) {
+        g2_add_step_sc(T[j], Q[j], d < 0, true, sc_);
+        apply_line_sc(f, P[j], sc_);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < k; j++) {
+    if ((skip >> j) & 1u) continue;
+    G2Aff q1, q2;
+    fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
+    fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
+    q2.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q2.y = Q[j].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
+    g2_add_step_sc(T[j], q1, false, true, sc_);
+    apply_line_sc(f, P[j], sc_);
+    g2_add_step_sc(T[j], q2, false, false, sc_);
+    apply_line_sc(f, P[j], sc_);
+  }
+}
+#else
 // Tangent at T (homogeneous projective), T <- 2T.  With E = 3b'Z^2:
 //   X3 = XY/2 (Y^2 - 3E), Y3 = ((Y^2+3E)/2)^2 - 3E^2, Z3 = 2Y^3Z
 //   line (times a subfield factor) = (-2YZ) yP + (3X^2) xP w + (E - Y^2) w^3
 BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
   BN_SCRATCH_DECL
+  BN_CTA_SYNC();
   Fp2 &A = sc_[0], &B = sc_[1], &C = sc_[2], &E = sc_[3], &F = sc_[4], &G = sc_[5], &H = sc_[6], &J = sc_[7], &t = sc_[8];
   fp2_mul(A, T.x, T.y); A = fp2_half(A);
   fp2_sqr(B, T.y);
@@ -47,6 +173,7 @@ BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
 //   line = L yP - O xP w + (O x2 - L y2) w^3
 BN_NOINLINE void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, bool update) {
   BN_SCRATCH_DECL
+  BN_CTA_SYNC();
   Fp2 &O = sc_[0], &L = sc_[1], &C = sc_[2], &D = sc_[3], &E = sc_[4], &F = sc_[5], &G = sc_[6], &H = sc_[7], &t = sc_[8];
   Fp2 t1;
   fp2_mul(t, Q.y, T.z); O = fp2_sub(T.y, t);
@@ -113,10 +240,12 @@ BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int
     apply_line(f, P[j], r0, r1, r2);
   }
 }
+#endif  // BN254_STAGED
 BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
   if (k == 1) miller_loop_t<1>(f, P, Q, T, 1);
   else miller_loop_t<0>(f, P, Q, T, k);
 }
+
 
 // ---- precomputed G2 line tables (north_star: fixed public-parameter / user-key G2 points) -----------------
 // The (r0, r1, r2) coefficients of every line of the Miller schedule depend on Q only.  For a fixed Q they are

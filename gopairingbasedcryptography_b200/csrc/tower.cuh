@@ -143,6 +143,35 @@ BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_inl(a, b); }
 #else
 BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_lazy(a, b); }
 #endif
+// -DBN254_ILP_MUL: the Fp2 product / square as ONE out-of-line by-value body whose 3 (2) Montgomery products run
+// interleaved (fp_mul_n); every leaf that multiplies calls it (FP2_MUL / FP2_SQR).
+#ifdef BN254_ILP_MUL
+BN_NOINLINE Fp2 fp2_mulx(Fp2 a, Fp2 b) {
+  Fp x[3] = {a.a0, a.a1, fp_add_noreduce(a.a0, a.a1)};
+  Fp y[3] = {b.a0, b.a1, fp_add_noreduce(b.a0, b.a1)};
+  Fp t[3];
+  fp_mul_n<3>(t, x, y);
+  Fp2 z;
+  z.a0 = fp_sub(t[0], t[1]);
+  z.a1 = fp_sub(fp_sub(t[2], t[0]), t[1]);
+  return z;
+}
+BN_NOINLINE Fp2 fp2_sqrx(Fp2 a) {
+  Fp x[2] = {a.a0, fp_add_noreduce(a.a0, a.a1)};
+  Fp y[2] = {a.a1, fp_sub(a.a0, a.a1)};
+  Fp t[2];
+  fp_mul_n<2>(t, x, y);
+  Fp2 z;
+  z.a0 = t[1];
+  z.a1 = fp_dbl(t[0]);
+  return z;
+}
+#define FP2_MUL(a, b) fp2_mulx(a, b)
+#define FP2_SQR(a) fp2_sqrx(a)
+#else
+#define FP2_MUL(a, b) fp2_mul_best(a, b)
+#define FP2_SQR(a) fp2_sqr_inl(a)
+#endif
 // out-of-line bodies shared by every tower routine
 #ifdef BN254_BYVAL_LEAVES
 BN_NOINLINE Fp2 fp2_mul_bv(Fp2 a, Fp2 b) { return fp2_mul_best(a, b); }
@@ -150,8 +179,8 @@ BN_NOINLINE Fp2 fp2_sqr_bv(Fp2 a) { return fp2_sqr_inl(a); }
 BN_HD void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_bv(a, b); }
 BN_HD void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_bv(a); }
 #else
-BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { fp2_st(z, fp2_mul_best(fp2_ld(a), fp2_ld(b))); }
-BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { fp2_st(z, fp2_sqr_inl(fp2_ld(a))); }
+BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { fp2_st(z, FP2_MUL(fp2_ld(a), fp2_ld(b))); }
+BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { fp2_st(z, FP2_SQR(fp2_ld(a))); }
 #endif
 BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
 BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
@@ -171,17 +200,35 @@ constexpr int kScratchStride = 592;
 extern __shared__ uint4 bn_dyn_smem[];
 BN_D Fp2* bn_scratch() { return reinterpret_cast<Fp2*>(reinterpret_cast<char*>(bn_dyn_smem) + threadIdx.x * kScratchStride); }
 #define BN_SCRATCH_DECL Fp2* sc_ = bn_scratch();
+// out-of-line routines that receive the scratch pointer re-derive it so the compiler knows it is shared memory
+#define BN_SC_REBIND(sc) sc = bn_scratch();
 #else
 #define BN_SCRATCH_DECL Fp2 sc_[kScratchSlots];
+#define BN_SC_REBIND(sc)
+#endif
+// -DBN254_CTA_LOCKSTEP: the warps of a CTA run the same instruction stream (one pairing per thread, no
+// data-dependent control flow), so keeping them loosely in step -- a CTA barrier at the entry of every composite
+// routine -- lets the four warps share each instruction-cache line fetched into the SM's L1.5 (32 KB against a
+// ~60 KB hot loop; ncu: no_instruction was the top stall of the staged build).  The barrier is taken only when the
+// kernel has established that EVERY thread of the CTA follows the same path (bn_lockstep, CTA-uniform).
+#if defined(BN254_CTA_LOCKSTEP) && defined(__CUDACC__)
+__shared__ int bn_lockstep;
+#define BN_CTA_SYNC() do { if (bn_lockstep) __syncthreads(); } while (0)
+BN_D void cta_lockstep_set(bool uniform) { __syncthreads(); if (threadIdx.x == 0) bn_lockstep = uniform ? 1 : 0; __syncthreads(); }
+#else
+#define BN_CTA_SYNC() do { } while (0)
+BN_D void cta_lockstep_set(bool) {}
 #endif
 // ------------------------------------------------------------------------------------------ Fp6
 BN_HD void fp6_add(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_add(x.b0, y.b0); z.b1 = fp2_add(x.b1, y.b1); z.b2 = fp2_add(x.b2, y.b2); }
 BN_HD void fp6_sub(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_sub(x.b0, y.b0); z.b1 = fp2_sub(x.b1, y.b1); z.b2 = fp2_sub(x.b2, y.b2); }
 BN_HD void fp6_neg(Fp6& z, const Fp6& x) { z.b0 = fp2_neg(x.b0); z.b1 = fp2_neg(x.b1); z.b2 = fp2_neg(x.b2); }
 BN_HD void fp6_mul_v(Fp6& z, const Fp6& x) { Fp2 t = fp2_mul_xi(x.b2); z.b2 = x.b1; z.b1 = x.b0; z.b0 = t; }
+#ifndef BN254_STAGED
 // Karatsuba, 6 Fp2 products.  z may alias x or y.
 BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
   BN_SCRATCH_DECL
+  BN_CTA_SYNC();
   Fp2 &v0 = sc_[0], &v1 = sc_[1], &v2 = sc_[2], &t = sc_[3], &u0 = sc_[4], &u1 = sc_[5], &s1 = sc_[6], &s2 = sc_[7];
   fp2_mul(v0, x.b0, y.b0);
   fp2_mul(v1, x.b1, y.b1);
@@ -197,6 +244,9 @@ BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
   z.b2 = fp2_add(fp2_sub(fp2_sub(t, v0), v2), v1);  // x, y are fully consumed: z may alias them
   z.b0 = u0; z.b1 = u1;
 }
+#else
+BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y);  // staged version below
+#endif
 BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
   Fp2 r0, r1, r2;
   fp2_mul(r0, x.b0, k); fp2_mul(r1, x.b1, k); fp2_mul(r2, x.b2, k);
@@ -205,6 +255,7 @@ BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
 // x * (c0 + c1 v), 5 Fp2 products
 BN_NOINLINE void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& c0, const Fp2& c1) {
   BN_SCRATCH_DECL
+  BN_CTA_SYNC();
   Fp2 &a = sc_[0], &b = sc_[1], &t = sc_[2], &r0 = sc_[3], &r2 = sc_[4], &s1 = sc_[5], &s2 = sc_[6];
   fp2_mul(a, x.b0, c0);
   fp2_mul(b, x.b1, c1);
@@ -241,6 +292,7 @@ BN_HD bool fp12_is_one(const Fp12& z) {
   return fp2_eq(z.c0.b0, fp2_one()) && fp2_is_zero(z.c0.b1) && fp2_is_zero(z.c0.b2) &&
          fp2_is_zero(z.c1.b0) && fp2_is_zero(z.c1.b1) && fp2_is_zero(z.c1.b2);
 }
+#ifndef BN254_STAGED
 BN_NOINLINE void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
   Fp6 a, b, s, t;
   fp6_mul(a, x.c0, y.c0);
@@ -260,6 +312,10 @@ BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x) {
   fp6_sub(s, s, m); fp6_mul_v(t, m); fp6_sub(z.c0, s, t);
   fp6_add(z.c1, m, m);
 }
+#else
+BN_NOINLINE void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y);
+BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x);
+#endif
 BN_HD void fp12_conj(Fp12& z, const Fp12& x) { z.c0 = x.c0; fp6_neg(z.c1, x.c1); }
 BN_NOINLINE void fp12_inv(Fp12& z, const Fp12& x) {
   Fp6 n, t;
@@ -280,6 +336,7 @@ BN_NOINLINE void fp12_frob(Fp12& z, const Fp12& x, int k) {
   }
   z.c0.b0 = g[0]; z.c1.b0 = g[1]; z.c0.b1 = g[2]; z.c1.b1 = g[3]; z.c0.b2 = g[4]; z.c1.b2 = g[5];
 }
+#ifndef BN254_STAGED
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
 // exponentiation).  Fp12 = Fp4[w]/(w^3 - s), s = w^3, s^2 = xi; z = A + B w + C w^2 with
 // A=(g0,g3) B=(g1,g4) C=(g2,g5):  z^2 = (3A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.
@@ -293,6 +350,7 @@ BN_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b, Fp2* tmp) {
 }
 BN_NOINLINE void fp12_cyclo_sqr(Fp12& z, const Fp12& x) {
   BN_SCRATCH_DECL
+  BN_CTA_SYNC();
   Fp2 &a0 = sc_[0], &a1 = sc_[1], &b0 = sc_[2], &b1 = sc_[3], &c0 = sc_[4], &c1 = sc_[5];
   fp4_sqr(a0, a1, x.c0.b0, x.c1.b1, sc_ + 6);
   fp4_sqr(b0, b1, x.c1.b0, x.c0.b2, sc_ + 6);
@@ -327,6 +385,10 @@ BN_NOINLINE void fp12_mul_conj(Fp12& z, const Fp12& x, const Fp12& y) {
   fp6_mul_v(b, b); fp6_sub(z.c0, a, b);
 }
 
+BN_HD void fp12_cyclo_sqr_n(Fp12& z, const Fp12& x, int n) { fp12_cyclo_sqr(z, x); for (int i = 1; i < n; i++) fp12_cyclo_sqr(z, z); }
+#else
+#include "tower_staged.cuh"
+#endif
 // x^e for x in the cyclotomic subgroup, e given as width-3 signed digits (LSB first); inverse = conjugate
 BN_NOINLINE void fp12_cyclo_exp_naf3(Fp12& z, const Fp12& x, const signed char* digits, int len) {
   // (copying the table entry and conjugating the copy measured 6 % FASTER on B200 than folding the conjugation
@@ -334,16 +396,19 @@ BN_NOINLINE void fp12_cyclo_exp_naf3(Fp12& z, const Fp12& x, const signed char* 
   Fp12 x3, acc, m;
   fp12_cyclo_sqr(x3, x); fp12_mul(x3, x3, x);
   bool started = false;
+  int pending = 0;  // squarings owed to acc: runs between non-zero digits are done in one staged pass
   for (int i = len - 1; i >= 0; i--) {
-    if (started) fp12_cyclo_sqr(acc, acc);
+    if (started) pending++;
     int d = digits[i];
     if (d) {
+      if (pending) { fp12_cyclo_sqr_n(acc, acc, pending); pending = 0; }
       int ad = d < 0 ? -d : d;
       if (ad == 1) m = x; else m = x3;
       if (d < 0) fp12_conj(m, m);
       if (started) fp12_mul(acc, acc, m); else { acc = m; started = true; }
     }
   }
+  if (pending) fp12_cyclo_sqr_n(acc, acc, pending);
   z = acc;
 }
 BN_HD void fp12_expt(Fp12& z, const Fp12& x) { fp12_cyclo_exp_naf3(z, x, X0_NAF3, X0_NAF3_LEN); }

@@ -15,7 +15,9 @@ import common
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "emu_bn254.cpp")
-SO = os.path.join(HERE, "emu", "_emu_bn254.so")
+# BN254_EMU_FLAGS: extra -D flags (e.g. "-DBN254_STAGED" / "-DBN254_LEGACY") to check a non-default device build
+EMU_FLAGS = os.environ.get("BN254_EMU_FLAGS", "").split()
+SO = os.path.join(HERE, "emu", "_emu_bn254%s.so" % ("_" + "_".join(f.lstrip("-D") for f in EMU_FLAGS) if EMU_FLAGS else ""))
 CSRC = os.path.join(HERE, "..", "gopairingbasedcryptography_b200", "csrc")
 
 
@@ -23,8 +25,8 @@ CSRC = os.path.join(HERE, "..", "gopairingbasedcryptography_b200", "csrc")
 def emu():
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL",
-                               "-o", SO, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL"] + EMU_FLAGS +
+                              ["-o", SO, SRC])
     return ctypes.CDLL(SO)
 
 
