@@ -7,40 +7,20 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# Default flags = the measured best of the profiles/r1 sweep: out-of-line add-type leaves and Montgomery
-# product (instruction footprint 380 KB -> 100 KB), 3 CTAs/SM (168 registers): 1.30M -> 2.03M pairings/s, and the
-# innermost Fp6 temporaries in a per-thread shared-memory scratch: -> 2.11M.
-DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH"]
+# Default flags = the measured best of the profiles/r1 sweeps: out-of-line add-type leaves and Montgomery product
+# (small instruction footprint), 3 CTAs/SM (168 registers), per-thread shared-memory scratch for the staged tower,
+# CTA lockstep barriers (the four warps of a CTA share instruction-cache lines).
+DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"]
+NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
-    "staged": DEFAULT + ["-DBN254_STAGED"],
-    "staged_ls": DEFAULT + ["-DBN254_STAGED", "-DBN254_CTA_LOCKSTEP"],
-    "staged_ls_ilp": DEFAULT + ["-DBN254_STAGED", "-DBN254_CTA_LOCKSTEP", "-DBN254_ILP_MUL"],
-    "ilp": DEFAULT + ["-DBN254_ILP_MUL"],
-    "ls": DEFAULT + ["-DBN254_CTA_LOCKSTEP"],
-    "staged_inl": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_STAGED"],
-    "inline_255": [],
-    "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
+    "nolockstep": NOLS,
+    "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
-    "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH"],
-    "blk64": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=6", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=64"],
-    "blk96": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=96"],
-    "blk192": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_BLOCK=192"],
-    "vmA": DEFAULT, "vmB": DEFAULT, "vmC": DEFAULT, "vmD": DEFAULT,
-    "byval": DEFAULT + ["-DBN254_BYVAL_LEAVES"],
-    "byval_b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_BYVAL_LEAVES"],
-    "byval_b4": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_BYVAL_LEAVES"],
+    "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
+    "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
     **{"k%dw%d" % (k, w): DEFAULT + ["-DBN254_VM_K=%d" % k, "-DBN254_VM_WARPS=%d" % w]
        for k in (1, 2, 3, 4, 6) for w in (1, 2, 3, 4, 6, 8)},
-    "b3": ["-DBN254_MIN_BLOCKS=3"],
-    "b4": ["-DBN254_MIN_BLOCKS=4"],
-    "ool": ["-DBN254_OOL_ADDS"],
-    "ool_b3": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=3"],
-    "ool_b4": ["-DBN254_OOL_ADDS", "-DBN254_MIN_BLOCKS=4"],
-    "oolm": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL"],
-    "oolm_b3": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
-    "oolm_b4": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4"],
-    "oolm_b6": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=6"],
 }
 VARIANT = os.environ.get("BN254_VARIANT", "")
 LIB = os.path.join(HERE, "lib", "libbn254_b200%s.so" % ("_" + VARIANT if VARIANT else ""))

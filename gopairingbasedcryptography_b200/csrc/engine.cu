@@ -51,6 +51,10 @@ __device__ __forceinline__ void store_struct(void* base, size_t idx, const T& sr
 }
 
 // Miller product of k pairs for one batch element, in passes of kPairChunk pairs.
+// UNIFORM: the caller guarantees that every thread of the CTA is live and walks the same (k, chunk) schedule; the
+// CTA then votes per pass whether any pair holds a point at infinity (the only data-dependent branch of the
+// Miller loop) and runs the pass in lockstep when none does.
+template <bool UNIFORM>
 __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t first, int k) {
   G1Aff p[kPairChunk];
   G2Aff q[kPairChunk];
@@ -58,7 +62,12 @@ __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t fir
   bool have = false;
   for (int base = 0; base < k; base += kPairChunk) {
     int c = min(kPairChunk, k - base);
-    for (int j = 0; j < c; j++) { load_struct(p[j], P, first + base + j); load_struct(q[j], Q, first + base + j); }
+    bool finite = true;
+    for (int j = 0; j < c; j++) {
+      load_struct(p[j], P, first + base + j); load_struct(q[j], Q, first + base + j);
+      finite = finite && !g1_is_inf(p[j]) && !g2_is_inf(q[j]);
+    }
+    if (UNIFORM) cta_lockstep_set(__syncthreads_and(finite) != 0);
     Fp12 g;
     Fp12& dst = have ? g : f;
     if (c == kPairChunk) miller_loop_t<kPairChunk>(dst, p, q, T, c);  // full passes: compile-time pair count
@@ -67,6 +76,7 @@ __device__ void miller_product(Fp12& f, const void* P, const void* Q, size_t fir
     have = true;
   }
 }
+__device__ __forceinline__ bool cta_is_full(size_t n) { return ((size_t)blockIdx.x + 1) * blockDim.x <= n; }
 
 // Coalesced CTA-wide staging: the kBlock operands of a CTA are contiguous in the caller's AoS arrays, so the CTA
 // copies them with unit-stride 128-bit accesses (every warp instruction touches one contiguous 512-byte span)
@@ -127,12 +137,18 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P
 // small products with a compile-time pair count (BLS verify: KC = 2): the pair loop unrolls
 template <int MODE, int KC>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair_c(const void* P, const void* Q, size_t n, void* out) {
-  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   G1Aff p[KC]; G2Aff q[KC]; G2Proj T[KC];
+  bool plain = i < n;
+  if (plain) {
 #pragma unroll
-  for (int j = 0; j < KC; j++) { load_struct(p[j], P, i * KC + j); load_struct(q[j], Q, i * KC + j); }
+    for (int j = 0; j < KC; j++) {
+      load_struct(p[j], P, i * KC + j); load_struct(q[j], Q, i * KC + j);
+      plain = plain && !g1_is_inf(p[j]) && !g2_is_inf(q[j]);
+    }
+  }
+  cta_lockstep_set(__syncthreads_and(plain) != 0);  // lockstep: full CTA without points at infinity
+  if (i >= n) return;
   Fp12 f;
   miller_loop_t<KC>(f, p, q, T, KC);
   if (MODE >= 1) final_exp(f, f);
@@ -146,7 +162,8 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const v
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f;
-  miller_product(f, P, Q, i * (size_t)k, k);
+  if (cta_is_full(n)) { miller_product<true>(f, P, Q, i * (size_t)k, k); cta_lockstep_set(true); }
+  else miller_product<false>(f, P, Q, i * (size_t)k, k);
   if (MODE >= 1) final_exp(f, f);
   if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
   else store_struct(out, i, f);
@@ -156,19 +173,20 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const v
 // partial Miller values of a product and finishes with ONE final exponentiation / check.
 constexpr int kMpChunk = 8;
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_partial(const void* P, const void* Q, size_t n, int k, int nchunks, void* partial) {
+  // grid: x = blocks of kBlock products, y = pair group: every thread of a CTA walks the same number of pairs
   cta_lockstep_set(false);
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * (size_t)nchunks) return;
-  size_t i = t / nchunks;
-  int ci = (int)(t % nchunks);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ci = blockIdx.y;
   int first = ci * kMpChunk, cnt = min(kMpChunk, k - first);
   Fp12 f;
-  miller_product(f, P, Q, i * (size_t)k + first, cnt);
-  store_struct(partial, t, f);
+  if (cta_is_full(n)) miller_product<true>(f, P, Q, i * (size_t)k + first, cnt);
+  else miller_product<false>(f, P, Q, i * (size_t)k + first, cnt);
+  store_struct(partial, i * (size_t)nchunks + ci, f);
 }
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_mp_combine(const void* partial, size_t n, int nchunks, void* out) {
-  cta_lockstep_set(false);
+  cta_lockstep_set(cta_is_full(n));
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f, g;
@@ -193,17 +211,19 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_g2_lines(const voi
 // served by L1; P[i][j] is the only per-thread operand.  out: partial[i * nchunks + chunk].
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const void* P, const Fp2* __restrict__ table, const uint8_t* __restrict__ qskip,
                                                                           size_t n, int m, int nchunks, void* partial) {
-  cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int ci = blockIdx.y;
-  if (i >= n) return;
   int first = ci * kMpChunk, cnt = min(kMpChunk, m - first);
   G1Aff p[kMpChunk];
   unsigned skip = 0;
-  for (int j = 0; j < cnt; j++) {
-    load_struct(p[j], P, i * (size_t)m + first + j);
-    if (g1_is_inf(p[j]) || qskip[first + j]) skip |= 1u << j;
+  if (i < n) {
+    for (int j = 0; j < cnt; j++) {
+      load_struct(p[j], P, i * (size_t)m + first + j);
+      if (g1_is_inf(p[j]) || qskip[first + j]) skip |= 1u << j;
+    }
   }
+  cta_lockstep_set(__syncthreads_and(i < n && skip == 0) != 0);  // lockstep: full CTA, no pair skipped
+  if (i >= n) return;
   Fp12 f;
   fp12_set_one(f);
   int s = 0;
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
   store_struct(partial, i * (size_t)nchunks + ci, f);
 }
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const void* in, size_t n, void* out) {
-  cta_lockstep_set(false);
+  cta_lockstep_set(cta_is_full(n));
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 f; load_struct(f, in, i);
@@ -699,7 +719,7 @@ cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, 
     if (e != cudaSuccess) return e;
     sl.mp_scratch_bytes = need;
   }
-  k_mp_partial<<<grid_for(n * (size_t)nchunks), kBlock, kTowerSmem, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
+  k_mp_partial<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
   k_mp_combine<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(sl.mp_scratch, n, nchunks, o);
   return cudaSuccess;
 }

@@ -228,67 +228,6 @@ BN_HD Fp fp_mul_v(const Fp& a, const Fp& b) {
 }
 BN_HD Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_v<BN254_MUL_VARIANT>(a, b); }
 
-// N independent Montgomery products advanced row by row, software-pipelined: while product k runs the reduction
-// half of a row, product k+1 runs the a*b half, so 4 carry chains are in flight instead of 2 and one warp alone
-// keeps the multiply pipe fed (ncu on k_pair: IMAD.WIDE issue was latency-bound, "wait" 60 % of the samples inside
-// the single-product routine with ~1.7 warps per scheduler multiplying at a time).
-// ptxas re-serialises independent products however they are written (and with all 2N chains free it runs out of
-// the 7 predicate registers that hold the carries and spills them through LOP3), so the overlap is pinned with a
-// data dependency it cannot remove: the carry out of a row's last word is zero by the bounds of the algorithm,
-// and that zero of product k is OR-ed into the multiplier word of product k+1's row.
-BN_HD void mont_row_next_tok(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi, uint32_t& tok) {
-#if defined(__CUDACC__)
-  asm volatile(
-      "add.cc.u32 %0, %0, %9;\n\t"
-      "madc.lo.cc.u32 %8, %17, %21, %10;\n\t madc.hi.cc.u32 %9, %17, %21, %11;\n\t"
-      "madc.lo.cc.u32 %10, %18, %21, %12;\n\t madc.hi.cc.u32 %11, %18, %21, %13;\n\t"
-      "madc.lo.cc.u32 %12, %19, %21, %14;\n\t madc.hi.cc.u32 %13, %19, %21, %15;\n\t"
-      "madc.lo.cc.u32 %14, %20, %21, 0;\n\t madc.hi.u32 %15, %20, %21, 0;\n\t"
-      "mad.lo.cc.u32 %0, %22, %21, %0;\n\t madc.hi.cc.u32 %1, %22, %21, %1;\n\t"
-      "madc.lo.cc.u32 %2, %23, %21, %2;\n\t madc.hi.cc.u32 %3, %23, %21, %3;\n\t"
-      "madc.lo.cc.u32 %4, %24, %21, %4;\n\t madc.hi.cc.u32 %5, %24, %21, %5;\n\t"
-      "madc.lo.cc.u32 %6, %25, %21, %6;\n\t madc.hi.cc.u32 %7, %25, %21, %7;\n\t"
-      "addc.cc.u32 %15, %15, 0;\n\t"
-      "addc.u32 %16, 0, 0;"
-      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
-        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "=r"(tok)
-      : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi), "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]));
-#else
-  mont_row_next(ev, od, a, bi);
-  tok = 0;  // the carry out of od[7] + carry: never set (row value < 2^288)
-#endif
-}
-template <int N>
-BN_HD void fp_mul_n(Fp* z, const Fp* a, const Fp* b) {
-  uint32_t e[N][8], o[N][8];
-  uint32_t tok = 0;
-#pragma unroll
-  for (int k = 0; k < N; k++) { mont_row_first(e[k], o[k], a[k].l, b[k].l[0]); mont_row_reduce(e[k], o[k]); }
-#pragma unroll
-  for (int i = 1; i < 8; i += 2) {
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-      mont_row_next_tok(o[k], e[k], a[k].l, b[k].l[i] | tok, tok);
-      mont_row_reduce(o[k], e[k]);
-    }
-    if (i + 1 < 8) {
-#pragma unroll
-      for (int k = 0; k < N; k++) {
-        mont_row_next_tok(e[k], o[k], a[k].l, b[k].l[i + 1] | tok, tok);
-        mont_row_reduce(e[k], o[k]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    Fp r;
-    r.l[0] = add_cc(e[k][0], o[k][1]); r.l[1] = addc_cc(e[k][1], o[k][2]); r.l[2] = addc_cc(e[k][2], o[k][3]); r.l[3] = addc_cc(e[k][3], o[k][4]);
-    r.l[4] = addc_cc(e[k][4], o[k][5]); r.l[5] = addc_cc(e[k][5], o[k][6]); r.l[6] = addc_cc(e[k][6], o[k][7]); r.l[7] = addc(e[k][7], 0u);
-    fp_reduce_once(r);
-    z[k] = r;
-  }
-}
-
 BN_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 
 // ---- lazy reduction building blocks (Aranha et al. style): a wide 8x8 -> 16-limb product and a

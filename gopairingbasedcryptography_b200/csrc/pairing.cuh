@@ -20,7 +20,6 @@ struct G2Proj { Fp2 x, y, z; };
 BN_HD bool g1_is_inf(const G1Aff& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
 BN_HD bool g2_is_inf(const G2Aff& q) { return fp2_is_zero(q.x) && fp2_is_zero(q.y); }
 
-#ifdef BN254_STAGED
 // Staged G2 steps (see tower_staged.cuh): T is copied into the scratch once (one local-memory round trip), every
 // Fp2 product then runs out of shared memory, the new T goes straight back to memory and the raw line
 // (r0, r1, r2) is LEFT in sc[3..5], where apply_line_sc consumes it -- the coefficients never visit local memory.
@@ -144,103 +143,6 @@ BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int
     apply_line_sc(f, P[j], sc_);
   }
 }
-#else
-// Tangent at T (homogeneous projective), T <- 2T.  With E = 3b'Z^2:
-//   X3 = XY/2 (Y^2 - 3E), Y3 = ((Y^2+3E)/2)^2 - 3E^2, Z3 = 2Y^3Z
-//   line (times a subfield factor) = (-2YZ) yP + (3X^2) xP w + (E - Y^2) w^3
-BN_NOINLINE void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {
-  BN_SCRATCH_DECL
-  BN_CTA_SYNC();
-  Fp2 &A = sc_[0], &B = sc_[1], &C = sc_[2], &E = sc_[3], &F = sc_[4], &G = sc_[5], &H = sc_[6], &J = sc_[7], &t = sc_[8];
-  fp2_mul(A, T.x, T.y); A = fp2_half(A);
-  fp2_sqr(B, T.y);
-  fp2_sqr(C, T.z);
-  fp2_mul(E, C, TWIST_3B);
-  F = fp2_add(fp2_dbl(E), E);
-  G = fp2_half(fp2_add(B, F));
-  fp2_sqr(H, fp2_add(T.y, T.z)); H = fp2_sub(fp2_sub(H, B), C);
-  fp2_sqr(J, T.x);
-  fp2_mul(T.x, A, fp2_sub(B, F));
-  fp2_sqr(t, E);
-  fp2_sqr(G, G);
-  T.y = fp2_sub(G, fp2_add(fp2_dbl(t), t));
-  fp2_mul(T.z, B, H);
-  r0 = fp2_neg(H);
-  r1 = fp2_add(fp2_dbl(J), J);
-  r2 = fp2_sub(E, B);
-}
-// Chord through T and affine Q, T <- T + Q.  O = Y1 - y2 Z1, L = X1 - x2 Z1:
-//   line = L yP - O xP w + (O x2 - L y2) w^3
-BN_NOINLINE void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, bool update) {
-  BN_SCRATCH_DECL
-  BN_CTA_SYNC();
-  Fp2 &O = sc_[0], &L = sc_[1], &C = sc_[2], &D = sc_[3], &E = sc_[4], &F = sc_[5], &G = sc_[6], &H = sc_[7], &t = sc_[8];
-  Fp2 t1;
-  fp2_mul(t, Q.y, T.z); O = fp2_sub(T.y, t);
-  fp2_mul(t, Q.x, T.z); L = fp2_sub(T.x, t);
-  fp2_mul(t, L, Q.y); fp2_mul(t1, Q.x, O);
-  r2 = fp2_sub(t1, t);
-  r0 = L;
-  r1 = fp2_neg(O);
-  if (!update) return;
-  fp2_sqr(C, O); fp2_sqr(D, L);
-  fp2_mul(E, L, D);
-  fp2_mul(F, T.z, C);
-  fp2_mul(G, T.x, D);
-  H = fp2_sub(fp2_add(E, F), fp2_dbl(G));
-  fp2_mul(t1, T.y, E);
-  fp2_mul(T.x, L, H);
-  fp2_mul(t, fp2_sub(G, H), O);
-  T.y = fp2_sub(t, t1);
-  fp2_mul(T.z, E, T.z);
-}
-BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, const Fp2& r2) {
-  fp12_mul_034(f, fp2_mul_fp(r0, P.y), fp2_mul_fp(r1, P.x), r2);
-}
-
-// Product of the Miller functions of k pairs with shared squarings (pairs containing infinity are skipped).
-// KC > 0: k == KC is a compile-time constant (loops over the pairs unroll, T[j] indexing is static);
-// KC == 0: run-time k.  T: scratch of k projective points.
-template <int KC>
-BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k_rt) {
-  const int k = KC > 0 ? KC : k_rt;
-  fp12_set_one(f);
-  unsigned skip = 0;  // bit j set: pair j contains the point at infinity
-  for (int j = 0; j < k; j++) {
-    if (g1_is_inf(P[j]) || g2_is_inf(Q[j])) skip |= 1u << j;
-    T[j].x = Q[j].x; T[j].y = Q[j].y; T[j].z = fp2_one();
-  }
-  if (skip == (k >= 32 ? 0xffffffffu : ((1u << k) - 1u))) return;
-  Fp2 r0, r1, r2;
-  for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
-    if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
-    int d = ATE_NAF[i];
-#pragma unroll
-    for (int j = 0; j < k; j++) {
-      if ((skip >> j) & 1u) continue;
-      g2_dbl_step(T[j], r0, r1, r2);
-      apply_line(f, P[j], r0, r1, r2);
-      if (d) {
-        if (d > 0) g2_add_step(T[j], Q[j], r0, r1, r2, true);
-        else { G2Aff q; q.x = Q[j].x; q.y = fp2_neg(Q[j].y); g2_add_step(T[j], q, r0, r1, r2, true); }
-        apply_line(f, P[j], r0, r1, r2);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < k; j++) {
-    if ((skip >> j) & 1u) continue;
-    G2Aff q1, q2;
-    fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
-    fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
-    q2.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q2.y = Q[j].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
-    g2_add_step(T[j], q1, r0, r1, r2, true);
-    apply_line(f, P[j], r0, r1, r2);
-    g2_add_step(T[j], q2, r0, r1, r2, false);
-    apply_line(f, P[j], r0, r1, r2);
-  }
-}
-#endif  // BN254_STAGED
 BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
   if (k == 1) miller_loop_t<1>(f, P, Q, T, 1);
   else miller_loop_t<0>(f, P, Q, T, k);
@@ -276,7 +178,9 @@ BN_NOINLINE void final_exp(Fp12& out, const Fp12& in) {
   Fp12 f, t0, t1, t2, t3, t4;
   fp12_conj(t0, in); fp12_inv(f, in); fp12_mul(t0, t0, f);
   fp12_frob(f, t0, 2); fp12_mul(f, f, t0);
-  if (fp12_is_one(f)) { out = f; return; }
+  // gnark returns early when the easy part is 1.  The hard part maps 1 to 1, so under CTA lockstep (where a
+  // data-dependent exit would leave the other warps waiting at a barrier) the thread simply computes on.
+  if (!cta_lockstep_on() && fp12_is_one(f)) { out = f; return; }
   fp12_expt(t0, f); fp12_conj(t0, t0); fp12_cyclo_sqr(t0, t0);
   fp12_cyclo_sqr(t1, t0); fp12_mul(t1, t0, t1);
   fp12_expt(t2, t1); fp12_conj(t2, t2);

@@ -74,18 +74,6 @@ BN_HD Fp2 fp2_mul_xi_i(const Fp2& a) {
   z.a1 = fp_add(fp_add(e1, a.a1), a.a0);
   return z;
 }
-#ifdef BN254_BYVAL_LEAVES
-// operands and results travel in registers across the out-of-line call: Fp2 temporaries of the callers no
-// longer have to live in local memory (ncu: CALL / IADD3 stalls were ~60-95% long-scoreboard on LDL)
-BN_LEAF Fp2 fp2_add(Fp2 a, Fp2 b) { return fp2_add_i(a, b); }
-BN_LEAF Fp2 fp2_sub(Fp2 a, Fp2 b) { return fp2_sub_i(a, b); }
-BN_LEAF Fp2 fp2_dbl(Fp2 a) { return fp2_dbl_i(a); }
-BN_LEAF Fp2 fp2_neg(Fp2 a) { return fp2_neg_i(a); }
-BN_LEAF Fp2 fp2_conj(Fp2 a) { return fp2_conj_i(a); }
-BN_LEAF Fp2 fp2_half(Fp2 a) { return fp2_half_i(a); }
-BN_LEAF Fp2 fp2_mul_fp(Fp2 a, Fp k) { return fp2_mul_fp_i(a, k); }
-BN_LEAF Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_i(a); }
-#else
 BN_LEAF Fp2 fp2_add(const Fp2& a, const Fp2& b) { return fp2_add_i(fp2_ld(a), fp2_ld(b)); }
 BN_LEAF Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return fp2_sub_i(fp2_ld(a), fp2_ld(b)); }
 BN_LEAF Fp2 fp2_dbl(const Fp2& a) { return fp2_dbl_i(fp2_ld(a)); }
@@ -94,7 +82,6 @@ BN_LEAF Fp2 fp2_conj(const Fp2& a) { return fp2_conj_i(fp2_ld(a)); }
 BN_LEAF Fp2 fp2_half(const Fp2& a) { return fp2_half_i(fp2_ld(a)); }
 BN_LEAF Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return fp2_mul_fp_i(fp2_ld(a), fp_ld(k)); }
 BN_LEAF Fp2 fp2_mul_xi(const Fp2& a) { return fp2_mul_xi_i(fp2_ld(a)); }
-#endif
 // Karatsuba: 3 Fp products
 BN_HD Fp2 fp2_mul_inl(const Fp2& a, const Fp2& b) {
   Fp t0 = FP_MUL(a.a0, b.a0);
@@ -143,45 +130,11 @@ BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_inl(a, b); }
 #else
 BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_lazy(a, b); }
 #endif
-// -DBN254_ILP_MUL: the Fp2 product / square as ONE out-of-line by-value body whose 3 (2) Montgomery products run
-// interleaved (fp_mul_n); every leaf that multiplies calls it (FP2_MUL / FP2_SQR).
-#ifdef BN254_ILP_MUL
-BN_NOINLINE Fp2 fp2_mulx(Fp2 a, Fp2 b) {
-  Fp x[3] = {a.a0, a.a1, fp_add_noreduce(a.a0, a.a1)};
-  Fp y[3] = {b.a0, b.a1, fp_add_noreduce(b.a0, b.a1)};
-  Fp t[3];
-  fp_mul_n<3>(t, x, y);
-  Fp2 z;
-  z.a0 = fp_sub(t[0], t[1]);
-  z.a1 = fp_sub(fp_sub(t[2], t[0]), t[1]);
-  return z;
-}
-BN_NOINLINE Fp2 fp2_sqrx(Fp2 a) {
-  Fp x[2] = {a.a0, fp_add_noreduce(a.a0, a.a1)};
-  Fp y[2] = {a.a1, fp_sub(a.a0, a.a1)};
-  Fp t[2];
-  fp_mul_n<2>(t, x, y);
-  Fp2 z;
-  z.a0 = t[1];
-  z.a1 = fp_dbl(t[0]);
-  return z;
-}
-#define FP2_MUL(a, b) fp2_mulx(a, b)
-#define FP2_SQR(a) fp2_sqrx(a)
-#else
 #define FP2_MUL(a, b) fp2_mul_best(a, b)
 #define FP2_SQR(a) fp2_sqr_inl(a)
-#endif
 // out-of-line bodies shared by every tower routine
-#ifdef BN254_BYVAL_LEAVES
-BN_NOINLINE Fp2 fp2_mul_bv(Fp2 a, Fp2 b) { return fp2_mul_best(a, b); }
-BN_NOINLINE Fp2 fp2_sqr_bv(Fp2 a) { return fp2_sqr_inl(a); }
-BN_HD void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { z = fp2_mul_bv(a, b); }
-BN_HD void fp2_sqr(Fp2& z, const Fp2& a) { z = fp2_sqr_bv(a); }
-#else
 BN_NOINLINE void fp2_mul(Fp2& z, const Fp2& a, const Fp2& b) { fp2_st(z, FP2_MUL(fp2_ld(a), fp2_ld(b))); }
 BN_NOINLINE void fp2_sqr(Fp2& z, const Fp2& a) { fp2_st(z, FP2_SQR(fp2_ld(a))); }
-#endif
 BN_NOINLINE void fp_inv_ool(Fp& z, const Fp& a) { z = fp_inv(a); }
 BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
   Fp n = fp_add(fp_sqr(a.a0), fp_sqr(a.a1));
@@ -215,61 +168,18 @@ BN_D Fp2* bn_scratch() { return reinterpret_cast<Fp2*>(reinterpret_cast<char*>(b
 __shared__ int bn_lockstep;
 #define BN_CTA_SYNC() do { if (bn_lockstep) __syncthreads(); } while (0)
 BN_D void cta_lockstep_set(bool uniform) { __syncthreads(); if (threadIdx.x == 0) bn_lockstep = uniform ? 1 : 0; __syncthreads(); }
+BN_D bool cta_lockstep_on() { return bn_lockstep != 0; }
 #else
 #define BN_CTA_SYNC() do { } while (0)
 BN_D void cta_lockstep_set(bool) {}
+BN_D bool cta_lockstep_on() { return false; }
 #endif
 // ------------------------------------------------------------------------------------------ Fp6
 BN_HD void fp6_add(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_add(x.b0, y.b0); z.b1 = fp2_add(x.b1, y.b1); z.b2 = fp2_add(x.b2, y.b2); }
 BN_HD void fp6_sub(Fp6& z, const Fp6& x, const Fp6& y) { z.b0 = fp2_sub(x.b0, y.b0); z.b1 = fp2_sub(x.b1, y.b1); z.b2 = fp2_sub(x.b2, y.b2); }
 BN_HD void fp6_neg(Fp6& z, const Fp6& x) { z.b0 = fp2_neg(x.b0); z.b1 = fp2_neg(x.b1); z.b2 = fp2_neg(x.b2); }
 BN_HD void fp6_mul_v(Fp6& z, const Fp6& x) { Fp2 t = fp2_mul_xi(x.b2); z.b2 = x.b1; z.b1 = x.b0; z.b0 = t; }
-#ifndef BN254_STAGED
-// Karatsuba, 6 Fp2 products.  z may alias x or y.
-BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y) {
-  BN_SCRATCH_DECL
-  BN_CTA_SYNC();
-  Fp2 &v0 = sc_[0], &v1 = sc_[1], &v2 = sc_[2], &t = sc_[3], &u0 = sc_[4], &u1 = sc_[5], &s1 = sc_[6], &s2 = sc_[7];
-  fp2_mul(v0, x.b0, y.b0);
-  fp2_mul(v1, x.b1, y.b1);
-  fp2_mul(v2, x.b2, y.b2);
-  s1 = fp2_add(x.b1, x.b2); s2 = fp2_add(y.b1, y.b2);
-  fp2_mul(t, s1, s2);
-  u0 = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(t, v1), v2)), v0);
-  s1 = fp2_add(x.b0, x.b1); s2 = fp2_add(y.b0, y.b1);
-  fp2_mul(t, s1, s2);
-  u1 = fp2_add(fp2_sub(fp2_sub(t, v0), v1), fp2_mul_xi(v2));
-  s1 = fp2_add(x.b0, x.b2); s2 = fp2_add(y.b0, y.b2);
-  fp2_mul(t, s1, s2);
-  z.b2 = fp2_add(fp2_sub(fp2_sub(t, v0), v2), v1);  // x, y are fully consumed: z may alias them
-  z.b0 = u0; z.b1 = u1;
-}
-#else
-BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y);  // staged version below
-#endif
-BN_HD void fp6_mul_fp2(Fp6& z, const Fp6& x, const Fp2& k) {
-  Fp2 r0, r1, r2;
-  fp2_mul(r0, x.b0, k); fp2_mul(r1, x.b1, k); fp2_mul(r2, x.b2, k);
-  z.b0 = r0; z.b1 = r1; z.b2 = r2;
-}
-// x * (c0 + c1 v), 5 Fp2 products
-BN_NOINLINE void fp6_mul_01(Fp6& z, const Fp6& x, const Fp2& c0, const Fp2& c1) {
-  BN_SCRATCH_DECL
-  BN_CTA_SYNC();
-  Fp2 &a = sc_[0], &b = sc_[1], &t = sc_[2], &r0 = sc_[3], &r2 = sc_[4], &s1 = sc_[5], &s2 = sc_[6];
-  fp2_mul(a, x.b0, c0);
-  fp2_mul(b, x.b1, c1);
-  s1 = fp2_add(x.b1, x.b2);
-  fp2_mul(t, s1, c1);
-  r0 = fp2_add(fp2_mul_xi(fp2_sub(t, b)), a);
-  s1 = fp2_add(x.b0, x.b2);
-  fp2_mul(t, s1, c0);
-  r2 = fp2_add(fp2_sub(t, a), b);
-  s1 = fp2_add(x.b0, x.b1); s2 = fp2_add(c0, c1);
-  fp2_mul(t, s1, s2);
-  z.b1 = fp2_sub(fp2_sub(t, a), b);
-  z.b0 = r0; z.b2 = r2;
-}
+BN_NOINLINE void fp6_mul(Fp6& z, const Fp6& x, const Fp6& y);  // tower_staged.cuh
 BN_NOINLINE void fp6_inv(Fp6& z, const Fp6& x) {
   Fp2 t0, t1, t2, s, n;
   fp2_sqr(t0, x.b0); fp2_mul(s, x.b1, x.b2); t0 = fp2_sub(t0, fp2_mul_xi(s));
@@ -292,30 +202,8 @@ BN_HD bool fp12_is_one(const Fp12& z) {
   return fp2_eq(z.c0.b0, fp2_one()) && fp2_is_zero(z.c0.b1) && fp2_is_zero(z.c0.b2) &&
          fp2_is_zero(z.c1.b0) && fp2_is_zero(z.c1.b1) && fp2_is_zero(z.c1.b2);
 }
-#ifndef BN254_STAGED
-BN_NOINLINE void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y) {
-  Fp6 a, b, s, t;
-  fp6_mul(a, x.c0, y.c0);
-  fp6_mul(b, x.c1, y.c1);
-  fp6_add(s, x.c0, x.c1); fp6_add(t, y.c0, y.c1);
-  fp6_mul(s, s, t);
-  fp6_sub(s, s, a); fp6_sub(z.c1, s, b);
-  fp6_mul_v(b, b); fp6_add(z.c0, a, b);
-}
-// complex squaring, 2 Fp6 products
-BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x) {
-  Fp6 m, s, t;
-  fp6_mul(m, x.c0, x.c1);
-  fp6_add(s, x.c0, x.c1);
-  fp6_mul_v(t, x.c1); fp6_add(t, t, x.c0);
-  fp6_mul(s, s, t);  // c0^2 + v c1^2 + (1+v) c0 c1
-  fp6_sub(s, s, m); fp6_mul_v(t, m); fp6_sub(z.c0, s, t);
-  fp6_add(z.c1, m, m);
-}
-#else
 BN_NOINLINE void fp12_mul(Fp12& z, const Fp12& x, const Fp12& y);
 BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x);
-#endif
 BN_HD void fp12_conj(Fp12& z, const Fp12& x) { z.c0 = x.c0; fp6_neg(z.c1, x.c1); }
 BN_NOINLINE void fp12_inv(Fp12& z, const Fp12& x) {
   Fp6 n, t;
@@ -336,59 +224,7 @@ BN_NOINLINE void fp12_frob(Fp12& z, const Fp12& x, int k) {
   }
   z.c0.b0 = g[0]; z.c1.b0 = g[1]; z.c0.b1 = g[2]; z.c1.b1 = g[3]; z.c0.b2 = g[4]; z.c1.b2 = g[5];
 }
-#ifndef BN254_STAGED
-// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final
-// exponentiation).  Fp12 = Fp4[w]/(w^3 - s), s = w^3, s^2 = xi; z = A + B w + C w^2 with
-// A=(g0,g3) B=(g1,g4) C=(g2,g5):  z^2 = (3A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3 B^2 - 2 conj C) w^2.
-BN_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b, Fp2* tmp) {
-  Fp2 &a2 = tmp[0], &b2 = tmp[1], &s = tmp[2];
-  fp2_sqr(a2, a); fp2_sqr(b2, b);
-  s = fp2_add(a, b);
-  fp2_sqr(s, s);
-  r1 = fp2_sub(fp2_sub(s, a2), b2);
-  r0 = fp2_add(a2, fp2_mul_xi(b2));
-}
-BN_NOINLINE void fp12_cyclo_sqr(Fp12& z, const Fp12& x) {
-  BN_SCRATCH_DECL
-  BN_CTA_SYNC();
-  Fp2 &a0 = sc_[0], &a1 = sc_[1], &b0 = sc_[2], &b1 = sc_[3], &c0 = sc_[4], &c1 = sc_[5];
-  fp4_sqr(a0, a1, x.c0.b0, x.c1.b1, sc_ + 6);
-  fp4_sqr(b0, b1, x.c1.b0, x.c0.b2, sc_ + 6);
-  fp4_sqr(c0, c1, x.c0.b1, x.c1.b2, sc_ + 6);
-  c1 = fp2_mul_xi(c1);
-  // every g_i of x is read only by its own output coefficient, so z may alias x without copies
-  z.c0.b0 = fp2_add(fp2_dbl(fp2_sub(a0, x.c0.b0)), a0);  // 3 a0 - 2 g0
-  z.c1.b1 = fp2_add(fp2_dbl(fp2_add(a1, x.c1.b1)), a1);  // 3 a1 + 2 g3
-  z.c0.b1 = fp2_add(fp2_dbl(fp2_sub(b0, x.c0.b1)), b0);
-  z.c1.b2 = fp2_add(fp2_dbl(fp2_add(b1, x.c1.b2)), b1);
-  z.c1.b0 = fp2_add(fp2_dbl(fp2_add(c1, x.c1.b0)), c1);  // 3 xi c1 + 2 g1
-  z.c0.b2 = fp2_add(fp2_dbl(fp2_sub(c0, x.c0.b2)), c0);  // 3 c0 - 2 g4
-}
-// z *= l0 + l1 w + l3 w^3  (sparse "034" line), 13 Fp2 products
-BN_NOINLINE void fp12_mul_034(Fp12& z, const Fp2& l0, const Fp2& l1, const Fp2& l3) {
-  Fp6 a, b, s;
-  fp6_mul_fp2(a, z.c0, l0);
-  fp6_mul_01(b, z.c1, l1, l3);
-  fp6_add(s, z.c0, z.c1);
-  fp6_mul_01(s, s, fp2_add(l0, l1), l3);
-  fp6_sub(s, s, a); fp6_sub(z.c1, s, b);
-  fp6_mul_v(b, b); fp6_add(z.c0, a, b);
-}
-// x * conj(y) without materialising conj(y) = (y0, -y1)
-BN_NOINLINE void fp12_mul_conj(Fp12& z, const Fp12& x, const Fp12& y) {
-  Fp6 a, b, s, t;
-  fp6_mul(a, x.c0, y.c0);
-  fp6_mul(b, x.c1, y.c1);
-  fp6_add(s, x.c0, x.c1); fp6_sub(t, y.c0, y.c1);
-  fp6_mul(s, s, t);
-  fp6_sub(s, s, a); fp6_add(z.c1, s, b);
-  fp6_mul_v(b, b); fp6_sub(z.c0, a, b);
-}
-
-BN_HD void fp12_cyclo_sqr_n(Fp12& z, const Fp12& x, int n) { fp12_cyclo_sqr(z, x); for (int i = 1; i < n; i++) fp12_cyclo_sqr(z, z); }
-#else
 #include "tower_staged.cuh"
-#endif
 // x^e for x in the cyclotomic subgroup, e given as width-3 signed digits (LSB first); inverse = conjugate
 BN_NOINLINE void fp12_cyclo_exp_naf3(Fp12& z, const Fp12& x, const signed char* digits, int len) {
   // (copying the table entry and conjugating the copy measured 6 % FASTER on B200 than folding the conjugation

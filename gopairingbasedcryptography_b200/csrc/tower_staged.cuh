@@ -1,4 +1,4 @@
-// Staged tower routines (included from tower.cuh INSIDE namespace bn254 when BN254_STAGED is defined).
+// Staged tower routines: the hot Fp6/Fp12 composites (included from tower.cuh INSIDE namespace bn254).
 //
 // Why: in the one-thread-per-pairing kernels every Fp12/Fp6 value lives on the per-thread local-memory stack.
 // With 227 KB of the SM given to the shared-memory scratch the L1 keeps ~75 B per thread, so every local

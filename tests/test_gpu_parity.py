@@ -99,6 +99,42 @@ def test_split_multi_pair_large_k(engine):
     assert (ok == port.pairing_check_batch(P, Q, n, k, 8).astype(bool)).all()
 
 
+def test_full_cta_lockstep_paths(engine):
+    """Full CTAs of 128 elements take the barrier-synchronised (lockstep) path of the pairing kernels; CTAs that are
+    ragged or hold a point at infinity fall back to the free-running one.  Both must agree with the oracle, including
+    elements whose final exponentiation leaves the easy part at 1 (gnark's early return) next to ones that do not."""
+    for k, n in ((1, 256 + 3), (2, 256), (3, 128 + 1), (5, 128 + 2), (9, 128), (37, 128 + 1)):
+        P, Q, _, _ = common.points(n * k, seed=7000 + k, threads=8)
+        P, Q = P.copy(), Q.copy()
+        if k >= 2:
+            # element 5: e(A,B) e(-A,B) -> the Miller product dies in the easy part; element n-1: infinity member
+            A, B = P[:64].copy(), Q[:128].copy()
+            negA = A.copy()
+            y = int.from_bytes(A[32:64].tobytes(), "little")
+            negA[32:64] = np.frombuffer(((o.P - y) % o.P).to_bytes(32, "little"), dtype=np.uint8)
+            base = 5 * k
+            P[64 * base:64 * (base + 1)] = A
+            Q[128 * base:128 * (base + 1)] = B
+            P[64 * (base + 1):64 * (base + 2)] = negA
+            Q[128 * (base + 1):128 * (base + 2)] = B
+            for j in range(2, k):
+                P[64 * (base + j):64 * (base + j + 1)] = 0
+            P[64 * ((n - 1) * k):64 * ((n - 1) * k + 1)] = 0
+        ref = port.multi_pair_batch(P, Q, n, k, 8) if k > 1 else port.pair_batch(P, Q, n, 8)
+        got = engine.multi_pair_batch(P, Q, k) if k > 1 else engine.pair_batch(P, Q)
+        assert (got.reshape(-1) == ref).all(), k
+        if k > 1:
+            assert got[5].tobytes() == o.gt_to_bytes(o.FP12_ONE)
+            assert (engine.final_exp_batch(engine.miller_loop_batch(P, Q, k)).reshape(-1) == ref).all(), k
+            assert (engine.pairing_check_batch(P, Q, k) == port.pairing_check_batch(P, Q, n, k, 8).astype(bool)).all(), k
+    # final exponentiation alone on a full CTA holding 1, 0 and random Fp12 values
+    rng = o.SplitMix64(31337)
+    vals = [o.FP12_ONE] + [tuple(tuple((rng.fp(), rng.fp()) for _ in range(3)) for _ in range(2)) for _ in range(127)]
+    buf = np.frombuffer(b"".join(o.gt_to_bytes(v) for v in vals), dtype=np.uint8).copy()
+    buf[384:768] = 0
+    assert (engine.final_exp_batch(buf).reshape(-1) == port.final_exp_batch(buf, 128, 8)).all()
+
+
 def test_fixed_base_tables(engine):
     """>= 4096 scalars on one base switch to the cached 32x255 window table; the cache follows the base."""
     n = 4096 + 5
