@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
   if (i >= n) return;
   Fp12 f;
   fp12_set_one(f);
+  BN_SCRATCH_DECL
   int s = 0;
   for (int it = ATE_NAF_LEN - 2; it >= -2; it--) {
     // it >= 0: tangent (+ chord if the digit is non-zero); it == -1, -2: the two Frobenius lines
@@ -235,9 +236,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
       for (int j = 0; j < cnt; j++) {
         if ((skip >> j) & 1u) continue;
         const Fp2* L = table + ((size_t)(first + j) * kLinesPerPoint + s) * 3;
-        Fp2 r0, r1, r2;
-        load_struct(r0, L, 0); load_struct(r1, L, 1); load_struct(r2, L, 2);
-        apply_line(f, p[j], r0, r1, r2);
+        apply_line_mem(f, p[j], L, sc_);
       }
     }
   }

@@ -83,15 +83,13 @@ BN_NOINLINE void g2_add_step_sc(G2Proj& T, const G2Aff& Q, bool neg, bool update
   fp2_mul(T.z, sc[7], sc[2]);                   // Z3 = E Z
 }
 // f *= line(P), raw line in sc[3..5]
-BN_NOINLINE void apply_line_sc(Fp12& f, const G1Aff& P, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc); }
-// line coefficients given in memory (line tables)
+BN_NOINLINE void apply_line_sc(Fp12& f, const G1Aff& P, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc, nullptr); }
+// f *= line(P), raw line (r0, r1, r2) in memory (line tables): fetched together with f.c1, one round trip
+BN_NOINLINE void apply_line_mem(Fp12& f, const G1Aff& P, const Fp2* r, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc, r); }
 BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, const Fp2& r2) {
   BN_SCRATCH_DECL
-  {
-    Fp2 a = fp2_ld(r0), b = fp2_ld(r1), c = fp2_ld(r2);
-    fp2_st(sc_[3], a); fp2_st(sc_[4], b); fp2_st(sc_[5], c);
-  }
-  apply_line_sc(f, P, sc_);
+  Fp2 r[3] = {r0, r1, r2};
+  apply_line_mem(f, P, r, sc_);
 }
 // compatibility forms writing the line to memory (line-table precomputation)
 BN_HD void g2_dbl_step(G2Proj& T, Fp2& r0, Fp2& r1, Fp2& r2) {

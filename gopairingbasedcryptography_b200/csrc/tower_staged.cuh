@@ -38,28 +38,32 @@ BN_NOINLINE void fp2_mul_rsub(Fp2& z, const Fp2& a, const Fp2& b, const Fp2& c) 
 //   t = (xa + xb) * (ya [+ yb]) - va [- vb]
 //   mode 0: r = xi*t + vc    mode 1: r = t + xi*vc    mode 2: r = t + vc    mode 3: r = t
 //   z = r [- e0] [- e1]
-// e0/e1 usually live in local memory: they are fetched first so the three Montgomery products hide the latency.
+// Everything that does not depend on the product is folded into ONE correction K before the multiplication
+// (K = c - S with S = va + vb [+ e0 + e1], xi applied to S or c as the mode needs), so the dependent chain after
+// the three Montgomery products is a single addition (xi + addition in mode 0) instead of five Fp2 operations,
+// and the pre-multiplication chains are independent of each other.  e0/e1 usually live in local memory; their
+// latency overlaps the pre-additions.
 enum { kCrossXiT = 0, kCrossXiV = 1, kCrossPlain = 2, kCrossNone = 3 };
 BN_NOINLINE void fp2_cross(Fp2& z, const Fp2& xa, const Fp2& xb, const Fp2& ya, const Fp2* yb, const Fp2& va, const Fp2* vb,
                            const Fp2* vc, int mode, const Fp2* e0, const Fp2* e1) {
-  Fp2 E0, E1;
-  if (e0) E0 = fp2_ld(*e0);
-  if (e1) E1 = fp2_ld(*e1);
+  Fp2 S = fp2_ld(va);
+  if (vb) S = fp2_add_i(S, fp2_ld(*vb));
+  if (mode == kCrossXiT) S = fp2_mul_xi_bv(S);
+  if (e0) S = fp2_add_i(S, fp2_ld(*e0));
+  if (e1) S = fp2_add_i(S, fp2_ld(*e1));
+  Fp2 K;
+  if (mode == kCrossNone) K = fp2_neg_i(S);
+  else {
+    Fp2 c = fp2_ld(*vc);
+    if (mode == kCrossXiV) c = fp2_mul_xi_bv(c);
+    K = fp2_sub_i(c, S);
+  }
   Fp2 x = fp2_add_i(fp2_ld(xa), fp2_ld(xb));
   Fp2 y = fp2_ld(ya);
   if (yb) y = fp2_add_i(y, fp2_ld(*yb));
   Fp2 t = FP2_MUL(x, y);
-  t = fp2_sub_i(t, fp2_ld(va));
-  if (vb) t = fp2_sub_i(t, fp2_ld(*vb));
-  if (mode != kCrossNone) {
-    Fp2 c = fp2_ld(*vc);
-    if (mode == kCrossXiT) t = fp2_mul_xi_bv(t);
-    else if (mode == kCrossXiV) c = fp2_mul_xi_bv(c);
-    t = fp2_add_i(t, c);
-  }
-  if (e0) t = fp2_sub_i(t, E0);
-  if (e1) t = fp2_sub_i(t, E1);
-  fp2_st(z, t);
+  if (mode == kCrossXiT) t = fp2_mul_xi_bv(t);
+  fp2_st(z, fp2_add_i(t, K));
 }
 
 // ---- staging: generic memory -> scratch slots, every load issued before the first store ---------------------
@@ -229,11 +233,14 @@ BN_NOINLINE void fp12_cyclo_sqr_n(Fp12& z, const Fp12& x, int n) {
 // f1 = s - a - b, f0 = a + v b.  13 Fp2 products.
 // The raw line coefficients r0, r1, r2 are expected in three scratch slots L[0..2] (left there by the G2 step
 // or copied from a line table); Y[0..2] and W[0..2] are the other six slots.
-BN_NOINLINE void line_stage_y(Fp2* L, Fp2* Y, const Fp6& fy, const Fp& px, const Fp& py) {
-  // Y <- f.c1; L0 <- r0 * yP; L1 <- r1 * xP (L2 = r2 stays)
+BN_NOINLINE void line_stage_y(Fp2* L, Fp2* Y, const Fp6& fy, const Fp& px, const Fp& py, const Fp2* raw) {
+  // Y <- f.c1; L0 <- r0 * yP; L1 <- r1 * xP; L2 <- r2.  raw == nullptr: (r0, r1, r2) already sit in L (left by the
+  // G2 step); otherwise they are read from memory (line table) in the same batch of loads as f.c1.
   Fp2 y0 = fp2_ld(fy.b0), y1 = fp2_ld(fy.b1), y2 = fp2_ld(fy.b2);
   Fp x = fp_ld(px), y = fp_ld(py);
-  Fp2 r0 = fp2_ld(L[0]), r1 = fp2_ld(L[1]);
+  const Fp2* src = raw ? raw : L;
+  Fp2 r0 = fp2_ld(src[0]), r1 = fp2_ld(src[1]);
+  if (raw) { Fp2 r2 = fp2_ld(raw[2]); fp2_st(L[2], r2); }
   fp2_st(Y[0], y0); fp2_st(Y[1], y1); fp2_st(Y[2], y2);
   fp2_st(L[0], fp2_mul_fp_i(r0, y));
   fp2_st(L[1], fp2_mul_fp_i(r1, x));
@@ -244,9 +251,9 @@ BN_NOINLINE void line_sum_xy(Fp2* L, Fp2* Y, const Fp2* X) {  // Y += X ; L0 += 
   fp2_st(Y[0], fp2_add_i(y0, x0)); fp2_st(Y[1], fp2_add_i(y1, x1)); fp2_st(Y[2], fp2_add_i(y2, x2));
   fp2_st(L[0], fp2_add_i(l0, l1));
 }
-BN_HD void apply_line_staged(Fp12& f, const Fp& px, const Fp& py, Fp2* L, Fp2* Y, Fp2* W) {
+BN_HD void apply_line_staged(Fp12& f, const Fp& px, const Fp& py, Fp2* L, Fp2* Y, Fp2* W, const Fp2* raw) {
   Fp6 a, b;
-  line_stage_y(L, Y, f.c1, px, py);
+  line_stage_y(L, Y, f.c1, px, py, raw);
   fp6_mul_01_staged(b, Y, L[1], L[2], W[0], W[1], nullptr, nullptr);
   stage6(W, f.c0);
   fp2_mul(a.b0, W[0], L[0]); fp2_mul(a.b1, W[1], L[0]); fp2_mul(a.b2, W[2], L[0]);

@@ -47,7 +47,22 @@ def bsw07_key_lines(engine, dj, dj_prime, d):
     return engine.g2_lines_create(qrow)
 
 
-def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, deltas, lines=None):
+def bsw07_policy_lines(engine, dj, dj_prime, d, deltas):
+    """Line tables of one user key WITH the policy's Lagrange coefficients folded in.  For a fixed key and a fixed
+    satisfied attribute set the coefficients D_i (access/tree/access_tree_node.go:151-158) are the same for every
+    ciphertext, and e(Cy_i, Dj_i)^{D_i} = e(Cy_i, [D_i]Dj_i), so the exponents move to the key side once:
+    Q = ([D_i]Dj_i, [-D_i]Dj'_i, -D).  A decryption is then ONE (2m+1)-pair product against fixed lines with the raw
+    ciphertext points -- no scalar multiplication, no GT exponentiation per ciphertext (same canonical GT result).
+    Use with bsw07_decrypt_batch(..., lines=handle, folded=True)."""
+    m = np.ascontiguousarray(dj).reshape(-1, G2_BYTES).shape[0]
+    dl = np.ascontiguousarray(deltas).reshape(m, 32)
+    q1 = engine.g2_mul_batch(np.ascontiguousarray(dj).reshape(m, G2_BYTES), dl).reshape(m, G2_BYTES)
+    q2 = neg_g2(engine.g2_mul_batch(np.ascontiguousarray(dj_prime).reshape(m, G2_BYTES), dl))
+    qrow = np.concatenate([q1, q2, neg_g2(np.ascontiguousarray(d).reshape(1, G2_BYTES))], axis=0)
+    return engine.g2_lines_create(qrow)
+
+
+def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, deltas, lines=None, folded=False):
     """Fused BSW07 decryption for n ciphertexts under ONE user key with m matched leaves
     (reference: access/tree/access_tree_node.go:96-164 + cpabe/bsw07/bsw07_cpabe.go:172-195).
 
@@ -56,6 +71,11 @@ def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, delta
     M = C~ * prod_i e([D_i]Cy_i, Dj_i) * e([D_i](-Cy'_i), Dj'_i) * e(-C, D): one (2m+1)-pair Miller product and
     one final exponentiation per ciphertext, bit-exact with the reference's unfused formula."""
     n, m = cy.shape[0], cy.shape[1]
+    if folded:  # lines = bsw07_policy_lines(...): exponents and signs already live in the key's line tables
+        P = np.concatenate([np.ascontiguousarray(cy).reshape(n, m, G1_BYTES), np.ascontiguousarray(cy_prime).reshape(n, m, G1_BYTES),
+                            np.ascontiguousarray(c).reshape(n, 1, G1_BYTES)], axis=1)
+        prod = engine.multi_pair_lines_batch(P.reshape(-1), lines)
+        return engine.gt_mul_batch(np.ascontiguousarray(c_tilde).reshape(-1, GT_BYTES), prod)
     sc = np.broadcast_to(np.ascontiguousarray(deltas).reshape(1, m, 32), (n, m, 32)).reshape(-1, 32)
     a = engine.g1_mul_batch(np.ascontiguousarray(cy).reshape(-1, G1_BYTES), sc).reshape(n, m, G1_BYTES)
     b = engine.g1_mul_batch(neg_g1(cy_prime), sc).reshape(n, m, G1_BYTES)

@@ -310,6 +310,9 @@ def test_bsw07_fused_decrypt_matches_unfused_reference_formula(engine):
         ecd = port.pair_batch(c[i], d, 1)
         M = port.gt_div_batch(ctil[i], port.gt_div_batch(ecd, A, 1), 1)
         assert (got[i] == M).all()
+    # Lagrange coefficients folded into the key's line tables: no per-ciphertext scalar multiplication
+    pol = schemes.bsw07_policy_lines(engine, dj, djp, d, deltas)
+    assert (schemes.bsw07_decrypt_batch(engine, cy, cyp, dj, djp, c, d, ctil, deltas, lines=pol, folded=True) == got).all()
 
 
 def test_bls_verify_driver(engine):
