@@ -15,10 +15,11 @@ NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "nolockstep": NOLS,
+    "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
+    "cross_inl": DEFAULT + ["-DBN254_CROSS_INLINE_MUL"],
     "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
-    "lazy": DEFAULT + ["-DBN254_LAZY_FP2"],
     **{"k%dw%d" % (k, w): DEFAULT + ["-DBN254_VM_K=%d" % k, "-DBN254_VM_WARPS=%d" % w]
        for k in (1, 2, 3, 4, 6) for w in (1, 2, 3, 4, 6, 8)},
 }

@@ -61,7 +61,18 @@ BN_NOINLINE void fp2_cross(Fp2& z, const Fp2& xa, const Fp2& xb, const Fp2& ya, 
   Fp2 x = fp2_add_i(fp2_ld(xa), fp2_ld(xb));
   Fp2 y = fp2_ld(ya);
   if (yb) y = fp2_add_i(y, fp2_ld(*yb));
+#ifdef BN254_CROSS_INLINE_MUL
+  // the three Montgomery products inline: the K / S chains above are independent of them, so the scheduler can
+  // issue those IADD3s in the shadow of the IMAD.WIDE chains (4 pipe cycles per multiply leave 3 issue slots)
+  Fp t0 = fp_mul(x.a0, y.a0);
+  Fp t1 = fp_mul(x.a1, y.a1);
+  Fp m = fp_mul(fp_add_noreduce(x.a0, x.a1), fp_add_noreduce(y.a0, y.a1));
+  Fp2 t;
+  t.a0 = fp_sub(t0, t1);
+  t.a1 = fp_sub(fp_sub(m, t0), t1);
+#else
   Fp2 t = FP2_MUL(x, y);
+#endif
   if (mode == kCrossXiT) t = fp2_mul_xi_bv(t);
   fp2_st(z, fp2_add_i(t, K));
 }
