@@ -16,7 +16,6 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "nolockstep": NOLS,
     "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
-    "cross_inl": DEFAULT + ["-DBN254_CROSS_INLINE_MUL"],
     "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],

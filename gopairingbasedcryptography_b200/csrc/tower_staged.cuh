@@ -38,42 +38,35 @@ BN_NOINLINE void fp2_mul_rsub(Fp2& z, const Fp2& a, const Fp2& b, const Fp2& c) 
 //   t = (xa + xb) * (ya [+ yb]) - va [- vb]
 //   mode 0: r = xi*t + vc    mode 1: r = t + xi*vc    mode 2: r = t + vc    mode 3: r = t
 //   z = r [- e0] [- e1]
-// Everything that does not depend on the product is folded into ONE correction K before the multiplication
-// (K = c - S with S = va + vb [+ e0 + e1], xi applied to S or c as the mode needs), so the dependent chain after
-// the three Montgomery products is a single addition (xi + addition in mode 0) instead of five Fp2 operations,
-// and the pre-multiplication chains are independent of each other.  e0/e1 usually live in local memory; their
-// latency overlaps the pre-additions.
+// Everything that does not depend on the product is folded into ONE correction K before the multiplication, so the
+// dependent chain after the product is a single addition (modes 1-3: z = prod + K, K = c - va - vb - e0 - e1 with
+// c = xi*vc, vc or 0) or subtract / xi / add (mode 0: z = xi*(prod - S) + K, S = va + vb, K = vc - e0 - e1 -- one xi
+// per call in every mode).  e0/e1 usually live in local memory; their latency overlaps the pre-additions.
 enum { kCrossXiT = 0, kCrossXiV = 1, kCrossPlain = 2, kCrossNone = 3 };
 BN_NOINLINE void fp2_cross(Fp2& z, const Fp2& xa, const Fp2& xb, const Fp2& ya, const Fp2* yb, const Fp2& va, const Fp2* vb,
                            const Fp2* vc, int mode, const Fp2* e0, const Fp2* e1) {
   Fp2 S = fp2_ld(va);
   if (vb) S = fp2_add_i(S, fp2_ld(*vb));
-  if (mode == kCrossXiT) S = fp2_mul_xi_bv(S);
-  if (e0) S = fp2_add_i(S, fp2_ld(*e0));
-  if (e1) S = fp2_add_i(S, fp2_ld(*e1));
   Fp2 K;
-  if (mode == kCrossNone) K = fp2_neg_i(S);
-  else {
-    Fp2 c = fp2_ld(*vc);
-    if (mode == kCrossXiV) c = fp2_mul_xi_bv(c);
-    K = fp2_sub_i(c, S);
+  if (mode == kCrossXiT) {
+    K = fp2_ld(*vc);
+    if (e0) K = fp2_sub_i(K, fp2_ld(*e0));
+    if (e1) K = fp2_sub_i(K, fp2_ld(*e1));
+  } else {
+    if (e0) S = fp2_add_i(S, fp2_ld(*e0));
+    if (e1) S = fp2_add_i(S, fp2_ld(*e1));
+    if (mode == kCrossNone) K = fp2_neg_i(S);
+    else {
+      Fp2 c = fp2_ld(*vc);
+      if (mode == kCrossXiV) c = fp2_mul_xi_bv(c);
+      K = fp2_sub_i(c, S);
+    }
   }
   Fp2 x = fp2_add_i(fp2_ld(xa), fp2_ld(xb));
   Fp2 y = fp2_ld(ya);
   if (yb) y = fp2_add_i(y, fp2_ld(*yb));
-#ifdef BN254_CROSS_INLINE_MUL
-  // the three Montgomery products inline: the K / S chains above are independent of them, so the scheduler can
-  // issue those IADD3s in the shadow of the IMAD.WIDE chains (4 pipe cycles per multiply leave 3 issue slots)
-  Fp t0 = fp_mul(x.a0, y.a0);
-  Fp t1 = fp_mul(x.a1, y.a1);
-  Fp m = fp_mul(fp_add_noreduce(x.a0, x.a1), fp_add_noreduce(y.a0, y.a1));
-  Fp2 t;
-  t.a0 = fp_sub(t0, t1);
-  t.a1 = fp_sub(fp_sub(m, t0), t1);
-#else
   Fp2 t = FP2_MUL(x, y);
-#endif
-  if (mode == kCrossXiT) t = fp2_mul_xi_bv(t);
+  if (mode == kCrossXiT) t = fp2_mul_xi_bv(fp2_sub_i(t, S));
   fp2_st(z, fp2_add_i(t, K));
 }
 
