@@ -32,9 +32,9 @@ UNIT = "pairings/s"
 MACS_PER_PAIRING = 2.081e6  # SURVEY.md §8d Model-M: 15300 Fp-mul equivalents x 136 limb-MACs
 BYTES_PER_PAIRING = 64 + 128 + 384
 # dram__bytes_read.sum + dram__bytes_write.sum of k_pair from the committed ncu --set full capture
-# (profiles/r1/ncu_k_pair_final_summary.txt: 30.8 + 157.7 GB for 2^18 pairings): the local-memory stack of the
-# one-thread-per-pairing kernel, ~1250x the algorithmic 576 B -- the first thing round 2 has to remove.
-NCU_DRAM_BYTES_PER_PAIRING = (30.817529e9 + 157.676779e9) / (1 << 18)
+# (profiles/r1/ncu_k_pair_staged_lockstep_lazy_summary.txt: 3.31 + 20.91 GB for 2^18 pairings): what is left of the
+# local-memory stack traffic after the staged tower (was 188.5 GB / 2^18 before it), still ~160x the algorithmic 576 B.
+NCU_DRAM_BYTES_PER_PAIRING = (3.313627e9 + 20.909593e9) / (1 << 18)
 
 
 def host_threads():
@@ -71,7 +71,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    sample = max(threads * 32, 1024)
+    sample = max(threads * 256, 2048)
     for _ in range(args.warmup):
         cpu_sample(threads * 4, threads)
     t0 = time.perf_counter()
@@ -257,7 +257,7 @@ def main():
         peak, peak_how = measure_imad_peak(local)
         achieved = MACS_PER_PAIRING * n / (kernel_ms * 1e-3)
         threads = host_threads()
-        sample = args.cpu_sample or max(threads * 64, 2048)
+        sample = args.cpu_sample or max(threads * 1024, 4096)  # ~20 s of CPU time on the C restatement
         cpu_v = cpu_sample(sample, threads)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -274,6 +274,31 @@ class Engine:
     def fp_mul_batch(self, a, b):
         return self._binary("bn254_fp_mul_batch", a, b, 32)
 
+    # ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2; hash/hash_to.go in the reference) ----
+    def _hash_to_curve(self, name, msgs, dst, out_bytes):
+        msgs = [bytes(m) for m in msgs]
+        dst = bytes(dst)
+        n = len(msgs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
+        d = np.frombuffer(dst or b"\0", dtype=np.uint8)
+        out = np.empty(n * out_bytes, dtype=np.uint8)
+        fn = getattr(self._lib, name)
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, blob.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n),
+                       d.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(dst)), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(n, out_bytes)
+
+    def hash_to_g1_batch(self, msgs, dst):
+        """n x bn254.HashToG1(msg, dst) -> (n, 64) affine points."""
+        return self._hash_to_curve("bn254_hash_to_g1_batch", msgs, dst, G1_BYTES)
+
+    def hash_to_g2_batch(self, msgs, dst):
+        """n x bn254.HashToG2(msg, dst) -> (n, 128) affine points."""
+        return self._hash_to_curve("bn254_hash_to_g2_batch", msgs, dst, G2_BYTES)
+
     # ---- device-resident entry points (pointers are ints, e.g. torch.Tensor.data_ptr()) ----
     def _dev(self, name, *args):
         fn = getattr(self._lib, name)
@@ -539,6 +564,16 @@ def Generators():
     _native.lib().bn254_generators(g1, g2)
     a1, a2 = G1Affine(bytes(g1)), G2Affine(bytes(g2))
     return (a1, 1), (a2, 1), a1, a2
+
+
+def HashToG1(msg, dst):
+    """bn254.HashToG1(msg, dst []byte) (G1Affine, error)"""
+    return G1Affine(default_engine().hash_to_g1_batch([msg], dst)[0].tobytes())
+
+
+def HashToG2(msg, dst):
+    """bn254.HashToG2(msg, dst []byte) (G2Affine, error)"""
+    return G2Affine(default_engine().hash_to_g2_batch([msg], dst)[0].tobytes())
 
 
 def _pack(Ps, Qs):

@@ -10,6 +10,7 @@
 
 #include "../../include/bn254_b200.h"
 #include "curve.cuh"
+#include "hash_to_curve.cuh"
 #include "vm.cuh"
 
 using namespace bn254;
@@ -379,6 +380,17 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void*
   if (MODE == 1) fp12_inv(y, y);
   fp12_mul(x, x, y);
   store_struct(out, i, x);
+}
+// hash-to-curve: one message per thread (SHA-256 expand_message_xmd, SVDW map x2, add, G2 cofactor clearing)
+template <int G>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_hash_to_curve(const uint8_t* msgs, const uint64_t* off, size_t n, const uint8_t* dst,
+                                                                           uint32_t dst_len, void* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* m = msgs + off[i];
+  size_t len = (size_t)(off[i + 1] - off[i]);
+  if (G == 1) { G1Aff r; hash_to_g1(r, m, len, dst, dst_len); store_struct(out, i, r); }
+  else { G2Aff r; hash_to_g2(r, m, len, dst, dst_len); store_struct(out, i, r); }
 }
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fp_mul(const void* a, const void* b, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,6 +764,50 @@ int ensure_fixed_table(bn254_ctx* ctx, int g, const void* base) {
 
 }  // namespace
 
+// n messages (concatenated bytes + n+1 offsets) -> points.  Chunks are sized to one staging slot.
+template <int G>
+int hash_to_curve_host(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out) {
+  if (!ctx) return BN254_ERR_BAD_ARG;
+  if (dst_len > 255) return fail(ctx, BN254_ERR_BAD_ARG, "hash-to-curve: domain separation tag longer than 255 bytes");
+  if (n == 0) return BN254_OK;
+  if (!msgs && offsets && offsets[n] != offsets[0]) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  if (!offsets || !out || (dst_len && !dst)) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  const size_t out_item = G == 1 ? BN254_G1_BYTES : BN254_G2_BYTES;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  size_t done = 0;
+  while (done < n) {
+    // largest c with  256 (dst) + 8 (c + 1) + bytes + out_item * c  <=  slot
+    size_t c = 0, bytes = 0;
+    while (done + c < n && c < kMaxChunkItems) {
+      size_t len = (size_t)(offsets[done + c + 1] - offsets[done + c]);
+      if (512 + 8 * (c + 2) + bytes + len + out_item * (c + 1) + 512 > ctx->slot_bytes) break;
+      bytes += len; c++;
+    }
+    if (c == 0) return fail(ctx, BN254_ERR_BAD_ARG, "message too large for staging");
+    unsigned char* h = reinterpret_cast<unsigned char*>(s.h);
+    memset(h, 0, 256);
+    if (dst_len) memcpy(h, dst, dst_len);
+    uint64_t* ho = reinterpret_cast<uint64_t*>(h + 256);
+    for (size_t j = 0; j <= c; j++) ho[j] = offsets[done + j] - offsets[done];
+    size_t o_msg = (256 + 8 * (c + 1) + 255) & ~size_t(255);
+    if (bytes) memcpy(h + o_msg, msgs + offsets[done], bytes);
+    size_t o_out = (o_msg + bytes + 255) & ~size_t(255);
+    CU(cudaMemcpyAsync(s.d, s.h, o_out, cudaMemcpyHostToDevice, s.stream));
+    const uint8_t* d = reinterpret_cast<const uint8_t*>(s.d);
+    k_hash_to_curve<G><<<grid_for(c), kBlock, kTowerSmem, s.stream>>>(d + o_msg, reinterpret_cast<const uint64_t*>(d + 256), c, d, (uint32_t)dst_len,
+                                                                     s.d + o_out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s.h + o_out, s.d + o_out, out_item * c, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    memcpy(static_cast<char*>(out) + done * out_item, s.h + o_out, out_item * c);
+    done += c;
+  }
+  return BN254_OK;
+}
+
 extern "C" {
 
 int bn254_device_count(void) {
@@ -788,7 +844,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
                                    (const void*)k_multi_pair_c<0, 2>, (const void*)k_multi_pair_c<1, 2>, (const void*)k_multi_pair_c<2, 2>,
                                    (const void*)k_multi_pair_c<0, 3>, (const void*)k_multi_pair_c<1, 3>, (const void*)k_multi_pair_c<2, 3>, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
                                    (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
-                                   (const void*)k_final_exp, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
+                                   (const void*)k_final_exp, (const void*)k_hash_to_curve<1>, (const void*)k_hash_to_curve<2>, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
     for (const void* k : tower_kernels)
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTowerSmem) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
   }
@@ -1084,4 +1140,11 @@ int bn254_fp_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, v
                   [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_fp_mul<<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
 }
 
+// ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2) -----------------------------------------------------------
+int bn254_hash_to_g1_batch(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out) {
+  return hash_to_curve_host<1>(ctx, msgs, offsets, n, dst, dst_len, out);
+}
+int bn254_hash_to_g2_batch(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out) {
+  return hash_to_curve_host<2>(ctx, msgs, offsets, n, dst, dst_len, out);
+}
 }  // extern "C"

@@ -199,6 +199,55 @@ def main():
     w("static constexpr int X0_NAF3_LEN = %d;" % len(x0_naf3))
     w("BN_CONST signed char X0_NAF3[%d] = {%s};  // width-3 signed digits of x0, LSB first" % (len(x0_naf3), ",".join(map(str, x0_naf3))))
     w("static constexpr unsigned long long X0_SEED = %dull;" % X0)
+    # ---- hash-to-curve (RFC 9380 SVDW; gnark hash_to_g1.go / hash_to_g2.go): constants derived from Z
+    def fsqrt(a):
+        r = pow(a % P, (P + 1) // 4, P)
+        assert r * r % P == a % P
+        return r
+
+    def fissq(a):
+        return a % P == 0 or pow(a % P, (P - 1) // 2, P) == 1
+
+    def f2sqrt(a):
+        if a[1] % P == 0:
+            return (fsqrt(a[0]), 0) if fissq(a[0]) else (0, fsqrt(-a[0] % P))
+        n = fsqrt((a[0] * a[0] + a[1] * a[1]) % P)
+        x2 = (a[0] + n) * pow(2, -1, P) % P
+        if not fissq(x2):
+            x2 = (a[0] - n) * pow(2, -1, P) % P
+        x = fsqrt(x2)
+        r = (x, a[1] * pow(2 * x, -1, P) % P)
+        assert f2mul(r, r) == (a[0] % P, a[1] % P)
+        return r
+
+    z1 = 1
+    gz = (z1**3 + 3) % P
+    c3 = fsqrt(-gz * 3 * z1 * z1 % P)
+    c3 = P - c3 if c3 & 1 else c3
+    h1 = {"Z": z1, "C1": gz, "C2": -z1 * pow(2, -1, P) % P, "C3": c3, "C4": -4 * gz * pow(3 * z1 * z1, -1, P) % P}
+    assert h1["C3"] == 8815841940592487685674414971303048083897117035520822607866  # gnark bn254 HashE1 c3
+    z2 = (0, 1)
+    gz2 = f2mul(f2mul(z2, z2), z2)
+    gz2 = ((gz2[0] + b2[0]) % P, (gz2[1] + b2[1]) % P)
+    z2sq3 = tuple(3 * c % P for c in f2mul(z2, z2))
+    c3 = f2sqrt(tuple(-c % P for c in f2mul(gz2, z2sq3)))
+    sgn = (c3[0] & 1) | (int(c3[0] == 0) & (c3[1] & 1))
+    c3 = tuple(-c % P for c in c3) if sgn else c3
+    c4 = tuple(-c % P for c in f2mul(tuple(4 * c % P for c in gz2), f2inv(z2sq3)))
+    h2 = {"Z": z2, "C1": gz2, "C2": tuple(-c * pow(2, -1, P) % P for c in z2), "C3": c3, "C4": c4}
+    for k, v in h1.items():
+        w("BN_CONST Fp H2C_G1_%s = %s;" % (k, fp_init(v)))
+    for k, v in h2.items():
+        w("BN_CONST Fp2 H2C_G2_%s = %s;" % (k, fp2_init(v)))
+    w("BN_CONST Fp CURVE_B = %s;" % fp_init(3))
+    w("BN_CONST uint32_t FP_PM1H[8] = {%s};  // (p-1)/2, Euler criterion" % limbs32((P - 1) // 2))
+    w("BN_CONST uint32_t FP_PP1Q[8] = {%s};  // (p+1)/4, square root (p = 3 mod 4)" % limbs32((P + 1) // 4))
+    w("BN_CONST Fp FP_HALF = %s;" % fp_init(pow(2, -1, P)))
+    # hash_to_field: a 48-byte big-endian integer c2 2^256 + c1 2^128 + c0 enters Montgomery form as
+    # mont(c0, R^2) + mont(c1, 2^128 R^2) + mont(c2, 2^256 R^2)  (raw limbs, every c_i < 2^128 < p)
+    for k in range(3):
+        w("BN_CONST Fp H2F_K%d = {{%s}};" % (k, limbs32((1 << (128 * k)) * MONT * MONT % P)))
+    w("BN_CONST Fp FP_RAW_ONE = {{%s}};  // mont(a, 1) = a/R: Montgomery -> regular form" % limbs32(1))
     w("}  // namespace bn254")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bn254_constants.cuh")
     with open(path, "w") as f:

@@ -140,3 +140,30 @@ def g1_msm_batch(engine, points, coeffs):
     terms = engine.g1_mul_batch(np.tile(np.ascontiguousarray(points).reshape(B, G1_BYTES), (n, 1)),
                                 np.ascontiguousarray(coeffs).reshape(-1, 32))
     return engine.g1_sum_batch(terms, B)
+
+
+# ---- hash/hash_to.go of the reference: the four domain-separated hash-to-curve wrappers, batched ----------------
+DST_STRING_G1 = b"Hash String To Element In G1"  # hash/hash_to.go:114
+DST_BYTES_G1 = b"Hash Bytes To Element In G1"    # hash/hash_to.go:170
+DST_STRING_G2 = b"Hash String To Element In G2"  # hash/hash_to.go:204
+DST_BYTES_G2 = b"Hash Bytes To Element In G2"    # hash/hash_to.go:272
+
+
+def to_g1_batch(engine, strings):
+    """hash.ToG1 for a batch of strings -> (n, 64)."""
+    return engine.hash_to_g1_batch([s.encode() if isinstance(s, str) else s for s in strings], DST_STRING_G1)
+
+
+def bytes_to_g1_batch(engine, msgs):
+    """hash.BytesToG1 for a batch of byte strings -> (n, 64)."""
+    return engine.hash_to_g1_batch(msgs, DST_BYTES_G1)
+
+
+def to_g2_batch(engine, strings):
+    """hash.ToG2 for a batch of strings -> (n, 128)."""
+    return engine.hash_to_g2_batch([s.encode() if isinstance(s, str) else s for s in strings], DST_STRING_G2)
+
+
+def bytes_to_g2_batch(engine, msgs):
+    """hash.BytesToG2 (the H(m) of BLS: signature/bls01_signature/bls_signature.go:60,73) -> (n, 128)."""
+    return engine.hash_to_g2_batch(msgs, DST_BYTES_G2)

@@ -137,6 +137,18 @@ int bn254_gt_cyclo_exp_base_batch(bn254_ctx*, const void* x1, const void* k, siz
 int bn254_gt_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 int bn254_gt_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 
+/* bn254.HashToG1(msg, dst) / bn254.HashToG2(msg, dst) for n messages at once
+ * [hash/hash_to.go:113-119 ToG1, 169-175 BytesToG1, 203-209 ToG2, 271-277 BytesToG2; callers
+ *  signature/bls01_signature/bls_signature.go:60,73, ibe/bf01_ibe/bf01_ibe.go:130,158, dabe/lw11_dabe.go:96,177,
+ *  bibe/afp25_bibe/afp25_bibe_utils.go:10-12].  RFC 9380 hash_to_curve as gnark configures it for BN254:
+ * expand_message_xmd(SHA-256), 48 bytes per field element, Shallue-van de Woestijne map (Z = 1 on G1, Z = u on G2),
+ * sum of the two mapped points, G2 cofactor cleared with the psi endomorphism.  Everything runs on the GPU.
+ * msgs: the n messages concatenated; offsets: n + 1 byte offsets into msgs (message i = [offsets[i], offsets[i+1]));
+ * dst: domain separation tag, at most 255 bytes (longer -> BN254_ERR_BAD_ARG, where gnark returns an error);
+ * out: n canonical affine points (64 B / 128 B each). */
+int bn254_hash_to_g1_batch(bn254_ctx*, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out);
+int bn254_hash_to_g2_batch(bn254_ctx*, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out);
+
 /* diagnostics used by the parity tests: raw Fp Montgomery product, 32 B operands */
 int bn254_fp_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 

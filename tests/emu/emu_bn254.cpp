@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstddef>
 #include "../../gopairingbasedcryptography_b200/csrc/curve.cuh"
+#include "../../gopairingbasedcryptography_b200/csrc/hash_to_curve.cuh"
 using namespace bn254;
 
 template <typename T> static T ld(const void* p, size_t i) { T t; memcpy(&t, (const char*)p + i * sizeof(T), sizeof(T)); return t; }
@@ -141,3 +142,11 @@ extern "C" void emu_multi_pair_lines(const void* P, const void* Q, size_t n, siz
   }
   delete[] table; delete[] qs;
 }
+
+// hash-to-curve device code on the host (same sources as k_hash_to_curve)
+extern "C" void emu_hash_to_g1(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
+  G1Aff r; hash_to_g1(r, msg, len, dst, (uint32_t)dst_len); st(out, 0, r); }
+extern "C" void emu_hash_to_g2(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
+  G2Aff r; hash_to_g2(r, msg, len, dst, (uint32_t)dst_len); st(out, 0, r); }
+extern "C" void emu_hash_to_field(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
+  Fp u[4]; hash_to_field<4>(u, msg, len, dst, (uint32_t)dst_len); for (int i = 0; i < 4; i++) st(out, i, u[i]); }
