@@ -17,10 +17,14 @@ BN_HD Fp f_add(const Fp& a, const Fp& b) { return fp_add(a, b); }
 BN_HD Fp f_sub(const Fp& a, const Fp& b) { return fp_sub(a, b); }
 BN_HD Fp f_dbl(const Fp& a) { return fp_dbl(a); }
 BN_HD Fp f_neg(const Fp& a) { return fp_neg(a); }
-BN_NOINLINE void fp_mul_ool(Fp& z, const Fp& a, const Fp& b) { z = fp_mul(a, b); }
-BN_HD Fp f_mul(const Fp& a, const Fp& b) { Fp z; fp_mul_ool(z, a, b); return z; }
-BN_HD Fp f_sqr(const Fp& a) { Fp z; fp_mul_ool(z, a, a); return z; }
-BN_HD Fp f_inv(const Fp& a) { Fp z; fp_inv_ool(z, a); return z; }
+// Products and inversions go through BY-VALUE out-of-line bodies (operands and results in registers).  The earlier
+// by-reference form (fp_mul_ool(z, a, b) with a temporary z) is avoided: nvcc 12.9 was seen to give the temporary
+// the stack slot of a still-live operand (t = sqr(x); y = mul(t, x) read x^2 for x -- hash_to_curve.cuh, found by
+// the GPU parity test against the oracle); values whose address is never taken cannot be hit by that.
+BN_NOINLINE Fp fp_inv_bv(Fp a) { return fp_inv(a); }
+BN_HD Fp f_mul(const Fp& a, const Fp& b) { return FP_MUL(a, b); }
+BN_HD Fp f_sqr(const Fp& a) { return FP_MUL(a, a); }
+BN_HD Fp f_inv(const Fp& a) { return fp_inv_bv(a); }
 BN_HD bool f_is_zero(const Fp& a) { return fp_is_zero(a); }
 BN_HD void f_set_one(Fp& a) { a = fp_one(); }
 BN_HD void f_set_zero(Fp& a) { a = fp_zero(); }
@@ -28,9 +32,14 @@ BN_HD Fp2 f_add(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
 BN_HD Fp2 f_sub(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
 BN_HD Fp2 f_dbl(const Fp2& a) { return fp2_dbl(a); }
 BN_HD Fp2 f_neg(const Fp2& a) { return fp2_neg(a); }
-BN_HD Fp2 f_mul(const Fp2& a, const Fp2& b) { Fp2 z; fp2_mul(z, a, b); return z; }
-BN_HD Fp2 f_sqr(const Fp2& a) { Fp2 z; fp2_sqr(z, a); return z; }
-BN_HD Fp2 f_inv(const Fp2& a) { Fp2 z; fp2_inv(z, a); return z; }
+BN_HD Fp2 f_mul(const Fp2& a, const Fp2& b) { return FP2_MUL(a, b); }
+BN_HD Fp2 f_sqr(const Fp2& a) { return FP2_SQR(a); }
+BN_HD Fp2 f_inv(const Fp2& a) {
+  Fp n = fp_add(f_sqr(a.a0), f_sqr(a.a1));
+  Fp ni = f_inv(n);
+  Fp2 r; r.a0 = f_mul(a.a0, ni); r.a1 = fp_neg(f_mul(a.a1, ni));
+  return r;
+}
 BN_HD bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
 BN_HD void f_set_one(Fp2& a) { a = fp2_one(); }
 BN_HD void f_set_zero(Fp2& a) { a = fp2_zero(); }

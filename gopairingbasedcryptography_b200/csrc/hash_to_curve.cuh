@@ -11,23 +11,13 @@
 
 namespace bn254 {
 
-// Products go through the BY-VALUE out-of-line bodies (operands and results in registers).  The by-reference
-// helpers of curve.cuh (f_mul / f_sqr -> fp_mul_ool(z, a, b)) are avoided here on purpose: with nvcc 12.9 the
-// pattern  t = sqr(x); y = mul(t, x)  had the stack slot of the temporary merged with the slot holding x, so
-// the second product read x^2 for x (seen on the B200 as off-curve outputs; the host build of the same source
-// was correct).  Values that never have their address taken cannot be hit by that.
-BN_NOINLINE Fp fp_inv_bv(Fp a) { return fp_inv(a); }
-BN_HD Fp h_mul(const Fp& a, const Fp& b) { return FP_MUL(a, b); }
-BN_HD Fp h_sqr(const Fp& a) { return FP_MUL(a, a); }
-BN_HD Fp h_inv(const Fp& a) { return fp_inv_bv(a); }
-BN_HD Fp2 h_mul(const Fp2& a, const Fp2& b) { return FP2_MUL(a, b); }
-BN_HD Fp2 h_sqr(const Fp2& a) { return FP2_SQR(a); }
-BN_HD Fp2 h_inv(const Fp2& a) {
-  Fp n = fp_add(h_sqr(a.a0), h_sqr(a.a1));
-  Fp ni = h_inv(n);
-  Fp2 r; r.a0 = h_mul(a.a0, ni); r.a1 = fp_neg(h_mul(a.a1, ni));
-  return r;
-}
+// Field products use the by-value helpers of curve.cuh (f_mul / f_sqr / f_inv).
+BN_HD Fp h_mul(const Fp& a, const Fp& b) { return f_mul(a, b); }
+BN_HD Fp h_sqr(const Fp& a) { return f_sqr(a); }
+BN_HD Fp h_inv(const Fp& a) { return f_inv(a); }
+BN_HD Fp2 h_mul(const Fp2& a, const Fp2& b) { return f_mul(a, b); }
+BN_HD Fp2 h_sqr(const Fp2& a) { return f_sqr(a); }
+BN_HD Fp2 h_inv(const Fp2& a) { return f_inv(a); }
 
 // ---- SHA-256 (FIPS 180-4), byte-streaming ------------------------------------------------------------------
 BN_CONST uint32_t SHA256_K[64] = {

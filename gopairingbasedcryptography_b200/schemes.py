@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .bn254 import G1_BYTES, G2_BYTES, GT_BYTES, P_MOD
+from .bn254 import G1_BYTES, G2_BYTES, GT_BYTES, P_MOD, R_MOD
 
 
 def neg_fp(elems):
@@ -123,6 +123,57 @@ def bb04_ibe_decrypt_batch(engine, a, b, c, d0, dj):
     Q = np.concatenate([np.ascontiguousarray(c).reshape(n, k, G2_BYTES), d0], axis=1)
     prod = engine.multi_pair_batch(np.ascontiguousarray(P).reshape(-1), np.ascontiguousarray(Q).reshape(-1), k + 1)
     return engine.gt_mul_batch(np.ascontiguousarray(a).reshape(-1, GT_BYTES), prod)
+
+
+def waters11_decrypt_batch(engine, c, c_prime, cx, dx, k, l, k_rho, weights):
+    """Fused Waters11 CP-ABE decryption (cpabe/waters11/waters11_cpabe.go:248-290) for n ciphertexts under ONE user key
+    with m selected rows each:
+        M = c / ( e(K, C') / prod_i (e(C_i, L) e(K_rho(i), D_i))^{w_i} )
+          = c * e(sum_i [w_i]C_i, L) * prod_i e([w_i]K_rho(i), D_i) * e(-K, C')
+    -- the m pairings against the fixed L collapse into ONE pairing of an m-term G1 sum, so a decryption is one
+    (m + 2)-pair product.  c: (n, 384); c_prime: (n, 128); cx: (n, m, 64); dx: (n, m, 128); k: (64,); l: (128,);
+    k_rho: (m, 64) key components in row order; weights: (n, m, 32) or (m, 32) reconstruction coefficients w_i."""
+    n, m = cx.shape[0], cx.shape[1]
+    w = np.broadcast_to(np.ascontiguousarray(weights).reshape(-1, m, 32), (n, m, 32)).reshape(-1, 32)
+    wc = engine.g1_mul_batch(np.ascontiguousarray(cx).reshape(-1, G1_BYTES), w)
+    csum = engine.g1_sum_batch(wc, m).reshape(n, 1, G1_BYTES)
+    wk = engine.g1_mul_batch(np.broadcast_to(np.ascontiguousarray(k_rho).reshape(1, m, G1_BYTES), (n, m, G1_BYTES)).reshape(-1, G1_BYTES),
+                             w).reshape(n, m, G1_BYTES)
+    negk = np.broadcast_to(neg_g1(np.ascontiguousarray(k).reshape(1, G1_BYTES)).reshape(1, 1, G1_BYTES), (n, 1, G1_BYTES))
+    P = np.concatenate([csum, wk, negk], axis=1)
+    Q = np.concatenate([np.broadcast_to(np.ascontiguousarray(l).reshape(1, 1, G2_BYTES), (n, 1, G2_BYTES)),
+                        np.ascontiguousarray(dx).reshape(n, m, G2_BYTES), np.ascontiguousarray(c_prime).reshape(n, 1, G2_BYTES)], axis=1)
+    prod = engine.multi_pair_batch(np.ascontiguousarray(P).reshape(-1), np.ascontiguousarray(Q).reshape(-1), m + 2)
+    return engine.gt_mul_batch(np.ascontiguousarray(c).reshape(-1, GT_BYTES), prod)
+
+
+def lw11_decrypt_batch(engine, c0, c1x, c2x, c3x, h_gid, k_rho, weights):
+    """Fused LW11 decentralised ABE decryption (dabe/lw11_dabe.go:176-203) for n ciphertexts of one user with m selected
+    rows each.  The reference exponentiates its RUNNING product in every iteration (lw11_dabe.go:191-195):
+        D_0 = 1,  D_x = (D_{x-1} * c1_x * e(H, c3_x) / e(K_rho(x), c2_x))^{w_x},  M = c0 / D_m,
+    so row x ends up raised to E_x = w_x w_{x+1} ... w_m; that quirk is reproduced exactly (it is what the reference
+    computes): M = c0 * prod_x c1_x^{-E_x} * e([-E_x]H, c3_x) * e([E_x]K_rho(x), c2_x), one 2m-pair product plus m
+    cyclotomic GT exponentiations.  c0: (n, 384); c1x: (n, m, 384); c2x, c3x: (n, m, 128); h_gid: (64,) = hash.ToG1(gid);
+    k_rho: (m, 64); weights: (n, m, 32) or (m, 32)."""
+    n, m = c1x.shape[0], c1x.shape[1]
+    w = np.broadcast_to(np.ascontiguousarray(weights).reshape(-1, m, 32), (n, m, 32))
+    E = np.empty((n, m, 32), dtype=np.uint8)  # suffix products of the weights mod r (host-side Fr work)
+    for i in range(n):
+        acc = 1
+        for x in range(m - 1, -1, -1):
+            acc = acc * int.from_bytes(w[i, x].tobytes(), "little") % R_MOD
+            E[i, x] = np.frombuffer(acc.to_bytes(32, "little"), dtype=np.uint8)
+    Ef = E.reshape(-1, 32)
+    hs = engine.g1_mul_batch(np.broadcast_to(neg_g1(np.ascontiguousarray(h_gid).reshape(1, G1_BYTES)).reshape(1, G1_BYTES), (n * m, G1_BYTES)), Ef)
+    ks = engine.g1_mul_batch(np.broadcast_to(np.ascontiguousarray(k_rho).reshape(1, m, G1_BYTES), (n, m, G1_BYTES)).reshape(-1, G1_BYTES), Ef)
+    P = np.concatenate([hs.reshape(n, m, G1_BYTES), ks.reshape(n, m, G1_BYTES)], axis=1)
+    Q = np.concatenate([np.ascontiguousarray(c3x).reshape(n, m, G2_BYTES), np.ascontiguousarray(c2x).reshape(n, m, G2_BYTES)], axis=1)
+    prod = engine.multi_pair_batch(np.ascontiguousarray(P).reshape(-1), np.ascontiguousarray(Q).reshape(-1), 2 * m)
+    c1e = engine.gt_cyclo_exp_batch(np.ascontiguousarray(c1x).reshape(-1, GT_BYTES), Ef).reshape(n, m, GT_BYTES)
+    den = c1e[:, 0]
+    for x in range(1, m):
+        den = engine.gt_mul_batch(den, c1e[:, x])
+    return engine.gt_mul_batch(engine.gt_div_batch(np.ascontiguousarray(c0).reshape(-1, GT_BYTES), den), prod)
 
 
 def g2_msm_batch(engine, points, coeffs):

@@ -593,3 +593,48 @@ def test_sw05_bb04_gwww25_fused_drivers(engine):
         for j in range(Bn):
             acc = port.g2_add_batch(acc, t[128 * j:128 * j + 128], 1)
         assert (got[i] == acc).all()
+
+
+def test_waters11_lw11_fused_drivers(engine):
+    """§8f-3: Waters11 CP-ABE (cpabe/waters11/waters11_cpabe.go:248-290) and LW11 DABE (dabe/lw11_dabe.go:176-203,
+    including its running-product exponent) -- fused batch drivers vs the reference's loops evaluated with the oracle."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    n, m = 3, 4
+    CX, DX, _, _ = common.points(n * m, seed=701, threads=8)
+    KR, _, _, _ = common.points(m, seed=702)
+    K1, CP, _, _ = common.points(n, seed=703)
+    _, L, _, _ = common.points(1, seed=704)
+    cx, dx = CX.reshape(n, m, 64), DX.reshape(n, m, 128)
+    k, l = K1[:64], L[:128]
+    cprime = CP.reshape(n, 128)
+    krho = KR.reshape(m, 64)
+    w = common.scalar_bytes(common.scalars(n * m, seed=705, edges=False)).reshape(n, m, 32)
+    c = engine.pair_batch(K1, CP)  # any GT elements
+    got = schemes.waters11_decrypt_batch(engine, c, cprime, cx, dx, k, l, krho, w)
+    for i in range(n):
+        den = None
+        for j in range(m):
+            t = port.gt_mul_batch(port.pair_batch(cx[i, j], l, 1), port.pair_batch(krho[j], dx[i, j], 1), 1)
+            t = port.gt_exp_batch(t, w[i, j], 1)
+            den = t if den is None else port.gt_mul_batch(den, t, 1)
+        egs = port.gt_div_batch(port.pair_batch(k, cprime[i], 1), den, 1)
+        assert (got[i] == port.gt_div_batch(c[i], egs, 1)).all()
+    # LW11: D = 1; for x: D = (D * c1x * e(H, c3x) / e(Krho, c2x))^{w_x};  M = c0 / D
+    C1P, C1Q, _, _ = common.points(n * m, seed=711, threads=8)
+    c1x = engine.pair_batch(C1P, C1Q).reshape(n, m, 384)
+    _, C2, _, _ = common.points(n * m, seed=712, threads=8)
+    _, C3, _, _ = common.points(n * m, seed=713, threads=8)
+    c2x, c3x = C2.reshape(n, m, 128), C3.reshape(n, m, 128)
+    H, _, _, _ = common.points(1, seed=714)
+    hgid = H[:64]
+    got = schemes.lw11_decrypt_batch(engine, c, c1x, c2x, c3x, hgid, krho, w)
+    one = np.frombuffer(o.gt_to_bytes(o.FP12_ONE), dtype=np.uint8)
+    for i in range(n):
+        D = one
+        for x in range(m):
+            D = port.gt_mul_batch(D, c1x[i, x], 1)
+            D = port.gt_mul_batch(D, port.pair_batch(hgid, c3x[i, x], 1), 1)
+            D = port.gt_div_batch(D, port.pair_batch(krho[x], c2x[i, x], 1), 1)
+            D = port.gt_exp_batch(D, w[i, x], 1)
+        assert (got[i] == port.gt_div_batch(c[i], D, 1)).all()
