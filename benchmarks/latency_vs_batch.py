@@ -14,7 +14,7 @@ from gopairingbasedcryptography_b200 import bn254  # noqa: E402
 from oracle import bn254_ref as o  # noqa: E402
 
 engs = {}
-os.environ.pop("BN254_IMPL", None)
+os.environ["BN254_IMPL"] = "thread"
 engs["thread"] = bn254.Engine(0)
 os.environ["BN254_IMPL"] = "vm"
 engs["vm"] = bn254.Engine(0)

@@ -546,7 +546,10 @@ struct bn254_ctx {
   size_t slot_bytes = 0;
   uint64_t launches = 0;
   // lane-group (tower VM) kernels
-  bool use_vm = false;         // BN254_IMPL=vm selects the lane-group (tower VM) kernels
+  // BN254_IMPL: "vm" = lane-group (tower VM) kernels always, "thread" = one-thread-per-pairing kernels always,
+  // unset = thread kernels, except that launches of at most kVmAutoMax elements take the lane-group kernels: they
+  // finish a small batch in 5.8 ms instead of 10.6 ms (profiles/r1/latency_vs_batch.jsonl; crossover ~20k elements)
+  int vm_mode = 0;             // 0 auto, 1 always, 2 never
   int sms = 0;
   int vm_blocks_per_sm[3] = {0, 0, 0};  // pair, miller, finalexp
   uint4* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
@@ -850,7 +853,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
 #endif
   const char* impl = getenv("BN254_IMPL");
-  ctx->use_vm = impl && std::string(impl) == "vm";  // default: one-thread-per-pairing kernels (faster so far)
+  ctx->vm_mode = !impl ? 0 : (std::string(impl) == "vm" ? 1 : (std::string(impl) == "thread" ? 2 : 0));
   ctx->sms = prop.multiProcessorCount;
   if (vm_prepare<VmProgPair>(ctx) != cudaSuccess || vm_prepare<VmProgMiller>(ctx) != cudaSuccess ||
       vm_prepare<VmProgFinalExp>(ctx) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
@@ -903,22 +906,24 @@ void bn254_generators(void* g1, void* g2) {
 }
 
 // ---- pairings -------------------------------------------------------------------------------
+constexpr size_t kVmAutoMax = 16384;
+static inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
 int bn254_pair_batch_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, void* d_out, void* stream) {
-  if (ctx && ctx->use_vm) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);
+  if (ctx && use_vm(ctx, n)) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);
   return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
 }
 int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, void* out) {
   return run_host(ctx, {P, BN254_G1_BYTES, false}, {Q, BN254_G2_BYTES, false}, out, BN254_GT_BYTES, n,
                   [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {
-                    if (ctx->use_vm) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);
+                    if (use_vm(ctx, c)) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);
                     else k_pair<<<grid_for(c), kBlock, kTowerSmem, s>>>(a, b, c, o);
                   });
 }
 #define MULTI_PAIR_ENTRY(name, MODE, OUT_BYTES, OUT_T)                                                                     \
   int name##_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, size_t k, OUT_T* d_out, void* stream) {         \
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
-    if (ctx && ctx->use_vm && k == 1 && MODE == 0) return run_dev_vm<VmProgMiller>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream); \
-    if (ctx && ctx->use_vm && k == 1 && MODE == 1) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);   \
+    if (ctx && use_vm(ctx, n) && k == 1 && MODE == 0) return run_dev_vm<VmProgMiller>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream); \
+    if (ctx && use_vm(ctx, n) && k == 1 && MODE == 1) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);   \
     return run_dev(ctx, n, [&] { cudaError_t e_ = launch_multi_pair<MODE>(ctx->dev_slot, dP, dQ, n, (int)k, d_out, (cudaStream_t)stream); (void)e_; }); \
   }                                                                                                                        \
   int name(bn254_ctx* ctx, const void* P, const void* Q, size_t n, size_t k, OUT_T* out) {                                 \
@@ -926,8 +931,8 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
     int kk = (int)k;                                                                                                       \
     return run_host(ctx, {P, BN254_G1_BYTES * k, false}, {Q, BN254_G2_BYTES * k, false}, out, OUT_BYTES, n,                \
                     [kk, ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {                  \
-                      if (ctx->use_vm && kk == 1 && MODE == 0) launch_vm<VmProgMiller>(ctx, a, b, c, o, cold, s);          \
-                      else if (ctx->use_vm && kk == 1 && MODE == 1) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);       \
+                      if (use_vm(ctx, c) && kk == 1 && MODE == 0) launch_vm<VmProgMiller>(ctx, a, b, c, o, cold, s);          \
+                      else if (use_vm(ctx, c) && kk == 1 && MODE == 1) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);       \
                       else launch_multi_pair<MODE>(ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0], a, b, c, kk, o, s);   \
                     });                                                                                                    \
   }
@@ -995,13 +1000,13 @@ int bn254_multi_pair_lines_batch(bn254_ctx* ctx, const void* P, const bn254_line
 }
 
 int bn254_final_exp_batch_dev(bn254_ctx* ctx, const void* d_in, size_t n, void* d_out, void* stream) {
-  if (ctx && ctx->use_vm) return run_dev_vm<VmProgFinalExp>(ctx, d_in, nullptr, n, d_out, (cudaStream_t)stream);
+  if (ctx && use_vm(ctx, n)) return run_dev_vm<VmProgFinalExp>(ctx, d_in, nullptr, n, d_out, (cudaStream_t)stream);
   return run_dev(ctx, n, [&] { k_final_exp<<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(d_in, n, d_out); });
 }
 int bn254_final_exp_batch(bn254_ctx* ctx, const void* in, size_t n, void* out) {
   return run_host(ctx, {in, BN254_GT_BYTES, false}, {nullptr, 0, false}, out, BN254_GT_BYTES, n,
                   [ctx](const void* a, const void*, size_t c, void* o, cudaStream_t s, uint4* cold) {
-                    if (ctx->use_vm) launch_vm<VmProgFinalExp>(ctx, a, nullptr, c, o, cold, s);
+                    if (use_vm(ctx, c)) launch_vm<VmProgFinalExp>(ctx, a, nullptr, c, o, cold, s);
                     else k_final_exp<<<grid_for(c), kBlock, kTowerSmem, s>>>(a, c, o);
                   });
 }

@@ -14,6 +14,17 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def engine():
+    """The parity suite drives the one-thread-per-element kernels (BN254_IMPL=thread, read at context creation); the
+    default context routes small pairing batches to the lane-group kernels, which test_small_batch_auto_routing and
+    test_lane_group_vm_implementation cover."""
     from gopairingbasedcryptography_b200 import bn254
 
-    return bn254.default_engine()
+    old = os.environ.get("BN254_IMPL")
+    os.environ["BN254_IMPL"] = "thread"
+    try:
+        return bn254.Engine(0)
+    finally:
+        if old is None:
+            del os.environ["BN254_IMPL"]
+        else:
+            os.environ["BN254_IMPL"] = old

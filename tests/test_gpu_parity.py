@@ -638,3 +638,23 @@ def test_waters11_lw11_fused_drivers(engine):
             D = port.gt_div_batch(D, port.pair_batch(krho[x], c2x[i, x], 1), 1)
             D = port.gt_exp_batch(D, w[i, x], 1)
         assert (got[i] == port.gt_div_batch(c[i], D, 1)).all()
+
+
+def test_small_batch_auto_routing(engine):
+    """The default context sends pair / miller(k=1) / final-exp launches of <= 16384 elements to the lane-group kernels
+    (5.8 ms instead of 10.6 ms for a small batch); both routes must give the same bytes as the oracle."""
+    from gopairingbasedcryptography_b200 import bn254
+
+    auto = bn254.default_engine()
+    for n in (1, 33, 300):
+        P, Q, _, _ = common.points(n, seed=900 + n, threads=8)
+        if n > 3:
+            P, Q = common.with_infinities(P, Q)
+        ref = port.pair_batch(P, Q, n, 8)
+        assert (auto.pair_batch(P, Q).reshape(-1) == ref).all()
+        assert (engine.pair_batch(P, Q).reshape(-1) == ref).all()
+        ml = auto.miller_loop_batch(P, Q, 1)
+        assert (auto.final_exp_batch(ml).reshape(-1) == ref).all()
+        assert (engine.final_exp_batch(ml).reshape(-1) == ref).all()
+    assert (bn254.Pair([bn254.G1Affine(P[:64].tobytes())], [bn254.G2Affine(Q[:128].tobytes())]).raw ==
+            port.pair_batch(P[:64], Q[:128], 1).tobytes())
