@@ -370,6 +370,13 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const
   if (!started) fp12_set_one(acc);
   store_struct(out, i, acc);
 }
+// ok[i] = (x[i] == 1): the comparison half of PairingCheck when the final exponentiation ran in another kernel
+__global__ void k_gt_is_one(const void* x, size_t n, uint8_t* ok) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f; load_struct(f, x, i);
+  ok[i] = fp12_is_one(f) ? 1 : 0;
+}
 // mode 0: a*b ; mode 1: a/b
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void* a, const void* b, size_t n, void* out) {
@@ -718,21 +725,41 @@ int gt_fixed_exp(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* 
                     k_gt_fixed_exp<<<grid_for(c), kBlock, kTowerSmem, s>>>(table, a, c, o);
                   });
 }
-// multi-pairing launch: single kernel for small k, split + combine for large k
+// multi-pairing launch: single kernel for small k, split + combine for large k.
+// cold != nullptr (host-buffer entry points): products of 2..16 pairs whose total pair count is small are latency-
+// bound in the one-thread-per-product kernels (a 1024-message BLS check takes ~15 ms whatever the GPU), so they go
+// through the lane-group kernels instead: Miller loop per PAIR (n*k lane groups), product of each k values, final
+// exponentiation per product -- ~6 ms for the same batch, same bytes out.
+constexpr size_t kVmAutoMax = 16384;
+static inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
+static cudaError_t ensure_mp_scratch(Slot& sl, size_t need, cudaStream_t s) {
+  if (sl.mp_scratch_bytes >= need) return cudaSuccess;
+  if (sl.mp_scratch) { cudaStreamSynchronize(s); cudaFree(sl.mp_scratch); sl.mp_scratch = nullptr; sl.mp_scratch_bytes = 0; }
+  cudaError_t e = cudaMalloc(&sl.mp_scratch, need);
+  if (e == cudaSuccess) sl.mp_scratch_bytes = need;
+  return e;
+}
 template <int MODE>
-cudaError_t launch_multi_pair(Slot& sl, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
+cudaError_t launch_multi_pair(bn254_ctx* ctx, Slot& sl, uint4* cold, const void* a, const void* b, size_t n, int k, void* o, cudaStream_t s) {
+  if (cold && k >= 2 && k <= 2 * kMpChunk && ctx->vm_mode != 2 && use_vm(ctx, n * (size_t)k)) {
+    size_t pairs = n * (size_t)k;
+    cudaError_t e = ensure_mp_scratch(sl, (pairs + n) * BN254_GT_BYTES, s);
+    if (e != cudaSuccess) return e;
+    char* ml = static_cast<char*>(sl.mp_scratch);
+    void* prod = MODE == 2 ? static_cast<void*>(ml + pairs * BN254_GT_BYTES) : o;
+    launch_vm<VmProgMiller>(ctx, a, b, pairs, ml, cold, s);
+    k_mp_combine<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(ml, n, k, prod);
+    if (MODE >= 1) launch_vm<VmProgFinalExp>(ctx, prod, nullptr, n, prod, cold, s);
+    if (MODE == 2) k_gt_is_one<<<grid_for(n), kBlock, 0, s>>>(prod, n, static_cast<uint8_t*>(o));
+    return cudaSuccess;
+  }
   if (k == 1) { k_multi_pair_c<MODE, 1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
   if (k == 2) { k_multi_pair_c<MODE, 2><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
   if (k == 3) { k_multi_pair_c<MODE, 3><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, o); return cudaSuccess; }
   if (k <= 2 * kMpChunk) { k_multi_pair<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, b, n, k, o); return cudaSuccess; }
   int nchunks = (k + kMpChunk - 1) / kMpChunk;
-  size_t need = n * (size_t)nchunks * BN254_GT_BYTES;
-  if (sl.mp_scratch_bytes < need) {
-    if (sl.mp_scratch) { cudaStreamSynchronize(s); cudaFree(sl.mp_scratch); sl.mp_scratch = nullptr; sl.mp_scratch_bytes = 0; }
-    cudaError_t e = cudaMalloc(&sl.mp_scratch, need);
-    if (e != cudaSuccess) return e;
-    sl.mp_scratch_bytes = need;
-  }
+  cudaError_t e = ensure_mp_scratch(sl, n * (size_t)nchunks * BN254_GT_BYTES, s);
+  if (e != cudaSuccess) return e;
   k_mp_partial<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(a, b, n, k, nchunks, sl.mp_scratch);
   k_mp_combine<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(sl.mp_scratch, n, nchunks, o);
   return cudaSuccess;
@@ -906,8 +933,6 @@ void bn254_generators(void* g1, void* g2) {
 }
 
 // ---- pairings -------------------------------------------------------------------------------
-constexpr size_t kVmAutoMax = 16384;
-static inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
 int bn254_pair_batch_dev(bn254_ctx* ctx, const void* dP, const void* dQ, size_t n, void* d_out, void* stream) {
   if (ctx && use_vm(ctx, n)) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);
   return run_dev(ctx, n, [&] { k_pair<<<grid_for(n), kBlock, kTowerSmem, (cudaStream_t)stream>>>(dP, dQ, n, d_out); });
@@ -924,7 +949,7 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
     if (ctx && use_vm(ctx, n) && k == 1 && MODE == 0) return run_dev_vm<VmProgMiller>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream); \
     if (ctx && use_vm(ctx, n) && k == 1 && MODE == 1) return run_dev_vm<VmProgPair>(ctx, dP, dQ, n, d_out, (cudaStream_t)stream);   \
-    return run_dev(ctx, n, [&] { cudaError_t e_ = launch_multi_pair<MODE>(ctx->dev_slot, dP, dQ, n, (int)k, d_out, (cudaStream_t)stream); (void)e_; }); \
+    return run_dev(ctx, n, [&] { cudaError_t e_ = launch_multi_pair<MODE>(ctx, ctx->dev_slot, nullptr, dP, dQ, n, (int)k, d_out, (cudaStream_t)stream); (void)e_; }); \
   }                                                                                                                        \
   int name(bn254_ctx* ctx, const void* P, const void* Q, size_t n, size_t k, OUT_T* out) {                                 \
     if (k == 0 || k > (1u << 20)) return fail(ctx, BN254_ERR_INVALID_SIZES, "invalid inputs sizes");                       \
@@ -933,7 +958,7 @@ int bn254_pair_batch(bn254_ctx* ctx, const void* P, const void* Q, size_t n, voi
                     [kk, ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {                  \
                       if (use_vm(ctx, c) && kk == 1 && MODE == 0) launch_vm<VmProgMiller>(ctx, a, b, c, o, cold, s);          \
                       else if (use_vm(ctx, c) && kk == 1 && MODE == 1) launch_vm<VmProgPair>(ctx, a, b, c, o, cold, s);       \
-                      else launch_multi_pair<MODE>(ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0], a, b, c, kk, o, s);   \
+                      else launch_multi_pair<MODE>(ctx, ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0], cold, a, b, c, kk, o, s);   \
                     });                                                                                                    \
   }
 MULTI_PAIR_ENTRY(bn254_miller_loop_batch, 0, BN254_GT_BYTES, void)

@@ -658,3 +658,18 @@ def test_small_batch_auto_routing(engine):
         assert (engine.final_exp_batch(ml).reshape(-1) == ref).all()
     assert (bn254.Pair([bn254.G1Affine(P[:64].tobytes())], [bn254.G2Affine(Q[:128].tobytes())]).raw ==
             port.pair_batch(P[:64], Q[:128], 1).tobytes())
+    # products of 2..16 pairs with a small total pair count: Miller loop per pair on the lane-group kernels,
+    # k-fold product, final exponentiation -- against the oracle and against the one-thread-per-product kernels
+    for k, n in ((2, 100), (3, 64), (5, 40), (16, 7)):
+        P, Q, _, _ = common.points(n * k, seed=950 + k, threads=8)
+        P, Q = common.with_infinities(P, Q)
+        ref = port.multi_pair_batch(P, Q, n, k, 8)
+        assert (auto.multi_pair_batch(P, Q, k).reshape(-1) == ref).all(), k
+        assert (auto.final_exp_batch(auto.miller_loop_batch(P, Q, k)).reshape(-1) == ref).all(), k
+        okr = port.pairing_check_batch(P, Q, n, k, 8).astype(bool)
+        assert (auto.pairing_check_batch(P, Q, k) == okr).all() and (engine.pairing_check_batch(P, Q, k) == okr).all()
+    # a passing check through the routed path: e(A, B) e(-A, B) == 1
+    A, B = P[:64].copy(), Q[:128].copy()
+    nA = A.copy()
+    nA[32:64] = np.frombuffer(((o.P - int.from_bytes(A[32:64].tobytes(), "little")) % o.P).to_bytes(32, "little"), dtype=np.uint8)
+    assert auto.pairing_check_batch(np.concatenate([A, nA]), np.concatenate([B, B]), 2)[0]
