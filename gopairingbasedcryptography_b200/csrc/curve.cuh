@@ -197,6 +197,7 @@ BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& be
   jac_add_aff(tab[2], tab[0], p2);
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
   for (int i = GLV_MAX_BITS - 1; i >= 0; i--) {
+    BN_CTA_SYNC();  // every thread runs all GLV_MAX_BITS iterations: a full, infinity-free CTA stays in lockstep
     jac_dbl(acc, acc);
     int b = (int)((k1[i >> 5] >> (i & 31)) & 1u) | ((int)((k2[i >> 5] >> (i & 31)) & 1u) << 1);
     if (b) jac_add(acc, acc, tab[b - 1]);
@@ -224,21 +225,21 @@ BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
 // the exponent bits -- a bit-serial or sliding-window ladder would make every warp pay for the union of its
 // lanes' multiplications.
 BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
-  Fp12 tab[3];  // x, x^2, x^3
-  tab[0] = x;
-  fp12_sqr(tab[1], x);
-  fp12_mul(tab[2], tab[1], x);
+  // Control flow is identical for every thread (always two squarings and one product per window, the product by
+  // tab[0] = 1 when the digit is 0), so a full CTA can run in lockstep; only the operand selection is per thread.
+  Fp12 tab[4];  // 1, x, x^2, x^3
+  fp12_set_one(tab[0]);
+  tab[1] = x;
+  fp12_sqr(tab[2], x);
+  fp12_mul(tab[3], tab[2], x);
   Fp12 acc;
-  bool started = false;
+  fp12_set_one(acc);
   for (int w = 127; w >= 0; w--) {
-    if (started) { fp12_sqr(acc, acc); fp12_sqr(acc, acc); }
+    if (w != 127) { fp12_sqr(acc, acc); fp12_sqr(acc, acc); }
     int d = (int)((k[w >> 4] >> ((w & 15) * 2)) & 3u);
-    if (d) {
-      if (started) fp12_mul(acc, acc, tab[d - 1]);
-      else { acc = tab[d - 1]; started = true; }
-    }
+    Fp12 m = tab[d];
+    fp12_mul(acc, acc, m);
   }
-  if (!started) fp12_set_one(acc);
   out = acc;
 }
 
@@ -266,20 +267,18 @@ BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
     if (v > 3) { v -= 8; carry = 1; } else carry = 0;
     dg[i] = (signed char)v;
   }
+  // uniform control flow (see gt_exp): three squarings and one product per digit, digit 0 multiplies by 1
   Fp12 acc;
-  bool started = false;
+  fp12_set_one(acc);
   for (int i = 85; i >= 0; i--) {
-    if (started) fp12_cyclo_sqr_n(acc, acc, 3);
+    if (i != 85) fp12_cyclo_sqr_n(acc, acc, 3);
     int d = dg[i];
-    if (d > 0) {
-      if (started) fp12_mul(acc, acc, tab[d - 1]);
-      else { acc = tab[d - 1]; started = true; }
-    } else if (d < 0) {
-      if (started) fp12_mul_conj(acc, acc, tab[-d - 1]);
-      else { fp12_conj(acc, tab[-d - 1]); started = true; }
-    }
+    Fp12 m;
+    if (d == 0) fp12_set_one(m);
+    else if (d > 0) m = tab[d - 1];
+    else fp12_conj(m, tab[-d - 1]);
+    fp12_mul(acc, acc, m);
   }
-  if (!started) fp12_set_one(acc);
   out = acc;
 }
 

@@ -254,8 +254,11 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_final_exp(const vo
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul(const void* base, size_t base_stride, const void* scalars, size_t n, void* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  A b;
+  bool plain = i < n;
+  if (plain) { load_struct(b, base, i * base_stride); plain = !aff_is_inf(b); }
+  cta_lockstep_set(__syncthreads_and(plain) != 0);  // the ladder has a fixed trip count; infinity bases return early
   if (i >= n) return;
-  A b; load_struct(b, base, i * base_stride);
   uint32_t s[8];
   const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(scalars) + i * 32);
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const 
 }
 template <int CYCLO>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
-  cta_lockstep_set(false);
+  cta_lockstep_set(cta_is_full(n));  // gt_exp / gt_cyclo_exp have thread-uniform control flow
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp12 b; load_struct(b, x, i * x_stride);
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void*
 // fixed-base GT exponentiation: out = prod_w table[w][byte_w(k)] -- 32 Fp12 products, no squarings.  The table
 // (32 x 255 x 384 B = 3.1 MB, L2-resident) is built once per base with k_gt_exp on the scalars d << 8w.
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const Fp12* table, const void* k, size_t n, void* out) {
-  cta_lockstep_set(false);
+  cta_lockstep_set(cta_is_full(n));
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
@@ -359,15 +362,13 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
   s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
   Fp12 acc, e;
-  bool started = false;
-  for (int w = 0; w < kFixedWindows; w++) {
+  fp12_set_one(acc);
+  for (int w = 0; w < kFixedWindows; w++) {  // uniform: one product per window, by 1 when the digit is 0
     int d = (int)((s[w >> 2] >> ((w & 3) * 8)) & 0xFFu);
-    if (d) {
-      load_struct(e, table, (size_t)w * kFixedEntries + d - 1);
-      if (started) fp12_mul(acc, acc, e); else { acc = e; started = true; }
-    }
+    if (d) load_struct(e, table, (size_t)w * kFixedEntries + d - 1);
+    else fp12_set_one(e);
+    fp12_mul(acc, acc, e);
   }
-  if (!started) fp12_set_one(acc);
   store_struct(out, i, acc);
 }
 // ok[i] = (x[i] == 1): the comparison half of PairingCheck when the final exponentiation ran in another kernel
