@@ -15,6 +15,9 @@ NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "nolockstep": NOLS,
+    "blk96": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=4", "-DBN254_BLOCK=96"],
+    "blk192": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=2", "-DBN254_BLOCK=192"],
+    "blk64": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=6", "-DBN254_BLOCK=64"],
     "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
     "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
