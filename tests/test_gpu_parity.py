@@ -208,10 +208,11 @@ def test_gt_vs_oracle(engine):
     assert (engine.gt_div_batch(gt, gt2).reshape(-1) == port.gt_div_batch(gt.reshape(-1), gt2.reshape(-1), n, 8)).all()
 
 
-def test_bilinearity_checksum_large(engine):
-    """Size-independent property at a size the oracle cannot finish: prod_i e(a_i G1, b_i G2) ==
-    e(G1,G2)^(sum a_i b_i), with the points generated on the GPU."""
-    n = 1 << 14
+@pytest.mark.parametrize("log2n", [14, 20])
+def test_bilinearity_checksum_large(engine, log2n):
+    """Size-independent property at a size the oracle cannot finish (2^20 = BASELINE configs[1]):
+    prod_i e(a_i G1, b_i G2) == e(G1,G2)^(sum a_i b_i), with the points generated on the GPU."""
+    n = 1 << log2n
     a = common.scalars(n, seed=7, edges=False)
     b = common.scalars(n, seed=8, edges=False)
     g1, g2 = port.generators()
