@@ -674,3 +674,57 @@ def test_small_batch_auto_routing(engine):
     nA = A.copy()
     nA[32:64] = np.frombuffer(((o.P - int.from_bytes(A[32:64].tobytes(), "little")) % o.P).to_bytes(32, "little"), dtype=np.uint8)
     assert auto.pairing_check_batch(np.concatenate([A, nA]), np.concatenate([B, B]), 2)[0]
+
+
+def test_bsw07_round_trip_full_size(engine):
+    """BASELINE configs[2] at its own size (batch 4096, 100-attribute AND policy) through a size-independent property:
+    decrypt(encrypt(M)) == M for every ciphertext.  Keys and ciphertexts follow cpabe/bsw07/bsw07_cpabe.go:55-170 with its
+    stub attribute hashes (H1 = g1, H2 = g2, bsw07_cpabe_utils.go:8-32); the 100 shares of each ciphertext are any values
+    with sum_i Delta_i q(i) = s (equivalent to a random degree-99 polynomial with q(0) = s)."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    n, m = 4096, 100
+    R = o.R
+    rng = o.SplitMix64(0xB2000254 + 3)
+    g1, g2 = port.generators()
+    alpha, beta, r = rng.scalar(), rng.scalar(), rng.scalar()
+    rj = [rng.scalar() for _ in range(m)]
+    inv_beta = pow(beta, -1, R)
+    # user key (G2 side)
+    d = engine.g2_mul_base_batch(g2, common.scalar_bytes([(alpha + r) * inv_beta % R]))[0]
+    dj = engine.g2_mul_base_batch(g2, common.scalar_bytes([(r + x) % R for x in rj]))
+    djp = engine.g2_mul_base_batch(g2, common.scalar_bytes(rj))
+    # Lagrange coefficients at 0 for the points 1..m (access_tree_node.go:151-158)
+    delta = []
+    for i in range(1, m + 1):
+        num, den = 1, 1
+        for j in range(1, m + 1):
+            if j != i:
+                num = num * (-j) % R
+                den = den * (i - j) % R
+        delta.append(num * pow(den, -1, R) % R)
+    # ciphertexts
+    s = [rng.scalar() for _ in range(n)]
+    msg = [rng.scalar() for _ in range(n)]
+    inv_last = pow(delta[-1], -1, R)
+    shares = np.empty((n, m, 32), dtype=np.uint8)
+    for c in range(n):
+        q = [rng.next() | (rng.next() << 64) | (rng.next() << 128) for _ in range(m - 1)]  # < 2^192 < r
+        acc = sum(dl * qi for dl, qi in zip(delta, q)) % R
+        q.append((s[c] - acc) * inv_last % R)
+        shares[c] = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in q), dtype=np.uint8).reshape(m, 32)
+    cy = engine.g1_mul_base_batch(g1, shares.reshape(-1, 32)).reshape(n, m, 64)  # Cy = g1^q(i); Cy' = H1^q(i) = the same
+    cc = engine.g1_mul_base_batch(g1, common.scalar_bytes([beta * x % R for x in s]))  # C = h^s, h = g1^beta
+    e = port.pair_batch(g1, g2, 1)
+    M = engine.gt_cyclo_exp_base_batch(e, common.scalar_bytes(msg))
+    ctil = engine.gt_cyclo_exp_base_batch(e, common.scalar_bytes([(mm + alpha * x) % R for mm, x in zip(msg, s)]))
+    db = common.scalar_bytes(delta).reshape(m, 32)
+    pol = schemes.bsw07_policy_lines(engine, dj, djp, d, db)
+    got = schemes.bsw07_decrypt_batch(engine, cy, cy, dj, djp, cc, d, ctil, db, lines=pol, folded=True)
+    assert (got == M).all()
+    assert (M[0] == port.gt_exp_batch(e, common.scalar_bytes([msg[0]]), 1)).all()
+    # the other two decryption routes on a slice of the same batch
+    k = 24
+    key = schemes.bsw07_key_lines(engine, dj, djp, d)
+    assert (schemes.bsw07_decrypt_batch(engine, cy[:k], cy[:k], dj, djp, cc[:k], d, ctil[:k], db, lines=key) == M[:k]).all()
+    assert (schemes.bsw07_decrypt_batch(engine, cy[:k], cy[:k], dj, djp, cc[:k], d, ctil[:k], db) == M[:k]).all()
