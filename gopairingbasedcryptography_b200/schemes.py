@@ -218,3 +218,63 @@ def to_g2_batch(engine, strings):
 def bytes_to_g2_batch(engine, msgs):
     """hash.BytesToG2 (the H(m) of BLS: signature/bls01_signature/bls_signature.go:60,73) -> (n, 128)."""
     return engine.hash_to_g2_batch(msgs, DST_BYTES_G2)
+
+
+# ---- SURVEY 8f-4: setup / key-generation batches (fixed-base heavy) ------------------------------------------------
+def _scalar_bytes(ks):
+    return np.frombuffer(b"".join(int(k % R_MOD).to_bytes(32, "little") for k in ks), dtype=np.uint8).reshape(-1, 32)
+
+
+def tau_powers_g1(engine, tau, B):
+    """[tau]1, [tau^2]1, ..., [tau^B]1 (bibe/afp25_bibe/afp25_bibe.go:156-162): the B dependent Fr products stay on
+    the host, the B fixed-base multiplications are ONE batch call on the window table of the generator."""
+    g1, _ = _generators(engine)
+    pw, acc = [], tau % R_MOD
+    for _ in range(B):
+        pw.append(acc)
+        acc = acc * tau % R_MOD
+    return engine.g1_mul_base_batch(g1, _scalar_bytes(pw))
+
+
+def tau_powers_g2(engine, tau, B):
+    """[tau]2 ... [tau^B]2 (bibe/gwww25_bibe/gwww25_bibe.go:107-112)."""
+    _, g2 = _generators(engine)
+    pw, acc = [], tau % R_MOD
+    for _ in range(B):
+        pw.append(acc)
+        acc = acc * tau % R_MOD
+    return engine.g2_mul_base_batch(g2, _scalar_bytes(pw))
+
+
+def waters05_setup(engine, alpha, u_exponents):
+    """Waters05 SetUp (ibe/waters05_ibe/waters05_ibe.go:117-151): g1^alpha and the 257 G2 public parameters
+    U', U_1..U_256 = g2^{u_i} as one fixed-base batch.  u_exponents: 257 integers.  -> (g1_alpha (64,), U (257, 128))."""
+    g1, g2 = _generators(engine)
+    g1a = engine.g1_mul_base_batch(g1, _scalar_bytes([alpha]))[0]
+    return g1a, engine.g2_mul_base_batch(g2, _scalar_bytes(u_exponents))
+
+
+def bsw07_keygen(engine, g2_alpha, beta, r, rj):
+    """BSW07 KeyGenerate (cpabe/bsw07/bsw07_cpabe.go:96-129) for one user with len(rj) attributes, with the reference's
+    stub hash H2(j) = g2: D = (g2^alpha g2^r)^{1/beta}, Dj = g2^r H2(j)^{rj}, Dj' = g2^{rj}.
+    g2_alpha: (128,) master-key component; beta, r: integers; rj: list of integers.  -> (D (128,), Dj (m, 128), Dj' (m, 128))."""
+    _, g2 = _generators(engine)
+    m = len(rj)
+    g2r = engine.g2_mul_base_batch(g2, _scalar_bytes([r]))
+    d = engine.g2_mul_batch(engine.g2_add_batch(np.ascontiguousarray(g2_alpha).reshape(1, G2_BYTES), g2r),
+                            _scalar_bytes([pow(beta, -1, R_MOD)]))[0]
+    djp = engine.g2_mul_base_batch(g2, _scalar_bytes(rj))  # H2(j)^{rj} with H2(j) = g2, and Dj' = g2^{rj}
+    dj = engine.g2_add_batch(np.broadcast_to(g2r.reshape(1, G2_BYTES), (m, G2_BYTES)).copy(), djp)
+    return d, dj, djp
+
+
+_GEN_CACHE = {}
+
+
+def _generators(engine):
+    if "g" not in _GEN_CACHE:
+        from .bn254 import Generators
+
+        _, _, a1, a2 = Generators()
+        _GEN_CACHE["g"] = (np.frombuffer(a1.raw, dtype=np.uint8).copy(), np.frombuffer(a2.raw, dtype=np.uint8).copy())
+    return _GEN_CACHE["g"]

@@ -728,3 +728,26 @@ def test_bsw07_round_trip_full_size(engine):
     key = schemes.bsw07_key_lines(engine, dj, djp, d)
     assert (schemes.bsw07_decrypt_batch(engine, cy[:k], cy[:k], dj, djp, cc[:k], d, ctil[:k], db, lines=key) == M[:k]).all()
     assert (schemes.bsw07_decrypt_batch(engine, cy[:k], cy[:k], dj, djp, cc[:k], d, ctil[:k], db) == M[:k]).all()
+
+
+def test_setup_keygen_batches(engine):
+    """§8f-4: tau-power ladders (afp25_bibe.go:156-162, gwww25_bibe.go:107-112), Waters05 SetUp (waters05_ibe.go:117-151)
+    and BSW07 KeyGenerate (bsw07_cpabe.go:96-129) as fixed-base batches, against the oracle."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    g1, g2 = port.generators()
+    tau, B = 0x1234567890ABCDEF1234567890ABCDEF % o.R, 40
+    pw = [pow(tau, i + 1, o.R) for i in range(B)]
+    assert (schemes.tau_powers_g1(engine, tau, B).reshape(-1) == port.g1_mul_base_batch(g1, common.scalar_bytes(pw), B, 8)).all()
+    assert (schemes.tau_powers_g2(engine, tau, B).reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes(pw), B, 8)).all()
+    us = common.scalars(257, seed=81, edges=False)
+    g1a, U = schemes.waters05_setup(engine, 987654321, us)
+    assert (g1a == port.g1_mul_base_batch(g1, common.scalar_bytes([987654321]), 1)).all()
+    assert (U.reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes(us), 257, 8)).all()
+    alpha, beta, r = common.scalars(3, seed=82, edges=False)
+    rj = common.scalars(7, seed=83, edges=False)
+    g2a = port.g2_mul_base_batch(g2, common.scalar_bytes([alpha]), 1)
+    d, dj, djp = schemes.bsw07_keygen(engine, g2a, beta, r, rj)
+    assert (d == port.g2_mul_base_batch(g2, common.scalar_bytes([(alpha + r) * pow(beta, -1, o.R) % o.R]), 1)).all()
+    assert (dj.reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes([(r + x) % o.R for x in rj]), 7, 8)).all()
+    assert (djp.reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes(rj), 7, 8)).all()
