@@ -82,8 +82,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 limbs (4x64 Montgomery)", "data": "synthetic",
-        "config": {"workload": "raw batched bn254.Pair, 2^%d random (G1,G2) pairs" % args.log2_batch,
-                   "sample_pairings_per_step": sample},
+        "config": {"workload": "raw batched bn254.Pair, 2^%d random (G1,G2) pairs per GPU" % args.log2_batch,
+                   "batch_per_gpu": 1 << args.log2_batch, "sample_pairings_per_step": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d pairings per step on %d threads; C restatement of gnark's algorithm (gnark itself "
                                    "cannot run: no Go toolchain)" % (sample, threads)},

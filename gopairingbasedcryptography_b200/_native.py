@@ -19,7 +19,7 @@ SYMBOLS = [
     "bn254_g1_mul_batch_dev", "bn254_g2_mul_batch_dev", "bn254_g1_add_batch", "bn254_g2_add_batch", "bn254_g1_subset_sum_batch", "bn254_g2_subset_sum_batch",
     "bn254_g1_sum_batch", "bn254_g2_sum_batch",
     "bn254_gt_exp_batch", "bn254_gt_exp_base_batch", "bn254_gt_cyclo_exp_batch", "bn254_gt_cyclo_exp_base_batch", "bn254_gt_exp_batch_dev", "bn254_gt_mul_batch",
-    "bn254_gt_div_batch", "bn254_fp_mul_batch", "bn254_hash_to_g1_batch", "bn254_hash_to_g2_batch",
+    "bn254_gt_div_batch", "bn254_fp_mul_batch", "bn254_hash_to_g1_batch", "bn254_hash_to_g2_batch", "bn254_pairing_check2_fixed_g1_batch",
 ]
 
 

@@ -274,6 +274,20 @@ class Engine:
     def fp_mul_batch(self, a, b):
         return self._binary("bn254_fp_mul_batch", a, b, 32)
 
+    def pairing_check2_fixed_g1_batch(self, p0, p1, q0, q1):
+        """ok[i] = PairingCheck([p0, p1], [q0[i], q1[i]]): two G1 points shared by the batch (BLS verification shape)."""
+        p01 = np.concatenate([_u8(p0, G1_BYTES, "p0"), _u8(p1, G1_BYTES, "p1")])
+        q0, q1 = _u8(q0, G2_BYTES, "q0"), _u8(q1, G2_BYTES, "q1")
+        if p01.size != 2 * G1_BYTES or q0.size != q1.size:
+            raise ValueError("invalid inputs sizes")
+        n = q0.size // G2_BYTES
+        out = np.empty(n, dtype=np.uint8)
+        fn = self._lib.bn254_pairing_check2_fixed_g1_batch
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, p01.ctypes.data_as(ctypes.c_void_p), q0.ctypes.data_as(ctypes.c_void_p),
+                       q1.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.astype(bool)
+
     # ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2; hash/hash_to.go in the reference) ----
     def _hash_to_curve(self, name, msgs, dst, out_bytes):
         msgs = [bytes(m) for m in msgs]

@@ -156,6 +156,25 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair_c(const
   if (MODE == 2) static_cast<uint8_t*>(out)[i] = fp12_is_one(f) ? 1 : 0;
   else store_struct(out, i, f);
 }
+// PairingCheck of e(P0, Q0[i]) e(P1, Q1[i]) with the two G1 points shared by the whole batch: the shape of BLS
+// verification (signature/bls01_signature/bls_signature.go:71-89: P0 = pk, P1 = -g1, Q0 = H(m_i), Q1 = sigma_i).
+// Saves a third of the host->device bytes and the host-side replication of (pk, -g1) per message.
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_check2_fixed_g1(const void* P01, const void* Q0, const void* Q1, size_t n, uint8_t* ok) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  G1Aff p[2]; G2Aff q[2]; G2Proj T[2];
+  bool plain = i < n;
+  if (plain) {
+    load_struct(p[0], P01, 0); load_struct(p[1], P01, 1);
+    load_struct(q[0], Q0, i); load_struct(q[1], Q1, i);
+    plain = !g1_is_inf(p[0]) && !g1_is_inf(p[1]) && !g2_is_inf(q[0]) && !g2_is_inf(q[1]);
+  }
+  cta_lockstep_set(__syncthreads_and(plain) != 0);
+  if (i >= n) return;
+  Fp12 f;
+  miller_loop_t<2>(f, p, q, T, 2);
+  final_exp(f, f);
+  ok[i] = fp12_is_one(f) ? 1 : 0;
+}
 // mode 0: Miller product only; 1: + final exponentiation; 2: pairing check (writes one byte)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_multi_pair(const void* P, const void* Q, size_t n, int k, void* out) {
@@ -370,6 +389,15 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const
     fp12_mul(acc, acc, e);
   }
   store_struct(out, i, acc);
+}
+// expands the fixed-G1 check into the (P, Q) pair arrays the per-pair lane-group Miller kernel reads
+__global__ void k_pack_check2(const void* P01, const void* Q0, const void* Q1, size_t n, void* P, void* Q) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Aff p0, p1; G2Aff q0, q1;
+  load_struct(p0, P01, 0); load_struct(p1, P01, 1); load_struct(q0, Q0, i); load_struct(q1, Q1, i);
+  store_struct(P, 2 * i, p0); store_struct(P, 2 * i + 1, p1);
+  store_struct(Q, 2 * i, q0); store_struct(Q, 2 * i + 1, q1);
 }
 // ok[i] = (x[i] == 1): the comparison half of PairingCheck when the final exponentiation ran in another kernel
 __global__ void k_gt_is_one(const void* x, size_t n, uint8_t* ok) {
@@ -587,17 +615,21 @@ int fail(bn254_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? BN254_ERR_OOM : BN254_ERR_CUDA, #call, e_); } while (0)
 
 struct Operand { const void* ptr; size_t item_bytes; bool broadcast; };
-// launch(d_in0, d_in1, count, d_out, stream)
+// Chunked, double-buffered host-buffer driver: up to three input operands (each per-item or broadcast), one output.
+// launch(d_in[3], count, d_out, stream, cold)
 template <typename L>
-int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_item, size_t n, L launch) {
+int run_host_n(bn254_ctx* ctx, const Operand* in, int nin, void* out, size_t out_item, size_t n, L launch) {
   if (!ctx) return BN254_ERR_BAD_ARG;
   if (n == 0) return BN254_OK;
-  if (!in0.ptr || !out || (in1.item_bytes && !in1.ptr)) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  if (!out) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  size_t fixed = 1024, per = out_item;
+  for (int k = 0; k < nin; k++) {
+    if (in[k].item_bytes && !in[k].ptr) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+    if (in[k].broadcast) fixed += in[k].item_bytes + 256; else per += in[k].item_bytes;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  size_t b0 = in0.broadcast ? in0.item_bytes : 0, b1 = in1.broadcast ? in1.item_bytes : 0;
-  size_t per = (in0.broadcast ? 0 : in0.item_bytes) + (in1.broadcast ? 0 : in1.item_bytes) + out_item;
-  size_t chunk = std::min<size_t>({n, kMaxChunkItems, (ctx->slot_bytes - b0 - b1 - 1024) / per});
+  size_t chunk = std::min<size_t>({n, kMaxChunkItems, (ctx->slot_bytes - fixed) / per});
   if (chunk == 0) return fail(ctx, BN254_ERR_BAD_ARG, "element too large for staging");
   auto finish = [&](Slot& s) -> int {
     if (!s.busy) return BN254_OK;
@@ -614,19 +646,17 @@ int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_ite
     int rc = finish(s);
     if (rc) return rc;
     size_t off = 0;
-    auto align = [&]() { off = (off + 255) & ~size_t(255); };
-    size_t o0 = off, l0 = in0.broadcast ? in0.item_bytes : in0.item_bytes * c;
-    memcpy(s.h + o0, static_cast<const char*>(in0.ptr) + (in0.broadcast ? 0 : done * in0.item_bytes), l0);
-    off += l0; align();
-    size_t o1 = off, l1 = 0;
-    if (in1.item_bytes) {
-      l1 = in1.broadcast ? in1.item_bytes : in1.item_bytes * c;
-      memcpy(s.h + o1, static_cast<const char*>(in1.ptr) + (in1.broadcast ? 0 : done * in1.item_bytes), l1);
-      off += l1; align();
+    const void* d_in[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < nin; k++) {
+      d_in[k] = s.d + off;
+      if (!in[k].item_bytes) continue;
+      size_t l = in[k].broadcast ? in[k].item_bytes : in[k].item_bytes * c;
+      memcpy(s.h + off, static_cast<const char*>(in[k].ptr) + (in[k].broadcast ? 0 : done * in[k].item_bytes), l);
+      off = (off + l + 255) & ~size_t(255);
     }
     size_t oo = off, lo = out_item * c;
     CU(cudaMemcpyAsync(s.d, s.h, oo, cudaMemcpyHostToDevice, s.stream));
-    launch(s.d + o0, s.d + o1, c, s.d + oo, s.stream, s.vm_cold);
+    launch(d_in, c, s.d + oo, s.stream, s.vm_cold);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h + oo, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream));
@@ -636,6 +666,14 @@ int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_ite
   }
   for (int i = 0; i < 2; i++) { int rc = finish(ctx->slot[(ci + i) & 1]); if (rc) return rc; }
   return BN254_OK;
+}
+// two-operand form: launch(d_in0, d_in1, count, d_out, stream, cold)
+template <typename L>
+int run_host(bn254_ctx* ctx, Operand in0, Operand in1, void* out, size_t out_item, size_t n, L launch) {
+  if (n && !in0.ptr) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  Operand in[2] = {in0, in1};
+  return run_host_n(ctx, in, 2, out, out_item, n,
+                    [&](const void* const* d, size_t c, void* o, cudaStream_t s, uint4* cold) { launch(d[0], d[1], c, o, s, cold); });
 }
 
 template <typename L>
@@ -875,7 +913,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
                                    (const void*)k_multi_pair_c<0, 2>, (const void*)k_multi_pair_c<1, 2>, (const void*)k_multi_pair_c<2, 2>,
                                    (const void*)k_multi_pair_c<0, 3>, (const void*)k_multi_pair_c<1, 3>, (const void*)k_multi_pair_c<2, 3>, (const void*)k_multi_pair<0>, (const void*)k_multi_pair<1>, (const void*)k_multi_pair<2>,
                                    (const void*)k_mp_partial, (const void*)k_mp_combine<0>, (const void*)k_mp_combine<1>, (const void*)k_mp_combine<2>,
-                                   (const void*)k_final_exp, (const void*)k_hash_to_curve<1>, (const void*)k_hash_to_curve<2>, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
+                                   (const void*)k_final_exp, (const void*)k_check2_fixed_g1, (const void*)k_hash_to_curve<1>, (const void*)k_hash_to_curve<2>, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
     for (const void* k : tower_kernels)
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTowerSmem) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
   }
@@ -1169,6 +1207,28 @@ int bn254_gt_div_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, v
 int bn254_fp_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, 32, false}, {b, 32, false}, out, 32, n,
                   [](const void* x, const void* y, size_t c, void* o, cudaStream_t s, uint4*) { k_fp_mul<<<grid_for(c), kBlock, 0, s>>>(x, y, c, o); });
+}
+
+// ---- BLS-shaped check: two G1 points fixed for the batch ---------------------------------------------------------
+int bn254_pairing_check2_fixed_g1_batch(bn254_ctx* ctx, const void* P01, const void* Q0, const void* Q1, size_t n, uint8_t* ok) {
+  if (n && (!P01 || !Q0 || !Q1)) return fail(ctx, BN254_ERR_BAD_ARG, "null pointer");
+  Operand in[3] = {{P01, 2 * BN254_G1_BYTES, true}, {Q0, BN254_G2_BYTES, false}, {Q1, BN254_G2_BYTES, false}};
+  return run_host_n(ctx, in, 3, ok, 1, n, [ctx](const void* const* d, size_t c, void* o, cudaStream_t s, uint4* cold) {
+    Slot& sl = ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0];
+    // small batch: lane-group kernels (see launch_multi_pair); falls through to the thread kernel if the scratch cannot grow
+    if (ctx->vm_mode != 2 && use_vm(ctx, 2 * c) &&
+        ensure_mp_scratch(sl, (size_t)(2 * c) * (BN254_G1_BYTES + BN254_G2_BYTES + BN254_GT_BYTES) + c * BN254_GT_BYTES, s) == cudaSuccess) {
+      char* base = static_cast<char*>(sl.mp_scratch);
+      char* Pp = base; char* Qp = Pp + 2 * c * BN254_G1_BYTES; char* ml = Qp + 2 * c * BN254_G2_BYTES; char* prod = ml + 2 * c * BN254_GT_BYTES;
+      k_pack_check2<<<grid_for(c), kBlock, 0, s>>>(d[0], d[1], d[2], c, Pp, Qp);
+      launch_vm<VmProgMiller>(ctx, Pp, Qp, 2 * c, ml, cold, s);
+      k_mp_combine<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(ml, c, 2, prod);
+      launch_vm<VmProgFinalExp>(ctx, prod, nullptr, c, prod, cold, s);
+      k_gt_is_one<<<grid_for(c), kBlock, 0, s>>>(prod, c, static_cast<uint8_t*>(o));
+      return;
+    }
+    k_check2_fixed_g1<<<grid_for(c), kBlock, kTowerSmem, s>>>(d[0], d[1], d[2], c, static_cast<uint8_t*>(o));
+  });
 }
 
 // ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2) -----------------------------------------------------------

@@ -94,12 +94,8 @@ def bsw07_decrypt_batch(engine, cy, cy_prime, dj, dj_prime, c, d, c_tilde, delta
 
 def bls_verify_batch(engine, pk, g1, hm, sigma_neg):
     """n BLS verifications e(pk, H(m_i)) e(g1, -sigma_i) == 1 (signature/bls01_signature/bls_signature.go:71-89).
-    pk, g1: (64,) ; hm, sigma_neg: (n, 128)."""
-    n = hm.shape[0]
-    P = np.concatenate([np.tile(np.ascontiguousarray(pk).reshape(1, 64), (n, 1)),
-                        np.tile(np.ascontiguousarray(g1).reshape(1, 64), (n, 1))], axis=1)
-    Q = np.concatenate([np.ascontiguousarray(hm).reshape(n, 128), np.ascontiguousarray(sigma_neg).reshape(n, 128)], axis=1)
-    return engine.pairing_check_batch(P.reshape(-1), Q.reshape(-1), 2)
+    pk, g1: (64,) ; hm, sigma_neg: (n, 128).  (pk, g1) are shared by the batch: one fixed-G1 check call, no replication."""
+    return engine.pairing_check2_fixed_g1_batch(pk, g1, np.ascontiguousarray(hm).reshape(-1, 128), np.ascontiguousarray(sigma_neg).reshape(-1, 128))
 
 
 def sw05_fibe_decrypt_batch(engine, di, ei, e_prime, deltas):

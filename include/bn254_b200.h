@@ -137,6 +137,11 @@ int bn254_gt_cyclo_exp_base_batch(bn254_ctx*, const void* x1, const void* k, siz
 int bn254_gt_mul_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 int bn254_gt_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
 
+/* ok[i] = PairingCheck({P0, P1}, {Q0[i], Q1[i]}) with the two G1 points shared by the batch: BLS verification
+ * [signature/bls01_signature/bls_signature.go:71-89: P0 = pk, P1 = -g1, Q0[i] = H(m_i), Q1[i] = sigma_i].
+ * P01: 128 B (P0 then P1); Q0, Q1: n x 128 B; ok: n bytes. */
+int bn254_pairing_check2_fixed_g1_batch(bn254_ctx*, const void* P01, const void* Q0, const void* Q1, size_t n, uint8_t* ok);
+
 /* bn254.HashToG1(msg, dst) / bn254.HashToG2(msg, dst) for n messages at once
  * [hash/hash_to.go:113-119 ToG1, 169-175 BytesToG1, 203-209 ToG2, 271-277 BytesToG2; callers
  *  signature/bls01_signature/bls_signature.go:60,73, ibe/bf01_ibe/bf01_ibe.go:130,158, dabe/lw11_dabe.go:96,177,

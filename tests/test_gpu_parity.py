@@ -751,3 +751,28 @@ def test_setup_keygen_batches(engine):
     assert (d == port.g2_mul_base_batch(g2, common.scalar_bytes([(alpha + r) * pow(beta, -1, o.R) % o.R]), 1)).all()
     assert (dj.reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes([(r + x) % o.R for x in rj]), 7, 8)).all()
     assert (djp.reshape(-1) == port.g2_mul_base_batch(g2, common.scalar_bytes(rj), 7, 8)).all()
+
+
+def test_fixed_g1_pairing_check(engine):
+    """bn254_pairing_check2_fixed_g1_batch (BLS verification shape) against the general check, on the thread kernels
+    (fixture) and on the default context (small batches routed to the lane-group kernels), ragged size, with failures."""
+    from gopairingbasedcryptography_b200 import bn254
+
+    n = 300
+    g1, g2 = port.generators()
+    skb = common.scalar_bytes([0xC0FFEE1234567])
+    pk = engine.g1_mul_base_batch(g1, skb)[0]
+    hm = engine.g2_mul_base_batch(g2, common.scalar_bytes(common.scalars(n, seed=31, edges=False)))
+    sig = engine.g2_mul_batch(hm, np.tile(skb, n))
+    sig[7] = hm[7]          # wrong signature
+    hm2 = hm.copy()
+    hm2[11] = 0             # point at infinity in one pair -> that pair is skipped, check fails
+    from gopairingbasedcryptography_b200 import schemes
+    ng1 = schemes.neg_g1(g1)[0]
+    P = np.concatenate([np.tile(pk.reshape(1, 64), (n, 1)), np.tile(ng1.reshape(1, 64), (n, 1))], axis=1)
+    Qg = np.concatenate([hm2, sig], axis=1)
+    ref = port.pairing_check_batch(P.reshape(-1), Qg.reshape(-1), n, 2, 8).astype(bool)
+    assert not ref[7] and not ref[11] and ref.sum() == n - 2
+    assert (engine.pairing_check2_fixed_g1_batch(pk, ng1, hm2, sig) == ref).all()
+    assert (bn254.default_engine().pairing_check2_fixed_g1_batch(pk, ng1, hm2, sig) == ref).all()
+    assert engine.pairing_check2_fixed_g1_batch(pk, ng1, b"", b"").shape == (0,)
