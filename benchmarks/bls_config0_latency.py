@@ -1,10 +1,10 @@
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import os
 import numpy as np
 from gopairingbasedcryptography_b200 import bn254, schemes
 from oracle import port, bn254_ref as o
-sys.path.insert(0, '/root/repo/tests'); import common
+sys.path.insert(0, os.path.join(ROOT, 'tests')); import common
 os.environ["BN254_IMPL"] = "thread"; thr = bn254.Engine(0); del os.environ["BN254_IMPL"]
 auto = bn254.Engine(0)
 n = 1024
