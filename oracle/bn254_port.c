@@ -3,7 +3,9 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library; the product (CUDA engine behind include/bn254_b200.h) never does.
  *
- * PARITY UNPINNED: the algorithm the reference runs lives in the third-party Go module
+ * PARITY UNPINNED AGAINST GNARK (one external anchor: the EIP-197 pairing-check vector of tests/test_external_kat.py
+ * holds for this library too; the final-exponent cofactor, hence the exact GT bytes, stays unpinned): the algorithm the
+ * reference runs lives in the third-party Go module
  * github.com/consensys/gnark-crypto v0.19.0 (/root/reference/go.mod:5), absent from disk, and
  * the reference's tests hold no golden vectors for this path.  This file restates
  * the *published* algorithm structure gnark documents for ecc/bn254:

@@ -4,11 +4,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this package.  The product (the CUDA engine
 behind ``include/bn254_b200.h``) never calls into it.
 
-PARITY UNPINNED: the arithmetic the reference executes lives in the third-party Go
-module ``github.com/consensys/gnark-crypto v0.19.0`` (/root/reference/go.mod:5), which
-is not on disk, and no Go toolchain exists in this image.  The reference's own tests
-hold no golden vectors for Pair / ScalarMultiplication / GT.Exp.
-This file therefore restates the *published* definitions:
+PARITY UNPINNED AGAINST GNARK, with one external anchor: the arithmetic the reference
+executes lives in the third-party Go module ``github.com/consensys/gnark-crypto v0.19.0``
+(/root/reference/go.mod:5), which is not on disk, and no Go toolchain exists in this
+image.  The reference's own tests hold no golden vectors for Pair / ScalarMultiplication /
+GT.Exp.  What IS pinned from outside the repository: the EIP-197
+pairing-check known-answer vector 'jeff1' of go-ethereum's bn256Pairing test set
+(tests/golden/eip197_pairing_check.json, tests/test_external_kat.py) holds -- it fixes
+the curve, the twist, the G2 generator, the group laws and the Miller loop + final
+exponentiation as a non-degenerate bilinear map.  A check against 1 cannot see the cofactor
+of the final exponent, so the exact GT bytes (gnark's cofactor s below) remain unpinned.
+This file restates the *published* definitions:
 
 * optimal-ate Miller function  f_{6x+2,Q}(P) * l_{[6x+2]Q,pi(Q)}(P) * l_{[6x+2]Q+pi(Q),-pi^2(Q)}(P)
   evaluated with textbook affine chord/tangent lines (no projective formulas, no
