@@ -8,7 +8,8 @@ PARITY UNPINNED AGAINST GNARK, with one external anchor: the arithmetic the refe
 executes lives in the third-party Go module ``github.com/consensys/gnark-crypto v0.19.0``
 (/root/reference/go.mod:5), which is not on disk, and no Go toolchain exists in this
 image.  The reference's own tests hold no golden vectors for Pair / ScalarMultiplication /
-GT.Exp.  What IS pinned from outside the repository: the EIP-197
+GT.Exp.  What IS pinned from outside the repository: G1 Add and
+ScalarMultiplication by the EIP-196 precompile vectors (exact outputs), and the EIP-197
 pairing-check known-answer vector 'jeff1' of go-ethereum's bn256Pairing test set
 (tests/golden/eip197_pairing_check.json, tests/test_external_kat.py) holds -- it fixes
 the curve, the twist, the G2 generator, the group laws and the Miller loop + final

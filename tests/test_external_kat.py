@@ -66,3 +66,49 @@ def test_eip197_vector_gpu(engine):
         assert e.pairing_check2_fixed_g1_batch(Pb[:64], Pb[64:], Qb[:128], Qb[128:])[0]
     # 200 copies fill a CTA: the lockstep path
     assert engine.pairing_check_batch(np.tile(Pb, 200), np.tile(Qb, 200), 2).all()
+
+
+# ---- EIP-196 (alt_bn128 add / scalar-mul precompiles): exact affine outputs, so these pin G1 Add and
+# ScalarMultiplication byte for byte -----------------------------------------------------------------------------------
+def load196():
+    with open(os.path.join(HERE, "golden", "eip197_pairing_check.json")) as f:
+        v = json.load(f)["eip196"]
+    wm = [int(v["mul"]["input"][i:i + 64], 16) for i in range(0, 192, 64)]
+    em = [int(v["mul"]["expected"][i:i + 64], 16) for i in range(0, 128, 64)]
+    wa = [int(v["add"]["input"][i:i + 64], 16) for i in range(0, 256, 64)]
+    ea = [int(v["add"]["expected"][i:i + 64], 16) for i in range(0, 128, 64)]
+    return ((wm[0], wm[1]), wm[2], (em[0], em[1])), ((wa[0], wa[1]), (wa[2], wa[3]), (ea[0], ea[1]))
+
+
+def g1b(p):
+    return np.frombuffer(o.g1_to_bytes(p), dtype=np.uint8).copy()
+
+
+def test_eip196_vectors_oracles():
+    (P, k, R), (A, B, S) = load196()
+    assert o.g1_on_curve(P) and o.g1_mul(P, k) == R and o.g1_add(A, B) == S
+    kb = np.frombuffer(o.scalar_to_bytes(k), dtype=np.uint8)
+    assert port.g1_mul_batch(g1b(P), kb, 1).tobytes() == o.g1_to_bytes(R)
+    assert port.g1_add_batch(g1b(A), g1b(B), 1).tobytes() == o.g1_to_bytes(S)
+
+
+def test_eip196_vectors_device_code_on_host(emu):  # noqa: F811
+    (P, k, R), (A, B, S) = load196()
+    kb = np.frombuffer(o.scalar_to_bytes(k), dtype=np.uint8).copy()
+    out = np.zeros(64, dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    pb, ab, bb = g1b(P), g1b(A), g1b(B)
+    emu.emu_g1_mul(vp(pb), ctypes.c_size_t(1), vp(kb), ctypes.c_size_t(1), vp(out))
+    assert out.tobytes() == o.g1_to_bytes(R)
+    emu.emu_g1_add(vp(ab), vp(bb), ctypes.c_size_t(1), vp(out))
+    assert out.tobytes() == o.g1_to_bytes(S)
+
+
+@pytest.mark.gpu
+def test_eip196_vectors_gpu(engine):
+    (P, k, R), (A, B, S) = load196()
+    kb = np.frombuffer(o.scalar_to_bytes(k), dtype=np.uint8).copy()
+    assert engine.g1_mul_batch(g1b(P), kb).tobytes() == o.g1_to_bytes(R)
+    assert engine.g1_add_batch(g1b(A), g1b(B)).tobytes() == o.g1_to_bytes(S)
+    n = 5000  # >= 4096 scalars on one base: the fixed-base window-table path
+    assert (engine.g1_mul_base_batch(g1b(P), np.tile(kb, n)) == np.frombuffer(o.g1_to_bytes(R), dtype=np.uint8)).all()
