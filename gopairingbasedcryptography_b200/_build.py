@@ -15,7 +15,6 @@ NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "": DEFAULT,
     "nolockstep": NOLS,
-    "regs128": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=4"],
     "blk96": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=4", "-DBN254_BLOCK=96"],
     "blk192": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=2", "-DBN254_BLOCK=192"],
     "blk64": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=6", "-DBN254_BLOCK=64"],

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul(const v
 // fixed base: 32 windowed mixed additions from a precomputed affine table (L2-resident, 0.5-1 MB)
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A* table, const void* scalars, size_t n, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A*
 }
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_aff_add(const void* a, const void* b, size_t n, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   A x, y, r; load_struct(x, a, i); load_struct(y, b, i);
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_aff_add(const void
 // (the reference pays one inversion per Add).
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum(const A* U, int m, const uint8_t* sel, size_t n, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   extern __shared__ uint4 su_raw[];
   A* su = reinterpret_cast<A*>(su_raw);
   {
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum(const A
 // out[g] = sum of the `len` consecutive points of group g, processed as ceil(len/32)-way partial sums per pass
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const void* pts, size_t groups, int len, int chunk, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   int nch = (len + chunk - 1) / chunk;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= groups * (size_t)nch) return;
@@ -421,6 +425,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void*
 template <int G>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_hash_to_curve(const uint8_t* msgs, const uint64_t* off, size_t n, const uint8_t* dst,
                                                                            uint32_t dst_len, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* m = msgs + off[i];
