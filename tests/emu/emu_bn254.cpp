@@ -150,3 +150,5 @@ extern "C" void emu_hash_to_g2(const unsigned char* msg, size_t len, const unsig
   G2Aff r; hash_to_g2(r, msg, len, dst, (uint32_t)dst_len); st(out, 0, r); }
 extern "C" void emu_hash_to_field(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
   Fp u[4]; hash_to_field<4>(u, msg, len, dst, (uint32_t)dst_len); for (int i = 0; i < 4; i++) st(out, i, u[i]); }
+
+extern "C" void emu_fp2_mul_xi(const void* a, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp2_mul_xi_i(ld<Fp2>(a, i))); }

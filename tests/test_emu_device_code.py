@@ -245,3 +245,18 @@ def test_precomputed_g2_lines(emu):
     emu.emu_multi_pair_lines(vp(P), vp(Q), sz(n), sz(m), vp(out))
     ref = port.multi_pair_batch(P, np.tile(Q, n), n, m)
     assert (out == ref).all()
+
+
+def test_xi_multiplication_fast_path(emu):
+    """(9+u) * a through the shift / small-quotient reduction (tower.cuh fp_mul9_add) against the oracle: random values
+    and the boundary cases of the quotient estimate (components 0, 1, p-1, p-2, values around k*p/9)."""
+    rng = o.SplitMix64(404)
+    vals = [0, 1, 2, o.P - 1, o.P - 2, o.P // 2, o.P // 9, o.P // 9 + 1, 2 * o.P // 9, (o.P - 1) // 3, 8 * o.P // 9 + 1]
+    pairs = [(x, y) for x in vals for y in vals] + [(rng.fp(), rng.fp()) for _ in range(4000)]
+    n = len(pairs)
+    a = np.frombuffer(b"".join(o.fp_to_mont_bytes(x) + o.fp_to_mont_bytes(y) for x, y in pairs), dtype=np.uint8).copy()
+    z = np.zeros(64 * n, dtype=np.uint8)
+    emu.emu_fp2_mul_xi(vp(a), sz(n), vp(z))
+    for i, (x, y) in enumerate(pairs):
+        e = o.fp2_mul_xi((x, y))
+        assert z[64 * i:64 * i + 64].tobytes() == o.fp_to_mont_bytes(e[0]) + o.fp_to_mont_bytes(e[1]), (x, y)
