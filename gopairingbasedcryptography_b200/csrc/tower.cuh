@@ -72,18 +72,10 @@ BN_HD Fp2 fp2_mul_fp_i(const Fp2& a, const Fp& k) { Fp2 z; z.a0 = FP_MUL(a.a0, k
 // subtracted and one conditional subtraction finishes.  ~70 instructions instead of ~125 for three reduced
 // doublings and two reduced additions; the 8 multiplies by q run while the multiply pipe is otherwise idle
 // (xi sits in the add-type phase of the leaves).
-BN_HD uint32_t bn_shl3(uint32_t lo, uint32_t hi) { return (hi << 3) | (lo >> 29); }
-BN_HD Fp fp_mul9_add(const Fp& x, const uint32_t* y) {
-  uint32_t v[9];
-  v[0] = add_cc(x.l[0] << 3, x.l[0]);
-#pragma unroll
-  for (int i = 1; i < 8; i++) v[i] = addc_cc(bn_shl3(x.l[i - 1], x.l[i]), x.l[i]);
-  v[8] = addc(x.l[7] >> 29, 0u);
-  v[0] = add_cc(v[0], y[0]);
-#pragma unroll
-  for (int i = 1; i < 8; i++) v[i] = addc_cc(v[i], y[i]);
-  v[8] = addc(v[8], 0u);
-  uint32_t q = ((((v[8] << 11) | (v[7] >> 21)) * 43336u) >> 24);  // floor(v / 2^245) * floor(2^269 / p) >> 24
+// v (9 limbs, 0 <= v < 64p) -> v mod p, canonical: quotient estimate from the top bits, one multiple of p subtracted,
+// one conditional subtraction.
+BN_HD Fp fp_reduce_small(const uint32_t* v) {
+  uint32_t q = ((((v[8] << 11) | (v[7] >> 21)) * 43336u) >> 24);  // floor(v / 2^245) * floor(2^269 / p) >> 24: q or q - 1
   uint32_t qp[9];
   uint64_t c = 0;
 #pragma unroll
@@ -96,6 +88,19 @@ BN_HD Fp fp_mul9_add(const Fp& x, const uint32_t* y) {
   (void)subc(v[8], qp[8]);  // the ninth limb of v - q p is zero: the difference is below 2p
   fp_reduce_once(w);
   return w;
+}
+BN_HD uint32_t bn_shl3(uint32_t lo, uint32_t hi) { return (hi << 3) | (lo >> 29); }
+BN_HD Fp fp_mul9_add(const Fp& x, const uint32_t* y) {
+  uint32_t v[9];
+  v[0] = add_cc(x.l[0] << 3, x.l[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) v[i] = addc_cc(bn_shl3(x.l[i - 1], x.l[i]), x.l[i]);
+  v[8] = addc(x.l[7] >> 29, 0u);
+  v[0] = add_cc(v[0], y[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) v[i] = addc_cc(v[i], y[i]);
+  v[8] = addc(v[8], 0u);
+  return fp_reduce_small(v);
 }
 // (9+u)(a0 + a1 u) = (9a0 - a1) + (a0 + 9a1) u
 BN_HD Fp2 fp2_mul_xi_i(const Fp2& a) {
