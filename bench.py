@@ -32,9 +32,9 @@ UNIT = "pairings/s"
 MACS_PER_PAIRING = 2.081e6  # SURVEY.md §8d Model-M: 15300 Fp-mul equivalents x 136 limb-MACs
 BYTES_PER_PAIRING = 64 + 128 + 384
 # dram__bytes_read.sum + dram__bytes_write.sum of k_pair from the committed ncu --set full capture
-# (profiles/r1/ncu_k_pair_staged_lockstep_lazy_summary.txt: 3.31 + 20.91 GB for 2^18 pairings): what is left of the
+# (profiles/r1/ncu_k_pair_final_r1_summary.txt: 3.46 + 21.17 GB for 2^18 pairings): what is left of the
 # local-memory stack traffic after the staged tower (was 188.5 GB / 2^18 before it), still ~160x the algorithmic 576 B.
-NCU_DRAM_BYTES_PER_PAIRING = (3.313627e9 + 20.909593e9) / (1 << 18)
+NCU_DRAM_BYTES_PER_PAIRING = (3.463922e9 + 21.169908e9) / (1 << 18)
 
 
 def host_threads():
