@@ -166,7 +166,7 @@ def main():
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            os.environ.pop("NCCL_DEBUG", None)  # VERSION / WARN print NCCL's banner on stdout; rank 0 prints ONE JSON line
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
