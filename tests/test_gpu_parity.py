@@ -65,6 +65,15 @@ def test_pair_batch_vs_oracle(engine):
     assert out[0].tobytes() == one and out[1].tobytes() == one and out[2].tobytes() == one
 
 
+def test_pair_batch_vs_oracle_20k(engine):
+    """A larger bit-exact sweep of the throughput kernels (lockstep CTAs, many distinct operands) against the C port."""
+    n = 20000 + 37
+    P, Q, _, _ = common.points(n, seed=4321, threads=16)
+    assert (engine.pair_batch(P, Q).reshape(-1) == port.pair_batch(P, Q, n, 16)).all()
+    ml = engine.miller_loop_batch(P, Q, 1)
+    assert (engine.final_exp_batch(ml).reshape(-1) == port.pair_batch(P, Q, n, 16)).all()
+
+
 def test_single_element_and_errors(engine):
     P, Q, _, _ = common.points(1, seed=99)
     assert (engine.pair_batch(P, Q).reshape(-1) == port.pair_batch(P, Q, 1)).all()
