@@ -99,8 +99,13 @@ class Engine:
             raise ValueError("invalid inputs sizes")
         raise EngineError("%s: %s" % (_ERRORS.get(rc, rc), self._lib.bn254_last_error(self._h).decode()))
 
-    def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8, pre_sizes=None, mid_sizes=None):
-        out = np.empty(n * out_bytes, dtype=np.uint8)
+    def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8, pre_sizes=None, mid_sizes=None, out=None):
+        if out is None:
+            out = np.empty(n * out_bytes, dtype=np.uint8)
+        else:  # caller-owned result buffer (page-locked memory is filled by direct device->host copies)
+            out = out.reshape(-1).view(np.uint8)
+            if out.size != n * out_bytes or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("invalid inputs sizes")
         fn = getattr(self._lib, name)
         if pre_sizes is not None:  # (ctx, buf0, size..., buf1, size..., out) argument order
             args = [self._h, bufs[0].ctypes.data_as(ctypes.c_void_p)] + [ctypes.c_size_t(s) for s in pre_sizes]
@@ -113,13 +118,14 @@ class Engine:
         return out
 
     # ---- pairings -------------------------------------------------------------------------
-    def pair_batch(self, P, Q):
-        """n independent pairings e(P[i], Q[i]) -> (n, 384)."""
+    def pair_batch(self, P, Q, out=None):
+        """n independent pairings e(P[i], Q[i]) -> (n, 384).  out: optional caller-owned (n, 384) uint8 buffer; with
+        P, Q and out in page-locked memory the library copies to / from the device directly (no staging memcpy)."""
         P, Q = _u8(P, G1_BYTES, "P"), _u8(Q, G2_BYTES, "Q")
         n = P.size // G1_BYTES
         if n != Q.size // G2_BYTES:
             raise ValueError("invalid inputs sizes")
-        return self._call("bn254_pair_batch", [P, Q], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+        return self._call("bn254_pair_batch", [P, Q], [n], GT_BYTES, n, out=out).reshape(n, GT_BYTES)
 
     def _kpairs(self, name, P, Q, k, out_bytes):
         P, Q = _u8(P, G1_BYTES, "P"), _u8(Q, G2_BYTES, "Q")

@@ -636,10 +636,20 @@ int run_host_n(bn254_ctx* ctx, const Operand* in, int nin, void* out, size_t out
   CU(cudaSetDevice(ctx->device));
   size_t chunk = std::min<size_t>({n, kMaxChunkItems, (ctx->slot_bytes - fixed) / per});
   if (chunk == 0) return fail(ctx, BN254_ERR_BAD_ARG, "element too large for staging");
+  // Caller buffers in page-locked memory (bn254_host_alloc, cudaHostRegister, torch pin_memory ...) are copied to /
+  // from the device directly, chunk by chunk, on the slot's stream; pageable ones go through the pinned staging area.
+  auto page_locked = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  bool in_pinned[3] = {false, false, false};
+  for (int k = 0; k < nin; k++) in_pinned[k] = in[k].item_bytes && !in[k].broadcast && page_locked(in[k].ptr);
+  const bool out_pinned = page_locked(out);
   auto finish = [&](Slot& s) -> int {
     if (!s.busy) return BN254_OK;
     CU(cudaStreamSynchronize(s.stream));
-    memcpy(s.user_out, s.h + s.out_off, s.out_bytes);
+    if (s.out_bytes) memcpy(s.user_out, s.h + s.out_off, s.out_bytes);
     s.busy = false;
     return BN254_OK;
   };
@@ -656,17 +666,19 @@ int run_host_n(bn254_ctx* ctx, const Operand* in, int nin, void* out, size_t out
       d_in[k] = s.d + off;
       if (!in[k].item_bytes) continue;
       size_t l = in[k].broadcast ? in[k].item_bytes : in[k].item_bytes * c;
-      memcpy(s.h + off, static_cast<const char*>(in[k].ptr) + (in[k].broadcast ? 0 : done * in[k].item_bytes), l);
+      const char* src = static_cast<const char*>(in[k].ptr) + (in[k].broadcast ? 0 : done * in[k].item_bytes);
+      if (in_pinned[k]) CU(cudaMemcpyAsync(s.d + off, src, l, cudaMemcpyHostToDevice, s.stream));
+      else { memcpy(s.h + off, src, l); CU(cudaMemcpyAsync(s.d + off, s.h + off, l, cudaMemcpyHostToDevice, s.stream)); }
       off = (off + l + 255) & ~size_t(255);
     }
     size_t oo = off, lo = out_item * c;
-    CU(cudaMemcpyAsync(s.d, s.h, oo, cudaMemcpyHostToDevice, s.stream));
     launch(d_in, c, s.d + oo, s.stream, s.vm_cold);
     ctx->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(s.h + oo, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream));
     s.user_out = static_cast<char*>(out) + done * out_item;
-    s.out_off = oo; s.out_bytes = lo; s.busy = true;
+    if (out_pinned) { CU(cudaMemcpyAsync(s.user_out, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream)); s.out_bytes = 0; }
+    else { CU(cudaMemcpyAsync(s.h + oo, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream)); s.out_bytes = lo; }
+    s.out_off = oo; s.busy = true;
     done += c; ci++;
   }
   for (int i = 0; i < 2; i++) { int rc = finish(ctx->slot[(ci + i) & 1]); if (rc) return rc; }

@@ -785,3 +785,24 @@ def test_fixed_g1_pairing_check(engine):
     assert (engine.pairing_check2_fixed_g1_batch(pk, ng1, hm2, sig) == ref).all()
     assert (bn254.default_engine().pairing_check2_fixed_g1_batch(pk, ng1, hm2, sig) == ref).all()
     assert engine.pairing_check2_fixed_g1_batch(pk, ng1, b"", b"").shape == (0,)
+
+
+def test_page_locked_caller_buffers(engine):
+    """Caller buffers in page-locked memory take the direct-copy path of the host API (no staging memcpy); pageable and
+    page-locked operands may be mixed and must give the same bytes."""
+    import torch
+
+    n = 3000
+    P, Q, _, _ = common.points(n, seed=77, threads=8)
+    ref = engine.pair_batch(P, Q)
+    hP = torch.from_numpy(P.copy()).pin_memory().numpy()
+    hQ = torch.from_numpy(Q.copy()).pin_memory().numpy()
+    out = torch.empty((n, 384), dtype=torch.uint8).pin_memory().numpy()
+    got = engine.pair_batch(hP, hQ, out=out)
+    assert (got == ref).all() and (out == ref).all()
+    assert (engine.pair_batch(hP, Q) == ref).all()           # mixed: pinned P, pageable Q, pageable result
+    out2 = np.empty((n, 384), dtype=np.uint8)
+    engine.pair_batch(P, hQ, out=out2)                          # pageable caller-owned result
+    assert (out2 == ref).all()
+    with pytest.raises(ValueError):
+        engine.pair_batch(P, Q, out=np.empty((n - 1, 384), dtype=np.uint8))
