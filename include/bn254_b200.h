@@ -18,8 +18,9 @@
  *                                   reference does with x.BigInt(new(big.Int)).
  * Arrays are contiguous AoS.  "_dev" variants take device pointers already resident in HBM and a
  * cudaStream_t (as void*), enqueue asynchronously and do not synchronize; the others take host
- * pointers (pageable or pinned), copy through per-context pinned staging on the context's streams
- * and return when the results are in `out`.
+ * pointers and return when the results are in `out`: buffers in page-locked memory (bn254_host_alloc,
+ * cudaHostRegister) are copied to / from the device directly, chunk by chunk on the context's two
+ * streams; pageable buffers go through the context's pinned staging area.
  *
  * Return value: 0 on success, negative BN254_ERR_* otherwise.  Thread-safety: a context is
  * internally locked; use one context per GPU (or several per GPU for concurrency).
