@@ -29,4 +29,13 @@ assert (eng.gt_div_batch(gt, np.roll(gt, 1, axis=0)).reshape(-1) == port.gt_div_
 sel = np.arange(32 * 3, dtype=np.uint8).reshape(3, 32)
 eng.g2_subset_sum_batch(np.tile(Q[:128], 257), sel)
 eng.g1_sum_batch(P, 11)
+from oracle import bn254_ref as o  # noqa: E402
+from oracle import hash_to_curve_ref as h2c  # noqa: E402
+msgs = [b"", b"abc", b"x" * 150]
+hm = eng.hash_to_g2_batch(msgs, h2c.DST_BYTES_G2)
+assert hm[1].tobytes() == o.g2_to_bytes(h2c.hash_to_g2(b"abc", h2c.DST_BYTES_G2))
+h1 = eng.hash_to_g1_batch(msgs, h2c.DST_BYTES_G1)
+assert h1[2].tobytes() == o.g1_to_bytes(h2c.hash_to_g1(b"x" * 150, h2c.DST_BYTES_G1))
+eng.pairing_check2_fixed_g1_batch(P[:64], P[64:128], Q[:128 * n], Q[128 * n:])
+eng.pairing_check_batch(P, Q, 2)
 print("sanitizer smoke ok, impl =", os.environ.get("BN254_IMPL", "thread"))

@@ -106,6 +106,14 @@ def test_gpu_hash_to_curve_vs_oracle(engine, vectors):
     for i in (0, 1, 7, 64, 127, 128, 149):
         assert g1[i].tobytes() == o.g1_to_bytes(h.hash_to_g1(msgs[i], h.DST_BYTES_G1))
         assert g2[i].tobytes() == o.g2_to_bytes(h.hash_to_g2(msgs[i], h.DST_BYTES_G2))
+    # SHA-256 padding boundaries of the b_0 block (64-byte Z_pad + msg + 3 + DST'), long messages, longest DST
+    edge = [bytes((7 * i + j) & 0xFF for j in range(ln)) for i, ln in enumerate((54, 55, 56, 63, 64, 65, 119, 120, 1000, 5000))]
+    for dst in (b"D", b"d" * 255):
+        e1 = engine.hash_to_g1_batch(edge, dst)
+        e2 = engine.hash_to_g2_batch(edge, dst)
+        for i in range(len(edge)):
+            assert e1[i].tobytes() == o.g1_to_bytes(h.hash_to_g1(edge[i], dst))
+            assert e2[i].tobytes() == o.g2_to_bytes(h.hash_to_g2(edge[i], dst))
     assert engine.hash_to_g2_batch([], b"x").shape == (0, 128)
     from gopairingbasedcryptography_b200.bn254 import EngineError
     with pytest.raises(EngineError):
