@@ -296,13 +296,25 @@ class Engine:
 
     # ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2; hash/hash_to.go in the reference) ----
     def _hash_to_curve(self, name, msgs, dst, out_bytes):
-        msgs = [bytes(m) for m in msgs]
+        """msgs: a sequence of bytes-like messages, or a pair (blob, offsets) — the concatenated messages as uint8 and
+        n + 1 uint64 offsets — which is what the C ABI takes and skips the per-message Python work."""
         dst = bytes(dst)
-        n = len(msgs)
-        off = np.zeros(n + 1, dtype=np.uint64)
-        if n:
-            off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
-        blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
+        if isinstance(msgs, tuple) and len(msgs) == 2 and isinstance(msgs[1], np.ndarray):
+            blob = np.ascontiguousarray(msgs[0], dtype=np.uint8).reshape(-1)
+            off = np.ascontiguousarray(msgs[1], dtype=np.uint64).reshape(-1)
+            n = off.size - 1
+            if n < 0 or (np.diff(off.astype(np.int64)) < 0).any() or (n >= 0 and int(off[-1]) > blob.size):
+                raise ValueError("invalid message offsets")
+            if blob.size == 0:
+                blob = np.zeros(1, dtype=np.uint8)
+        else:
+            if not isinstance(msgs, (list, tuple)):
+                msgs = list(msgs)
+            n = len(msgs)
+            off = np.zeros(n + 1, dtype=np.uint64)
+            if n:
+                np.cumsum(np.fromiter(map(len, msgs), dtype=np.uint64, count=n), out=off[1:])
+            blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
         d = np.frombuffer(dst or b"\0", dtype=np.uint8)
         out = np.empty(n * out_bytes, dtype=np.uint8)
         fn = getattr(self._lib, name)

@@ -861,17 +861,29 @@ int hash_to_curve_host(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offs
   const size_t out_item = G == 1 ? BN254_G1_BYTES : BN254_G2_BYTES;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  Slot& s = ctx->slot[0];
+  // Two slots in flight: chunk i's kernel runs while chunk i-1's points are copied back and handed to the caller.
+  // Chunks are capped so that a large batch splits into >= 4 of them (a whole wave of CTAs each at the least).
+  const size_t cap = std::min<size_t>(kMaxChunkItems, std::max<size_t>((n + 3) / 4, 148 * 3 * kBlock));
+  struct Pending { size_t done = 0, c = 0, o_out = 0; bool live = false; } pend[2];
+  auto drain = [&](int i) -> int {
+    if (!pend[i].live) return BN254_OK;
+    CU(cudaStreamSynchronize(ctx->slot[i].stream));
+    memcpy(static_cast<char*>(out) + pend[i].done * out_item, ctx->slot[i].h + pend[i].o_out, out_item * pend[i].c);
+    pend[i].live = false;
+    return BN254_OK;
+  };
   size_t done = 0;
-  while (done < n) {
+  for (int it = 0; done < n; it ^= 1) {
+    if (int rc = drain(it)) return rc;
+    Slot& s = ctx->slot[it];
     // largest c with  256 (dst) + 8 (c + 1) + bytes + out_item * c  <=  slot
     size_t c = 0, bytes = 0;
-    while (done + c < n && c < kMaxChunkItems) {
+    while (done + c < n && c < cap) {
       size_t len = (size_t)(offsets[done + c + 1] - offsets[done + c]);
       if (512 + 8 * (c + 2) + bytes + len + out_item * (c + 1) + 512 > ctx->slot_bytes) break;
       bytes += len; c++;
     }
-    if (c == 0) return fail(ctx, BN254_ERR_BAD_ARG, "message too large for staging");
+    if (c == 0) { drain(it ^ 1); return fail(ctx, BN254_ERR_BAD_ARG, "message too large for staging"); }
     unsigned char* h = reinterpret_cast<unsigned char*>(s.h);
     memset(h, 0, 256);
     if (dst_len) memcpy(h, dst, dst_len);
@@ -887,10 +899,11 @@ int hash_to_curve_host(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offs
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h + o_out, s.d + o_out, out_item * c, cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
-    memcpy(static_cast<char*>(out) + done * out_item, s.h + o_out, out_item * c);
+    pend[it].done = done; pend[it].c = c; pend[it].o_out = o_out; pend[it].live = true;
     done += c;
   }
+  if (int rc = drain(0)) return rc;
+  if (int rc = drain(1)) return rc;
   return BN254_OK;
 }
 

@@ -114,6 +114,16 @@ def test_gpu_hash_to_curve_vs_oracle(engine, vectors):
         for i in range(len(edge)):
             assert e1[i].tobytes() == o.g1_to_bytes(h.hash_to_g1(edge[i], dst))
             assert e2[i].tobytes() == o.g2_to_bytes(h.hash_to_g2(edge[i], dst))
+    # (blob, offsets) form of the same call; enough messages for several pipelined chunks
+    many = [b"%06d" % i * (i % 5) for i in range(300000)]
+    blob = np.frombuffer(b"".join(many), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum([len(m) for m in many])]).astype(np.uint64)
+    big = engine.hash_to_g1_batch((blob, offs), b"D")
+    assert (big == engine.hash_to_g1_batch(many, b"D")).all()
+    for i in (0, 1, 4, 147455, 150000, 299999):
+        assert big[i].tobytes() == o.g1_to_bytes(h.hash_to_g1(many[i], b"D"))
+    with pytest.raises(ValueError):
+        engine.hash_to_g1_batch((blob[:10], offs), b"D")
     assert engine.hash_to_g2_batch([], b"x").shape == (0, 128)
     from gopairingbasedcryptography_b200.bn254 import EngineError
     with pytest.raises(EngineError):
