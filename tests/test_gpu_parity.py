@@ -806,3 +806,38 @@ def test_page_locked_caller_buffers(engine):
     assert (out2 == ref).all()
     with pytest.raises(ValueError):
         engine.pair_batch(P, Q, out=np.empty((n - 1, 384), dtype=np.uint8))
+
+
+def test_concurrent_callers(engine):
+    """Host threads sharing one context serialise on its lock, and two contexts on one GPU run side by side (two Go
+    goroutines calling into the library): every call returns the bytes of the single-threaded call."""
+    import threading
+    from gopairingbasedcryptography_b200 import bn254
+
+    n = 2500
+    P, Q, _, _ = common.points(n, seed=78, threads=8)
+    sb = common.scalar_bytes(common.scalars(n, seed=79, edges=True))
+    ref_pair = engine.pair_batch(P, Q)
+    ref_mul = engine.g2_mul_batch(Q, sb)
+    ref_chk = engine.pairing_check_batch(P, Q, 2)
+    second = bn254.Engine(0)
+    errs = []
+
+    def worker(eng, kind):
+        try:
+            for _ in range(3):
+                if kind == 0:
+                    assert (eng.pair_batch(P, Q) == ref_pair).all()
+                elif kind == 1:
+                    assert (eng.g2_mul_batch(Q, sb) == ref_mul).all()
+                else:
+                    assert (eng.pairing_check_batch(P, Q, 2) == ref_chk).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ths = [threading.Thread(target=worker, args=(e, k)) for e in (engine, second) for k in (0, 1, 2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
