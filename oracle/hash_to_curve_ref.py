@@ -9,7 +9,11 @@ Shallue-van de Woestijne map (RFC 9380 section 6.6.1, straight-line version F.1)
 the two points added, and (G2 only) the cofactor cleared with gnark's endomorphism formula
     [x0]Q + psi([3 x0]Q) + psi^2([x0]Q) + psi^3(Q)      (Fuentes-Castaneda, Knapp, Rodriguez-Henriquez, section 6.1).
 
-PARITY UNPINNED against gnark (no Go toolchain, module absent, the reference holds no vectors for it).  What is pinned:
+G1: PINNED by gnark-crypto's own known answer (ecc/bn254/hash_vectors_test.go, HashToG1 of the empty message under
+"QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_"; tests/test_external_kat.py) -- expand_message_xmd, hash_to_field,
+the SVDW constants and sign choices and the final addition all enter that one point.
+G2: PARITY UNPINNED against gnark (no Go toolchain, module absent, the reference holds no vectors for it); it shares
+expand_message_xmd / hash_to_field / the SVDW straight-line program with the pinned G1 path.  Also pinned:
   * expand_message_xmd against the RFC 9380 appendix K.1 vectors (tests/test_hash_to_curve.py);
   * the G1 map constants: with Z = 1 the derived c2, c3, c4 equal the decimal constants of gnark's generator
     configuration for bn254 (`internal/generator/config/bn254.go`, HashE1) as recalled by the survey author

@@ -112,3 +112,30 @@ def test_eip196_vectors_gpu(engine):
     assert engine.g1_add_batch(g1b(A), g1b(B)).tobytes() == o.g1_to_bytes(S)
     n = 5000  # >= 4096 scalars on one base: the fixed-base window-table path
     assert (engine.g1_mul_base_batch(g1b(P), np.tile(kb, n)) == np.frombuffer(o.g1_to_bytes(R), dtype=np.uint8)).all()
+
+
+# ---- gnark-crypto's own HashToG1 known answer (ecc/bn254/hash_vectors_test.go): pins expand_message_xmd, hash_to_field
+# (L = 48), the SVDW constants and sign choice, and the G1 addition of the two mapped points, byte for byte ------------
+def load_h2c():
+    with open(os.path.join(HERE, "golden", "eip197_pairing_check.json")) as f:
+        v = json.load(f)["gnark_hash_to_g1"]
+    return v["msg"].encode(), v["dst"].encode(), (int(v["x"], 16), int(v["y"], 16))
+
+
+def test_gnark_hash_to_g1_vector_oracle_and_device_code_on_host(emu):  # noqa: F811
+    from oracle import hash_to_curve_ref as h2c
+
+    msg, dst, want = load_h2c()
+    assert o.g1_on_curve(want)
+    assert h2c.hash_to_g1(msg, dst) == want
+    out = (ctypes.c_uint8 * 64)()
+    emu.emu_hash_to_g1(msg, ctypes.c_size_t(len(msg)), dst, ctypes.c_size_t(len(dst)), out)
+    assert bytes(out) == o.g1_to_bytes(want)
+
+
+@pytest.mark.gpu
+def test_gnark_hash_to_g1_vector_gpu(engine):
+    msg, dst, want = load_h2c()
+    got = engine.hash_to_g1_batch([msg] * 130 + [b"x"], dst)  # a full CTA (lockstep) and a ragged one
+    assert (got[:130] == np.frombuffer(o.g1_to_bytes(want), dtype=np.uint8)).all()
+    assert got[130].tobytes() != o.g1_to_bytes(want)
