@@ -894,7 +894,8 @@ int hash_to_curve_host(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offs
     size_t o_out = (o_msg + bytes + 255) & ~size_t(255);
     CU(cudaMemcpyAsync(s.d, s.h, o_out, cudaMemcpyHostToDevice, s.stream));
     const uint8_t* d = reinterpret_cast<const uint8_t*>(s.d);
-    k_hash_to_curve<G><<<grid_for(c), kBlock, kTowerSmem, s.stream>>>(d + o_msg, reinterpret_cast<const uint64_t*>(d + 256), c, d, (uint32_t)dst_len,
+    // no tower scratch in this kernel: launched without dynamic shared memory, G1 (90 registers) runs 5 CTAs per SM
+    k_hash_to_curve<G><<<grid_for(c), kBlock, 0, s.stream>>>(d + o_msg, reinterpret_cast<const uint64_t*>(d + 256), c, d, (uint32_t)dst_len,
                                                                      s.d + o_out);
     ctx->launches++;
     CU(cudaGetLastError());
