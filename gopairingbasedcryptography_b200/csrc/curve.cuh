@@ -188,19 +188,27 @@ BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& be
   p2.x = f_mul_beta(base.x, beta); p2.y = base.y;
   if (n1) p1.y = f_neg(p1.y);
   if (n2) p2.y = f_neg(p2.y);
-  // table {P1, P2, P1+P2} in Jacobian form, indexed by the joint bit pair: every lane of a warp runs the SAME
-  // doubling + one Jacobian addition per bit (a data-dependent choice between three addition paths would make
-  // each warp execute all of them)
-  J tab[3];
-  tab[0].x = p1.x; tab[0].y = p1.y; f_set_one(tab[0].z);
-  tab[1].x = p2.x; tab[1].y = p2.y; f_set_one(tab[1].z);
-  jac_add_aff(tab[2], tab[0], p2);
+  // table {P1, P2, P1+P2} in AFFINE form, indexed by the joint bit pair: every lane of a warp runs the SAME
+  // doubling + one MIXED addition per bit (a data-dependent choice between addition paths would make each warp
+  // execute all of them).  Normalising P1+P2 costs one inversion (~300 Fp-mul) and makes all ~96 additions of the
+  // ladder mixed ones (G1: 11 instead of 16 Fp-mul each, G2: 30 instead of 44): -7 % / -18 % multiplications, and a
+  // third less table on the stack.
+  A tab[3];
+  tab[0] = p1; tab[1] = p2;
+  {
+    J t; t.x = p1.x; t.y = p1.y; f_set_one(t.z);
+    jac_add_aff(t, t, p2);
+    jac_to_aff(tab[2], t);  // (0, 0) if P1 + P2 is the point at infinity (only off the prime-order subgroup)
+  }
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
   for (int i = GLV_MAX_BITS - 1; i >= 0; i--) {
     BN_CTA_SYNC();  // every thread runs all GLV_MAX_BITS iterations: a full, infinity-free CTA stays in lockstep
     jac_dbl(acc, acc);
     int b = (int)((k1[i >> 5] >> (i & 31)) & 1u) | ((int)((k2[i >> 5] >> (i & 31)) & 1u) << 1);
-    if (b) jac_add(acc, acc, tab[b - 1]);
+    if (b) {
+      A e = tab[b - 1];
+      if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+    }
   }
   jac_to_aff(out, acc);
 }
