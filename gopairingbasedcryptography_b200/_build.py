@@ -19,6 +19,7 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
     "blk192": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=2", "-DBN254_BLOCK=192"],
     "blk64": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=6", "-DBN254_BLOCK=64"],
     "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
+    "ool_jac": DEFAULT + ["-DBN254_OOL_JAC"],
     "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],

@@ -44,12 +44,17 @@ BN_HD bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
 BN_HD void f_set_one(Fp2& a) { a = fp2_one(); }
 BN_HD void f_set_zero(Fp2& a) { a = fp2_zero(); }
 
+#ifdef BN254_OOL_JAC
+#define BN_JAC BN_NOINLINE
+#else
+#define BN_JAC BN_HD
+#endif
 template <typename J>
 BN_HD bool jac_is_inf(const J& p) { return f_is_zero(p.z); }
 
 // a = 0 doubling (dbl-2009-l)
 template <typename J>
-BN_HD void jac_dbl(J& r, const J& p) {
+BN_JAC void jac_dbl(J& r, const J& p) {
   if (jac_is_inf(p)) { r = p; return; }
   auto A = f_sqr(p.x), B = f_sqr(p.y), C = f_sqr(B);
   auto D = f_dbl(f_sub(f_sub(f_sqr(f_add(p.x, B)), A), C));
@@ -62,7 +67,7 @@ BN_HD void jac_dbl(J& r, const J& p) {
 }
 // mixed addition, q affine and finite; handles p = inf, p = q (doubling), p = -q (infinity)
 template <typename J, typename A>
-BN_HD void jac_add_aff(J& r, const J& p, const A& q) {
+BN_JAC void jac_add_aff(J& r, const J& p, const A& q) {
   if (jac_is_inf(p)) { r.x = q.x; r.y = q.y; f_set_one(r.z); return; }
   auto z2 = f_sqr(p.z);
   auto u2 = f_mul(q.x, z2);
