@@ -237,10 +237,11 @@ BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
 // E12.Exp shape): every lane of a warp multiplies at the same 128 positions, so the SIMT lanes never diverge on
 // the exponent bits -- a bit-serial or sliding-window ladder would make every warp pay for the union of its
 // lanes' multiplications.
-BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
+// tab: 4 Fp12 of table space private to the thread (see gt_cyclo_exp about where it should live)
+BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k, Fp12* tab) {
   // Control flow is identical for every thread (always two squarings and one product per window, the product by
   // tab[0] = 1 when the digit is 0), so a full CTA can run in lockstep; only the operand selection is per thread.
-  Fp12 tab[4];  // 1, x, x^2, x^3
+  // tab = 1, x, x^2, x^3
   fp12_set_one(tab[0]);
   tab[1] = x;
   fp12_sqr(tab[2], x);
@@ -260,7 +261,7 @@ BN_HD void gt_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
 // pairing outputs -- all GT.Exp call sites of the reference): Granger-Scott squarings, FIXED
 // 3-bit signed windows (digits -4..3, inverse = conjugate), table x..x^4: 258 cyclotomic squarings + <= 86
 // products at lane-uniform positions.
-BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
+BN_HD void gt_cyclo_exp_windowed(Fp12& out, const Fp12& x, const uint32_t* k) {
   Fp12 tab[4];  // x, x^2, x^3, x^4
   tab[0] = x;
   fp12_cyclo_sqr(tab[1], x);
@@ -293,6 +294,48 @@ BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k) {
     fp12_mul(acc, acc, m);
   }
   out = acc;
+}
+
+// GT.Exp for elements of GT proper (order r: pairing outputs and their products / quotients / powers) by the
+// 2-dimensional GLV decomposition of the exponent that the G1 / G2 ladders use: p^2 = -lambda (mod r), so
+// x^lambda = conj(frobenius^2(x)) costs 5 Fp2 x Fp products, and x^k = x^k1 * (x^lambda)^k2 with |k1|, |k2| < 2^129.
+// Joint FIXED 2-bit windows over the 16-entry table x^i * (x^lambda)^j: 130 cyclotomic squarings + 65 products at
+// lane-uniform positions + 11 products for the table, ~6.4 k Fp-mul instead of ~9.3 k for the 256-bit signed-window
+// ladder above (kept as -DBN254_GT_EXP_WINDOWED; it also serves cyclotomic elements outside GT).
+// tab: 16 Fp12 of caller-provided table space, private to the thread and CONTIGUOUS (the kernel hands out a slice of a
+// global scratch: a per-thread digit indexes the table, and on the local-memory stack -- interleaved word by word
+// across the lanes of a warp -- such a gather touches 32 sectors per word: ncu showed 22 GB of DRAM reads per wave and
+// the multiply pipe at 47 %; one contiguous 384-byte entry per lane moves 1/8 of that).
+BN_HD void gt_cyclo_exp(Fp12& out, const Fp12& x, const uint32_t* k, Fp12* tab) {
+#ifdef BN254_GT_EXP_WINDOWED
+  gt_cyclo_exp_windowed(out, x, k);
+#else
+  uint32_t k1[8], k2[8];
+  bool n1, n2;
+  glv_decompose(k, k1, n1, k2, n2);
+  // tab[4 j + i] = a^i b^j, a = x^(+-1), b = (x^lambda)^(+-1)
+  fp12_set_one(tab[0]);
+  if (n1) fp12_conj(tab[1], x); else tab[1] = x;
+  fp12_frob(tab[4], x, 2);                       // x^(-lambda)
+  if (!n2) fp12_conj(tab[4], tab[4]);
+  fp12_cyclo_sqr(tab[2], tab[1]);
+  fp12_mul(tab[3], tab[2], tab[1]);
+  fp12_cyclo_sqr(tab[8], tab[4]);
+  fp12_mul(tab[12], tab[8], tab[4]);
+  for (int j = 1; j < 4; j++)
+    for (int i = 1; i < 4; i++) fp12_mul(tab[4 * j + i], tab[4 * j], tab[i]);
+  constexpr int kWin = (GLV_MAX_BITS + 2) / 2;  // 2-bit windows covering bits 0 .. GLV_MAX_BITS
+  Fp12 acc;
+  fp12_set_one(acc);
+  for (int w = kWin - 1; w >= 0; w--) {
+    if (w != kWin - 1) fp12_cyclo_sqr_n(acc, acc, 2);
+    int bit = 2 * w;
+    int d = (int)((k1[bit >> 5] >> (bit & 31)) & 3u) | ((int)((k2[bit >> 5] >> (bit & 31)) & 3u) << 2);
+    Fp12 m = tab[d];
+    fp12_mul(acc, acc, m);
+  }
+  out = acc;
+#endif
 }
 
 }  // namespace bn254

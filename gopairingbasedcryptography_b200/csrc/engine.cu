@@ -360,8 +360,9 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const 
   jac_to_aff(r, acc);
   store_struct(out, t, r);
 }
+constexpr size_t kGtCycloTable = 16;  // Fp12 entries of per-thread table space gt_cyclo_exp needs
 template <int CYCLO>
-__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out) {
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void* x, size_t x_stride, const void* k, size_t n, void* out, Fp12* tabmem = nullptr) {
   cta_lockstep_set(cta_is_full(n));  // gt_exp / gt_cyclo_exp have thread-uniform control flow
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -371,7 +372,11 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_exp(const void*
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
   s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
   Fp12 r;
-  if (CYCLO) gt_cyclo_exp(r, b, s); else gt_exp(r, b, s);
+  if (CYCLO) gt_cyclo_exp(r, b, s, tabmem + i * kGtCycloTable);
+  else {
+    Fp12 loc[4];  // table on the stack when the launch has no scratch (device-pointer entry point, table builds)
+    gt_exp(r, b, s, tabmem ? tabmem + i * 4 : loc);
+  }
   store_struct(out, i, r);
 }
 // fixed-base GT exponentiation: out = prod_w table[w][byte_w(k)] -- 32 Fp12 products, no squarings.  The table
@@ -851,6 +856,22 @@ int ensure_fixed_table(bn254_ctx* ctx, int g, const void* base) {
 }  // namespace
 
 // n messages (concatenated bytes + n+1 offsets) -> points.  Chunks are sized to one staging slot.
+// GT exponentiation in launches of at most one full wave of CTAs, each thread with its own contiguous 4-entry
+// (generic) / 16-entry (cyclotomic) table slice in the slot's device scratch (6 KB per thread, <= 350 MB per slot, allocated on first use);
+// launches of one call are stream-ordered, so consecutive waves reuse the same slices.
+template <int CYCLO>
+static void launch_gt_exp(bn254_ctx* ctx, uint4* cold, const void* x, size_t stride, const void* k, size_t n, void* o, cudaStream_t s) {
+  Slot& sl = ctx->slot[cold == ctx->slot[1].vm_cold ? 1 : 0];
+  const size_t wave = (size_t)ctx->sms * BN254_MIN_BLOCKS * kBlock;
+  if (ensure_mp_scratch(sl, std::min(n, wave) * (CYCLO ? kGtCycloTable : 4) * sizeof(Fp12), s) != cudaSuccess) return;  // run_host reports cudaGetLastError()
+  for (size_t off = 0; off < n; off += wave) {
+    size_t c = std::min(wave, n - off);
+    k_gt_exp<CYCLO><<<grid_for(c), kBlock, kTowerSmem, s>>>(static_cast<const char*>(x) + off * stride * BN254_GT_BYTES, stride,
+                                                        static_cast<const char*>(k) + off * BN254_SCALAR_BYTES, c,
+                                                        static_cast<char*>(o) + off * BN254_GT_BYTES, static_cast<Fp12*>(sl.mp_scratch));
+  }
+}
+
 template <int G>
 int hash_to_curve_host(bn254_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out) {
   if (!ctx) return BN254_ERR_BAD_ARG;
@@ -1211,21 +1232,29 @@ int bn254_gt_exp_batch_dev(bn254_ctx* ctx, const void* d_x, size_t stride, const
 }
 int bn254_gt_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
+                  [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {
+                    // one wave or less: table in the slot scratch; larger chunks keep ONE launch with the table on the stack
+                    // (wave-sized launches in series measured 14 % slower here than the single launch)
+                    if (c <= (size_t)ctx->sms * BN254_MIN_BLOCKS * kBlock) launch_gt_exp<0>(ctx, cold, a, 1, b, c, o, s);
+                    else k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o);
+                  });
 }
 int bn254_gt_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   if (ctx && x1 && n >= kFixedMin) return gt_fixed_exp(ctx, x1, k, n, out);
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
+                  [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) {
+                    if (c <= (size_t)ctx->sms * BN254_MIN_BLOCKS * kBlock) launch_gt_exp<0>(ctx, cold, a, 0, b, c, o, s);
+                    else k_gt_exp<0><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o);
+                  });
 }
 int bn254_gt_cyclo_exp_batch(bn254_ctx* ctx, const void* x, const void* k, size_t n, void* out) {
   return run_host(ctx, {x, BN254_GT_BYTES, false}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 1, b, c, o); });
+                  [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) { launch_gt_exp<1>(ctx, cold, a, 1, b, c, o, s); });
 }
 int bn254_gt_cyclo_exp_base_batch(bn254_ctx* ctx, const void* x1, const void* k, size_t n, void* out) {
   if (ctx && x1 && n >= kFixedMin) return gt_fixed_exp(ctx, x1, k, n, out);
   return run_host(ctx, {x1, BN254_GT_BYTES, true}, {k, BN254_SCALAR_BYTES, false}, out, BN254_GT_BYTES, n,
-                  [](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4*) { k_gt_exp<1><<<grid_for(c), kBlock, kTowerSmem, s>>>(a, 0, b, c, o); });
+                  [ctx](const void* a, const void* b, size_t c, void* o, cudaStream_t s, uint4* cold) { launch_gt_exp<1>(ctx, cold, a, 0, b, c, o, s); });
 }
 int bn254_gt_mul_batch(bn254_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
   return run_host(ctx, {a, BN254_GT_BYTES, false}, {b, BN254_GT_BYTES, false}, out, BN254_GT_BYTES, n,

@@ -129,9 +129,11 @@ int bn254_g2_sum_batch(bn254_ctx*, const void* points, size_t groups, size_t len
 int bn254_gt_exp_batch(bn254_ctx*, const void* x, const void* k, size_t n, void* out);
 int bn254_gt_exp_base_batch(bn254_ctx*, const void* x1, const void* k, size_t n, void* out);
 int bn254_gt_exp_batch_dev(bn254_ctx*, const void* d_x, size_t x_stride_elems, const void* d_k, size_t n, void* d_out, void* stream);
-/* Same result as bn254_gt_exp_batch when x lies in the cyclotomic subgroup (any Pair output, or a product,
+/* Same result as bn254_gt_exp_batch when x lies in GT proper, the order-r subgroup (any Pair output, or a product,
  * quotient or power of Pair outputs -- every GT.Exp base in the reference's non-test code):
- * Granger-Scott squarings + signed windows, ~2.8x less work.  Undefined for other Fp12 elements. */
+ * 2-dimensional GLV split of the exponent (x^lambda = conj(frobenius^2 x)), Granger-Scott squarings, joint fixed
+ * windows: ~2.5x less work.  Undefined for other Fp12 elements (including cyclotomic elements of order not
+ * dividing r). */
 int bn254_gt_cyclo_exp_batch(bn254_ctx*, const void* x, const void* k, size_t n, void* out);
 int bn254_gt_cyclo_exp_base_batch(bn254_ctx*, const void* x1, const void* k, size_t n, void* out);
 /* (*GT).Mul / (*GT).Div  [access_tree_node.go:114,157; bsw07_cpabe.go:189-190] */

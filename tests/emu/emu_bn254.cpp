@@ -38,7 +38,7 @@ void emu_g2_mul(const void* base, size_t stride, const void* s, size_t n, void* 
 void emu_g1_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G1Aff r; aff_add<G1Jac, G1Aff>(r, ld<G1Aff>(a, i), ld<G1Aff>(b, i)); st(out, i, r); } }
 void emu_g2_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G2Aff r; aff_add<G2Jac, G2Aff>(r, ld<G2Aff>(a, i), ld<G2Aff>(b, i)); st(out, i, r); } }
 void emu_gt_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
-  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); gt_exp(r, b, k); st(out, i, r); } }
+  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); Fp12 tab[4]; gt_exp(r, b, k, tab); st(out, i, r); } }
 void emu_gt_mul(const void* a, const void* b, size_t n, int div, void* out) {
   for (size_t i = 0; i < n; i++) { Fp12 x = ld<Fp12>(a, i), y = ld<Fp12>(b, i); if (div) fp12_inv(y, y); fp12_mul(x, x, y); st(out, i, x); } }
 void emu_gt_sqr(const void* a, size_t n, int cyclo, void* out) {
@@ -117,7 +117,7 @@ void emu_g1_mul_fixed(const void* base1, const void* s, size_t n, void* out) {
   for (size_t i = 0; i < n; i++) { uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); G1Aff r; scalar_mul_fixed<G1Jac, G1Aff>(r, table, k); st(out, i, r); } }
 }
 extern "C" void emu_gt_cyclo_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
-  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); gt_cyclo_exp(r, b, k); st(out, i, r); } }
+  for (size_t i = 0; i < n; i++) { Fp12 b = ld<Fp12>(x, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); Fp12 tab[16]; gt_cyclo_exp(r, b, k, tab); st(out, i, r); } }
 // line tables: precompute for the m points of Q, then out[i] = FE(prod_j lines_j evaluated at P[i*m+j])
 extern "C" void emu_multi_pair_lines(const void* P, const void* Q, size_t n, size_t m, void* out) {
   Fp2* table = new Fp2[m * kLinesPerPoint * 3];
