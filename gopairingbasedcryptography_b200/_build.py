@@ -1,9 +1,14 @@
-"""Build libbn254_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libbn254_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+One translation unit per kernel family (csrc/k_*.cu) plus the host runtime (csrc/engine.cu), compiled in parallel and
+linked into one shared library.  Each family has its own compile flags: the register cap that is right for the
+pairing tower is not the one the group ladders want."""
 from __future__ import annotations
 
 import glob
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -12,31 +17,27 @@ CSRC = os.path.join(HERE, "csrc")
 # CTA lockstep barriers (the four warps of a CTA share instruction-cache lines).
 DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"]
 NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
-VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>
+UNITS = ["k_pairing", "k_group", "k_gt", "k_hash", "k_vm", "k_fr", "engine"]
+VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for every unit, or {unit: flags}
     "": DEFAULT,
     "nolockstep": NOLS,
-    "blk96": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=4", "-DBN254_BLOCK=96"],
-    "blk192": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=2", "-DBN254_BLOCK=192"],
-    "blk64": [f for f in DEFAULT if "MIN_BLOCKS" not in f] + ["-DBN254_MIN_BLOCKS=6", "-DBN254_BLOCK=64"],
     "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
     "ool_jac": DEFAULT + ["-DBN254_OOL_JAC"],
-    "inline_fpmul": [f for f in DEFAULT if f != "-DBN254_OOL_FPMUL"],
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
-    **{"k%dw%d" % (k, w): DEFAULT + ["-DBN254_VM_K=%d" % k, "-DBN254_VM_WARPS=%d" % w]
-       for k in (1, 2, 3, 4, 6) for w in (1, 2, 3, 4, 6, 8)},
 }
+# per-unit additions on top of the variant's flags
+UNIT_FLAGS = {}
 VARIANT = os.environ.get("BN254_VARIANT", "")
 LIB = os.path.join(HERE, "lib", "libbn254_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
-]
+OBJDIR = os.path.join(HERE, "lib", "obj" + ("_" + VARIANT if VARIANT else ""))
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-fvisibility=default"]
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
-                  glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "bn254_b200.h")])
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "bn254_b200.h"), os.path.abspath(__file__)])
 
 
 def is_stale():
@@ -46,13 +47,31 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+def unit_flags(unit):
+    v = VARIANTS[VARIANT]
+    flags = list(v.get(unit, v.get("*", DEFAULT)) if isinstance(v, dict) else v)
+    return flags + UNIT_FLAGS.get(unit, [])
+
+
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + VARIANTS[VARIANT] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")]
-    subprocess.check_call(cmd)
+
+    def compile_unit(unit):
+        obj = os.path.join(OBJDIR, unit + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + unit_flags(unit) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, unit + ".cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, r.stdout, r.stderr))
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_unit, UNITS))
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 
 

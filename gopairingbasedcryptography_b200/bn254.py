@@ -103,8 +103,10 @@ class Engine:
         if out is None:
             out = np.empty(n * out_bytes, dtype=np.uint8)
         else:  # caller-owned result buffer (page-locked memory is filled by direct device->host copies)
+            if not isinstance(out, np.ndarray) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+                raise ValueError("out must be a writable C-contiguous numpy array (a strided view would be copied, not filled)")
             out = out.reshape(-1).view(np.uint8)
-            if out.size != n * out_bytes or not out.flags["C_CONTIGUOUS"]:
+            if out.size != n * out_bytes:
                 raise ValueError("invalid inputs sizes")
         fn = getattr(self._lib, name)
         if pre_sizes is not None:  # (ctx, buf0, size..., buf1, size..., out) argument order
@@ -331,7 +333,126 @@ class Engine:
         """n x bn254.HashToG2(msg, dst) -> (n, 128) affine points."""
         return self._hash_to_curve("bn254_hash_to_g2_batch", msgs, dst, G2_BYTES)
 
+
+    # ---- explicit table handles ------------------------------------------------------------
+    def fixed_base_create(self, group, base):
+        """Immutable 32 x 255 window table of ONE base: group 1 = G1, 2 = G2, 3 = GT (bn254_fixed_base_create)."""
+        item = {1: G1_BYTES, 2: G2_BYTES, 3: GT_BYTES}[int(group)]
+        base = _u8(base, item, "base")
+        if base.size != item:
+            raise ValueError("invalid inputs sizes")
+        h = ctypes.c_void_p()
+        fn = self._lib.bn254_fixed_base_create
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, ctypes.c_int(int(group)), base.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
+        return FixedBase(self, h, int(group))
+
+    def _fixed(self, name, table, scalars, item, group):
+        if table.engine is not self or table.group != group:
+            raise ValueError("fixed-base handle of another engine or group")
+        scalars = _u8(scalars, SCALAR_BYTES, "scalars")
+        n = scalars.size // SCALAR_BYTES
+        out = np.empty(n * item, dtype=np.uint8)
+        fn = getattr(self._lib, name)
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, table.handle, scalars.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(n, item)
+
+    def g1_fixed_mul_batch(self, table, scalars):
+        return self._fixed("bn254_g1_fixed_mul_batch", table, scalars, G1_BYTES, 1)
+
+    def g2_fixed_mul_batch(self, table, scalars):
+        return self._fixed("bn254_g2_fixed_mul_batch", table, scalars, G2_BYTES, 2)
+
+    def gt_fixed_exp_batch(self, table, k):
+        return self._fixed("bn254_gt_fixed_exp_batch", table, k, GT_BYTES, 3)
+
+    def msm_table_create(self, group, points):
+        """Per-point byte-window tables of `len` shared points (bn254_msm_table_create): group 1 = G1, 2 = G2."""
+        item = {1: G1_BYTES, 2: G2_BYTES}[int(group)]
+        points = _u8(points, item, "points")
+        n = points.size // item
+        h = ctypes.c_void_p()
+        fn = self._lib.bn254_msm_table_create
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, ctypes.c_int(int(group)), points.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.byref(h)))
+        return MsmTable(self, h, int(group), n)
+
+    def msm_batch(self, table, scalars):
+        """out[v] = sum_j [scalars[v, j]] P_j over the table's points: scalars (nvec, len, 32) -> (nvec, 64 | 128)."""
+        if table.engine is not self:
+            raise ValueError("MSM table of another engine")
+        scalars = _u8(scalars, SCALAR_BYTES * table.len, "scalars")
+        nvec = scalars.size // (SCALAR_BYTES * table.len)
+        item = G1_BYTES if table.group == 1 else G2_BYTES
+        out = np.empty(nvec * item, dtype=np.uint8)
+        fn = self._lib.bn254_msm_batch
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, table.handle, scalars.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(nvec), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(nvec, item)
+
+    # ---- Fr feeders (fr.Element = 32 B Montgomery, gnark layout) ------------------------------
+    def fr_poly_from_roots(self, roots):
+        """Coefficients c_0..c_n (fr.Element) of prod (X - root_i) (afp25_bibe_utils.go:14-43 computePolynomialCoeffs)."""
+        roots = _u8(roots, 32, "roots")
+        n = roots.size // 32
+        out = np.empty((n + 1) * 32, dtype=np.uint8)
+        fn = self._lib.bn254_fr_poly_from_roots
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, roots.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(n + 1, 32)
+
+    def fr_quotient_coeffs(self, f, ids):
+        """For every id the n coefficients of f(X) / (X - id), as regular-form scalars (nvec, n, 32)."""
+        f, ids = _u8(f, 32, "f"), _u8(ids, 32, "ids")
+        n, nvec = f.size // 32 - 1, ids.size // 32
+        if n <= 0:
+            raise ValueError("invalid inputs sizes")
+        out = np.empty(nvec * n * 32, dtype=np.uint8)
+        fn = self._lib.bn254_fr_quotient_coeffs
+        fn.restype = ctypes.c_int
+        self._check(fn(self._h, f.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ids.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(nvec),
+                       out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(nvec, n, 32)
+
     # ---- device-resident entry points (pointers are ints, e.g. torch.Tensor.data_ptr()) ----
+    # kinds: p = device pointer, z = size_t, h = table handle object, b = host bytes (pointer + length)
+    _DEV_SIGS = {
+        "pair_batch_dev": "ppzp", "multi_pair_batch_dev": "ppzzp", "pairing_check_batch_dev": "ppzzp", "miller_loop_batch_dev": "ppzzp",
+        "final_exp_batch_dev": "pzp", "multi_pair_lines_batch_dev": "phzp", "g1_mul_batch_dev": "pzpzp", "g2_mul_batch_dev": "pzpzp",
+        "g1_fixed_mul_batch_dev": "hpzp", "g2_fixed_mul_batch_dev": "hpzp", "gt_fixed_exp_batch_dev": "hpzp", "msm_batch_dev": "hpzp",
+        "g1_add_batch_dev": "ppzp", "g2_add_batch_dev": "ppzp", "g1_neg_batch_dev": "pzp", "g2_neg_batch_dev": "pzp",
+        "g1_subset_sum_batch_dev": "pzpzp", "g2_subset_sum_batch_dev": "pzpzp", "g1_sum_batch_dev": "pzzp", "g2_sum_batch_dev": "pzzp",
+        "gt_exp_batch_dev": "pzpzp", "gt_cyclo_exp_batch_dev": "pzpzp", "gt_mul_batch_dev": "pzpzzp", "gt_div_batch_dev": "pzpzzp",
+        "pairing_check2_fixed_g1_batch_dev": "pppzp", "hash_to_g1_batch_dev": "ppzbp", "hash_to_g2_batch_dev": "ppzbp",
+        "fr_poly_from_roots_dev": "pzp", "fr_quotient_coeffs_dev": "pzpzp", "fr_to_scalars_dev": "pzp",
+    }
+
+    def dev(self, name, *args, stream=0):
+        """Enqueue bn254_<name> on `stream` (a cudaStream_t as int); returns immediately, nothing is synchronised."""
+        sig = self._DEV_SIGS[name]
+        if len(args) != len(sig):
+            raise TypeError("%s takes %d arguments" % (name, len(sig)))
+        cargs, keep = [self._h], []
+        for kind, a in zip(sig, args):
+            if kind == "p":
+                cargs.append(ctypes.c_void_p(int(a)))
+            elif kind == "z":
+                cargs.append(ctypes.c_size_t(int(a)))
+            elif kind == "h":
+                if a.engine is not self:
+                    raise ValueError("table handle of another engine")
+                cargs.append(a.handle)
+            else:
+                b = bytes(a)
+                buf = ctypes.create_string_buffer(b or b"\0", max(len(b), 1))
+                keep.append(buf)
+                cargs += [ctypes.cast(buf, ctypes.c_void_p), ctypes.c_size_t(len(b))]
+        cargs.append(ctypes.c_void_p(int(stream)))
+        fn = getattr(self._lib, "bn254_" + name)
+        fn.restype = ctypes.c_int
+        self._check(fn(*cargs))
+
     def _dev(self, name, *args):
         fn = getattr(self._lib, name)
         fn.restype = ctypes.c_int
@@ -368,6 +489,75 @@ class Engine:
     def gt_exp_batch_dev(self, d_x, stride, d_k, n, d_out, stream=0):
         self._dev("bn254_gt_exp_batch_dev", ctypes.c_void_p(d_x), ctypes.c_size_t(stride), ctypes.c_void_p(d_k),
                   ctypes.c_size_t(n), ctypes.c_void_p(d_out), ctypes.c_void_p(stream))
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if self.handle:
+            fn = getattr(self.engine._lib, self._destroy)
+            fn.argtypes = [ctypes.c_void_p]
+            fn.restype = None
+            fn(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FixedBase(_Handle):
+    """Handle of an immutable fixed-base window table (bn254_fixed_base)."""
+    _destroy = "bn254_fixed_base_destroy"
+
+    def __init__(self, engine, handle, group):
+        self.engine, self.handle, self.group = engine, handle, group
+
+
+class MsmTable(_Handle):
+    """Handle of per-point window tables for shared-point MSMs (bn254_msm_table)."""
+    _destroy = "bn254_msm_table_destroy"
+
+    def __init__(self, engine, handle, group, length):
+        self.engine, self.handle, self.group, self.len = engine, handle, group, length
+
+
+def fr_from_ints(vals):
+    """ints -> (n, 32) fr.Element (Montgomery form, gnark layout)."""
+    return np.frombuffer(b"".join((int(v) % R_MOD * (1 << 256) % R_MOD).to_bytes(32, "little") for v in vals), dtype=np.uint8).reshape(-1, 32).copy()
+
+
+def fr_to_ints(elems):
+    """(n, 32) fr.Element -> ints (regular value)."""
+    rinv = pow(1 << 256, -1, R_MOD)
+    e = np.ascontiguousarray(elems).reshape(-1, 32)
+    return [int.from_bytes(e[i].tobytes(), "little") * rinv % R_MOD for i in range(e.shape[0])]
+
+
+def fr_lagrange_basis(s, x):
+    """Delta_{s_i,S}(x) for every i (utils/compute_lagrange_basis.go:8-30) with one inversion: fr.Element in and out.
+    Host-side C++ in the library (no GPU work)."""
+    s, x = _u8(s, 32, "s"), _u8(x, 32, "x")
+    n = s.size // 32
+    out = np.empty(n * 32, dtype=np.uint8)
+    fn = _native.lib().bn254_fr_lagrange_basis
+    fn.restype = None
+    fn(s.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+    return out.reshape(n, 32)
+
+
+def fr_to_scalars(elems):
+    """fr.Element array -> regular-form little-endian scalars (x.BigInt(new(big.Int)))."""
+    e = _u8(elems, 32, "elems")
+    n = e.size // 32
+    out = np.empty(n * 32, dtype=np.uint8)
+    fn = _native.lib().bn254_fr_to_scalars
+    fn.restype = None
+    fn(e.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p))
+    return out.reshape(n, 32)
 
 
 class G2Lines:

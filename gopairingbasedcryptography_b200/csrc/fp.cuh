@@ -16,7 +16,7 @@
 #if defined(__CUDACC__)
 #define BN_HD __device__ __forceinline__
 #define BN_D __device__ __forceinline__
-#define BN_NOINLINE __device__ __noinline__
+#define BN_NOINLINE static __device__ __noinline__
 #else
 #define BN_HD static inline
 #define BN_D static inline

@@ -809,7 +809,7 @@ def mont32(v):
     return ", ".join("0x%08xu" % (((v << 256) % P >> (32 * i)) & 0xFFFFFFFF) for i in range(8))
 
 
-def emit(outdir, Ks=(1, 3)):
+def emit(outdir, Ks=(3,)):
     lines = ["// GENERATED by vmgen.py -- do not edit.", "#pragma once", "namespace bn254 { namespace vm {"]
     lines.append("static constexpr int N_CONST2 = %d;" % len(CONST2))
     lines.append("BN_CONST Fp2 VM_CONST2[%d] = {" % len(CONST2))
@@ -832,6 +832,7 @@ def emit(outdir, Ks=(1, 3)):
             lines.append("//   op histogram: %s" % meta["hist"])
             lines.append("static constexpr int %s_ROUNDS = %d;" % (tag, meta["rounds"]))
             lines.append("static constexpr int %s_NSLOTS = %d;" % (tag, meta["nslots"]))
+            lines.append("static constexpr int %s_NCOLD = %d;" % (tag, meta["ncold"]))
             lines.append("BN_CONST int %s_IN[%d] = {%s};" % (tag, len(meta["in_slots"]), ", ".join(map(str, meta["in_slots"]))))
             lines.append("BN_CONST int %s_OUT[6] = {%s};" % (tag, ", ".join(map(str, meta["out_slots"]))))
             print(tag, {k: v for k, v in meta.items() if k != "hist"})
@@ -842,5 +843,5 @@ def emit(outdir, Ks=(1, 3)):
 
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
-    Ks = tuple(int(x) for x in sys.argv[1:]) or (1, 3)
+    Ks = tuple(int(x) for x in sys.argv[1:]) or (3,)  # other lane widths (1, 2, 4, 6) regenerate on demand
     emit(here, Ks)

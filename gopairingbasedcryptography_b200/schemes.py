@@ -274,3 +274,147 @@ def _generators(engine):
         _, _, a1, a2 = Generators()
         _GEN_CACHE["g"] = (np.frombuffer(a1.raw, dtype=np.uint8).copy(), np.frombuffer(a2.raw, dtype=np.uint8).copy())
     return _GEN_CACHE["g"]
+
+
+# =====================================================================================================================
+# Device-resident pipelines (round 2): one upload, a stream-ordered sequence of *_dev launches with every intermediate
+# in HBM, one download.  torch is used for device memory and streams only.
+# =====================================================================================================================
+def _torch():
+    import torch
+
+    return torch
+
+
+def _up(x, torch, device):
+    """host bytes -> device tensor on the current stream.  A page-locked torch tensor (torch.Tensor.pin_memory, the
+    caller's reusable staging buffer) is copied asynchronously; numpy arrays go through the driver's own staging."""
+    if isinstance(x, torch.Tensor):
+        return x.reshape(-1).view(torch.uint8).to(device, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(x).reshape(-1).view(np.uint8)).to(device, non_blocking=True)
+
+
+def afp25_batch_setup(engine, tau_powers_g1, identities_fr):
+    """Per identity batch (Digest time, bibe/afp25_bibe/afp25_bibe.go:293-307): window tables of the points
+    (g1, [tau]1 .. [tau^(B-1)]1) the quotient polynomials are evaluated on, and the coefficients of
+    f(X) = prod (X - id_i) on the GPU.  tau_powers_g1: (>= B-1, 64) = mpk.G1ExpTauPowers; identities_fr: (B, 32)
+    fr.Element.  Returns (msm_table over B points, f coefficients (B+1, 32) fr.Element)."""
+    ids = np.ascontiguousarray(identities_fr).reshape(-1, 32)
+    B = ids.shape[0]
+    g1, _ = _generators(engine)
+    pts = np.concatenate([g1.reshape(1, G1_BYTES), np.ascontiguousarray(tau_powers_g1).reshape(-1, G1_BYTES)[:B - 1]], axis=0)
+    return engine.msm_table_create(1, pts), engine.fr_poly_from_roots(ids)
+
+
+def afp25_decrypt_batch(engine, table, f_coeffs, ids_fr, c1, c2, d, sk):
+    """AFP25 batch decryption (bibe/afp25_bibe/afp25_bibe.go:369-418) of n ciphertexts for n identities of one batch:
+        q_id(X) = f(X) / (X - id)            O(B) synthetic division per identity (reference: O(B^2) re-expansion)
+        pi_id   = sum_k [q_k] T_k            one shared-point MSM over the table (reference: B mults + B affine adds)
+        M       = C2 / ( e(D, C1[0]) e(pi, C1[1]) e(sk, C1[2]) )   ONE 3-pair product, one final exponentiation
+    All stages run back to back on one stream; only ids / ciphertexts go up and the n messages come down.
+    ids_fr: (n, 32) fr.Element; c1: (n, 3, 128); c2: (n, 384); d, sk: (64,).  Returns (n, 384)."""
+    torch = _torch()
+    dev = torch.device("cuda", engine.device)
+    ids = np.ascontiguousarray(ids_fr).reshape(-1, 32)
+    n, B = ids.shape[0], table.len
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream().cuda_stream
+        d_f, d_ids = _up(f_coeffs, torch, dev), _up(ids, torch, dev)
+        d_c1, d_c2 = _up(c1, torch, dev), _up(c2, torch, dev)
+        # P rows = (D, pi_v, sk): D and sk broadcast on the host side of the upload (2 x 64 B per row)
+        P = torch.empty((n, 3, G1_BYTES), dtype=torch.uint8, device=dev)
+        P[:, 0] = _up(d, torch, dev)
+        P[:, 2] = _up(sk, torch, dev)
+        q = torch.empty((n, B, 32), dtype=torch.uint8, device=dev)
+        pi = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
+        engine.dev("fr_quotient_coeffs_dev", d_f.data_ptr(), B, d_ids.data_ptr(), n, q.data_ptr(), stream=s)
+        engine.dev("msm_batch_dev", table, q.data_ptr(), n, pi.data_ptr(), stream=s)
+        P[:, 1] = pi
+        prod = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        engine.dev("multi_pair_batch_dev", P.data_ptr(), d_c1.data_ptr(), n, 3, prod.data_ptr(), stream=s)
+        out = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        engine.dev("gt_div_batch_dev", d_c2.data_ptr(), 1, prod.data_ptr(), 1, n, out.data_ptr(), stream=s)
+        return out.cpu().numpy()
+
+
+def bsw07_decrypt_batch_dev(engine, cy, cy_prime, lines, c, c_tilde, deltas=None):
+    """BSW07 decryption with the key's line tables, device-resident: [Delta_i]Cy_i and [Delta_i](-Cy'_i) (skipped when
+    the coefficients are folded into the tables: deltas=None), the (2m+1)-pair product from the tables and the final
+    product with C~ run as one stream-ordered sequence; the ciphertext points go up once, n messages come down.
+    cy, cy_prime: (n, m, 64); c: (n, 64); c_tilde: (n, 384); deltas: (m, 32) scalars or None."""
+    torch = _torch()
+    dev = torch.device("cuda", engine.device)
+    n, m = cy.shape[0], cy.shape[1]
+    k = 2 * m + 1
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream().cuda_stream
+        P = torch.empty((n, k, G1_BYTES), dtype=torch.uint8, device=dev)
+        d_cy, d_cyp, d_c = _up(cy, torch, dev).view(n, m, G1_BYTES), _up(cy_prime, torch, dev).view(n, m, G1_BYTES), _up(c, torch, dev).view(n, G1_BYTES)
+        d_ct = _up(c_tilde, torch, dev)
+        if deltas is None:  # folded tables: raw ciphertext points
+            P[:, :m] = d_cy
+            P[:, m:2 * m] = d_cyp
+            P[:, 2 * m] = d_c
+        else:
+            d_dl = _up(np.broadcast_to(np.ascontiguousarray(deltas).reshape(1, m, 32), (n, m, 32)), torch, dev)
+            a = torch.empty((n, m, G1_BYTES), dtype=torch.uint8, device=dev)
+            b = torch.empty((n, m, G1_BYTES), dtype=torch.uint8, device=dev)
+            ncyp = torch.empty((n, m, G1_BYTES), dtype=torch.uint8, device=dev)
+            nc = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
+            engine.dev("g1_mul_batch_dev", d_cy.data_ptr(), 1, d_dl.data_ptr(), n * m, a.data_ptr(), stream=s)
+            engine.dev("g1_neg_batch_dev", d_cyp.data_ptr(), n * m, ncyp.data_ptr(), stream=s)
+            engine.dev("g1_mul_batch_dev", ncyp.data_ptr(), 1, d_dl.data_ptr(), n * m, b.data_ptr(), stream=s)
+            engine.dev("g1_neg_batch_dev", d_c.data_ptr(), n, nc.data_ptr(), stream=s)
+            P[:, :m] = a
+            P[:, m:2 * m] = b
+            P[:, 2 * m] = nc
+        prod = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        engine.dev("multi_pair_lines_batch_dev", P.data_ptr(), lines, n, prod.data_ptr(), stream=s)
+        out = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        engine.dev("gt_mul_batch_dev", d_ct.data_ptr(), 1, prod.data_ptr(), 1, n, out.data_ptr(), stream=s)
+        return out.cpu().numpy()
+
+
+class Waters05Params:
+    """Fixed-base handles of one Waters05 parameter set (ibe/waters05_ibe/waters05_ibe.go:117-151): g1, the constant
+    pairing e(g1^alpha, g2) (waters05_ibe.go:214, hoisted: it does not depend on the message or the identity) and the
+    257 Waters-hash points on the device."""
+
+    def __init__(self, engine, g1_alpha, U):
+        torch = _torch()
+        g1, g2 = _generators(engine)
+        self.engine = engine
+        self.m = np.ascontiguousarray(U).reshape(-1, G2_BYTES).shape[0] - 1
+        self.e_const = engine.pair_batch(np.ascontiguousarray(g1_alpha).reshape(-1), g2)[0]
+        self.t_g1 = engine.fixed_base_create(1, g1)
+        self.t_gt = engine.fixed_base_create(3, self.e_const)
+        self.dev = torch.device("cuda", engine.device)
+        with torch.cuda.device(self.dev):
+            self.d_U = _up(U, torch, self.dev)
+            torch.cuda.synchronize()
+
+
+def waters05_encrypt_batch_dev(params, ids, msgs, ts):
+    """Waters05 Encrypt (ibe/waters05_ibe/waters05_ibe.go:206-244) for n (identity, message) pairs, device-resident:
+        c1 = e(g1^alpha, g2)^t * M   fixed-base GT table + GT product
+        c2 = [t] g1                  fixed-base G1 table
+        c3 = [t] (U' + sum_{bits} U_j)   Waters hash as one Jacobian subset sum, then a GLV multiplication
+    ids: (n, m/8) identity bit strings (MSB first per byte, waters05_ibe.go:302-313); msgs: (n, 384); ts: (n, 32).
+    One upload (ids, messages, scalars), five launches on one stream, one download -> (c1 (n,384), c2 (n,64), c3 (n,128))."""
+    torch = _torch()
+    e, dev = params.engine, params.dev
+    n = np.ascontiguousarray(ts).reshape(-1, 32).shape[0]
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream().cuda_stream
+        d_ids, d_m, d_t = _up(ids, torch, dev), _up(msgs, torch, dev), _up(ts, torch, dev)
+        et = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        c1 = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        c2 = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
+        h = torch.empty((n, G2_BYTES), dtype=torch.uint8, device=dev)
+        c3 = torch.empty((n, G2_BYTES), dtype=torch.uint8, device=dev)
+        e.dev("gt_fixed_exp_batch_dev", params.t_gt, d_t.data_ptr(), n, et.data_ptr(), stream=s)
+        e.dev("gt_mul_batch_dev", et.data_ptr(), 1, d_m.data_ptr(), 1, n, c1.data_ptr(), stream=s)
+        e.dev("g1_fixed_mul_batch_dev", params.t_g1, d_t.data_ptr(), n, c2.data_ptr(), stream=s)
+        e.dev("g2_subset_sum_batch_dev", params.d_U.data_ptr(), params.m, d_ids.data_ptr(), n, h.data_ptr(), stream=s)
+        e.dev("g2_mul_batch_dev", h.data_ptr(), 1, d_t.data_ptr(), n, c3.data_ptr(), stream=s)
+        return c1.cpu().numpy(), c2.cpu().numpy(), c3.cpu().numpy()

@@ -59,9 +59,6 @@ const uint64_t kMiller3[] = {
 const uint64_t kFinalExp3[] = {
 #include "../../gopairingbasedcryptography_b200/csrc/vm_prog_finalexp_k3.inc"
 };
-const uint64_t kPair1[] = {
-#include "../../gopairingbasedcryptography_b200/csrc/vm_prog_pair_k1.inc"
-};
 void run_rounds(Fp2* slots, const uint64_t* prog, int rounds, int K) {
   vm::SlotFile f; f.hot = reinterpret_cast<uint4*>(slots); f.cold = nullptr; f.nslots = 256; f.hot_stride = 0; f.pid = 0; f.cold_stride = 0; f.gpid = 0;
   for (int r = 0; r < rounds; r++) {
@@ -72,7 +69,7 @@ void run_rounds(Fp2* slots, const uint64_t* prog, int rounds, int K) {
 }
 }
 extern "C" {
-// mode 0: pair (K=3), 1: miller only, 2: final exp only, 3: pair with the K=1 program
+// mode 0: pair (K=3), 1: miller only, 2: final exp only
 void emu_vm(const void* in0, const void* in1, size_t n, int mode, void* out) {
   using namespace vm;
   for (size_t i = 0; i < n; i++) {
@@ -80,8 +77,7 @@ void emu_vm(const void* in0, const void* in1, size_t n, int mode, void* out) {
     const int* IN; const int* OUT; const uint64_t* prog; int rounds, K = 3, nin = 3;
     if (mode == 0) { IN = PAIR_K3_IN; OUT = PAIR_K3_OUT; prog = kPair3; rounds = PAIR_K3_ROUNDS; }
     else if (mode == 1) { IN = MILLER_K3_IN; OUT = MILLER_K3_OUT; prog = kMiller3; rounds = MILLER_K3_ROUNDS; }
-    else if (mode == 2) { IN = FINALEXP_K3_IN; OUT = FINALEXP_K3_OUT; prog = kFinalExp3; rounds = FINALEXP_K3_ROUNDS; nin = 6; }
-    else { IN = PAIR_K1_IN; OUT = PAIR_K1_OUT; prog = kPair1; rounds = PAIR_K1_ROUNDS; K = 1; }
+    else { IN = FINALEXP_K3_IN; OUT = FINALEXP_K3_OUT; prog = kFinalExp3; rounds = FINALEXP_K3_ROUNDS; nin = 6; }
     if (nin == 3) {
       memcpy(&slots[IN[0]], (const char*)in0 + i * 64, 64);
       memcpy(&slots[IN[1]], (const char*)in1 + i * 128, 64);

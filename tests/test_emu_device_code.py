@@ -139,11 +139,11 @@ def test_groups_and_gt(emu):
 
 def test_tower_vm_programs_on_host(emu):
     """The lane-group kernels' generated micro-op programs (vmgen.py), run by the C++ interpreter (vm.cuh)
-    with lock-step round semantics: pair (K=3 and K=1), miller-only and final-exp-only programs."""
+    with lock-step round semantics: pair, miller-only and final-exp-only programs (K = 3, the in-tree lane width)."""
     n = 3
     P, Q, _, _ = common.points(n, seed=123)
     ref = port.pair_batch(P, Q, n)
-    for mode in (0, 3):
+    for mode in (0,):
         out = np.zeros(384 * n, np.uint8)
         emu.emu_vm(vp(P), vp(Q), sz(n), mode, vp(out))
         assert (out == ref).all()

@@ -59,3 +59,48 @@ def test_g2_encodings_round_trip():
     assert wire.g2_unmarshal(wire.g2_bytes(inf)) == inf and wire.g2_unmarshal(wire.g2_marshal(inf)) == inf
     with pytest.raises(ValueError):
         wire.g2_unmarshal(bytes([0x80]) + bytes(62) + b"\x05")  # x with no point on the twist (or non-square)
+
+
+def test_uncompressed_infinity_is_all_zero_and_validation():
+    """gnark RawBytes() of the point at infinity on BN254 writes mUncompressed (0b00) and zero coordinates -- 0b01 is
+    the COMPRESSED infinity flag.  Unmarshal runs gnark's curve / subgroup checks."""
+    assert wire.g1_marshal(bytes(64)) == bytes(64) and wire.g2_marshal(bytes(128)) == bytes(128)
+    assert wire.g1_bytes(bytes(64)) == bytes([0x40]) + bytes(31) and wire.g2_bytes(bytes(128)) == bytes([0x40]) + bytes(63)
+    with pytest.raises(ValueError):  # (1, 3) is not on y^2 = x^3 + 3
+        wire.g1_unmarshal((1).to_bytes(32, "big") + (3).to_bytes(32, "big"))
+    with pytest.raises(ValueError):  # infinity flag with trailing garbage
+        wire.g1_unmarshal(bytes([0x40]) + bytes(30) + b"\x01")
+    # a point ON the twist but OUTSIDE the order-r subgroup (the twist has cofactor 2p - r): find one by x-increment
+    x = (1, 0)
+    while True:
+        rhs = wire._fp2_mul(wire._fp2_mul(x, x), x)
+        rhs = ((rhs[0] + wire._B2[0]) % o.P, (rhs[1] + wire._B2[1]) % o.P)
+        y = wire._fp2_sqrt(rhs)
+        if y is not None:
+            break
+        x = (x[0] + 1, 0)
+    assert not wire._g2_in_subgroup(x, y)
+    enc = b"".join(v.to_bytes(32, "big") for v in (x[1], x[0], y[1], y[0]))
+    with pytest.raises(ValueError, match="subgroup"):
+        wire.g2_unmarshal(enc)
+    g = o.g2_mul(o.G2_GEN, 5)
+    assert wire._g2_in_subgroup(g[0], g[1])
+
+
+def test_reference_consumers_of_the_encodings():
+    """hash.FromGT (hash/hash_from_gt.go:5-8) and Gentry06's h (ibe/gentry06_ibe/gentry06_ibe.go:319-343), restated
+    independently here from the oracle's integer tuples."""
+    import hashlib
+
+    u = o.g1_mul(o.G1_GEN, 4242)
+    v = o.pair([o.G1_GEN], [o.G2_GEN])
+    w = o.pair([u], [o.G2_GEN])
+    flat = lambda e: [e[c][b][a] for c in (1, 0) for b in (2, 1, 0) for a in (1, 0)]  # C1.B2.A1 ... C0.B0.A0
+    vb = b"".join(t.to_bytes(32, "big") for t in flat(v))
+    wb = b"".join(t.to_bytes(32, "big") for t in flat(w))
+    assert wire.hash_from_gt(o.gt_to_bytes(v)) == vb
+    ub = bytearray(u[0].to_bytes(32, "big"))
+    ub[0] |= 0xC0 if u[1] > (o.P - 1) // 2 else 0x80
+    beta = int.from_bytes(hashlib.sha256(bytes(ub) + vb + wb).digest(), "big") % o.R
+    got = wire.gentry06_h(o.g1_to_bytes(u), o.gt_to_bytes(v), o.gt_to_bytes(w))
+    assert int.from_bytes(got, "little") == beta * (1 << 256) % o.R
