@@ -119,7 +119,7 @@ def test_device_resident_entry_points_match_host_paths(engine):
     n = 200
     P, Q, _, _ = common.points(n, seed=41, threads=8)
     ks = sb(common.scalars(n, seed=42, edges=True))
-    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev)
+    up = lambda a: torch.from_numpy(np.array(a, copy=True).reshape(-1)).to(dev)
     dn = lambda t: t.cpu().numpy()
     s = torch.cuda.current_stream().cuda_stream
     dP, dQ, dk = up(P), up(Q), up(ks)
@@ -139,9 +139,10 @@ def test_device_resident_entry_points_match_host_paths(engine):
     o1 = torch.empty(n * 64, dtype=torch.uint8, device=dev)
     o2 = torch.empty(n * 128, dtype=torch.uint8, device=dev)
     P2, Q2 = np.roll(P, 64), np.roll(Q, 128)
-    engine.dev("g1_add_batch_dev", dP.data_ptr(), up(P2).data_ptr(), n, o1.data_ptr(), stream=s)
+    dP2, dQ2 = up(P2), up(Q2)  # keep every device operand referenced until its launch has been enqueued
+    engine.dev("g1_add_batch_dev", dP.data_ptr(), dP2.data_ptr(), n, o1.data_ptr(), stream=s)
     assert (dn(o1).reshape(n, 64) == engine.g1_add_batch(P, P2)).all()
-    engine.dev("g2_add_batch_dev", dQ.data_ptr(), up(Q2).data_ptr(), n, o2.data_ptr(), stream=s)
+    engine.dev("g2_add_batch_dev", dQ.data_ptr(), dQ2.data_ptr(), n, o2.data_ptr(), stream=s)
     assert (dn(o2).reshape(n, 128) == engine.g2_add_batch(Q, Q2)).all()
     from gopairingbasedcryptography_b200 import schemes
 
@@ -161,11 +162,12 @@ def test_device_resident_entry_points_match_host_paths(engine):
     U = Q.reshape(n, 128)[: m + 1]
     sel = np.frombuffer(hashlib.sha256(b"sel").digest() * 8, dtype=np.uint8)[: 20 * (m // 8)].reshape(20, m // 8)
     ho = torch.empty(20 * 128, dtype=torch.uint8, device=dev)
-    engine.dev("g2_subset_sum_batch_dev", up(U).data_ptr(), m, up(sel).data_ptr(), 20, ho.data_ptr(), stream=s)
+    dU, dsel = up(U), up(sel)
+    engine.dev("g2_subset_sum_batch_dev", dU.data_ptr(), m, dsel.data_ptr(), 20, ho.data_ptr(), stream=s)
     assert (dn(ho).reshape(20, 128) == engine.g2_subset_sum_batch(U, sel)).all()
     # BLS-shaped check, hash-to-curve, line tables
     ok = torch.empty(n, dtype=torch.uint8, device=dev)
-    engine.dev("pairing_check2_fixed_g1_batch_dev", dP.data_ptr(), dQ.data_ptr(), up(Q2).data_ptr(), n, ok.data_ptr(), stream=s)
+    engine.dev("pairing_check2_fixed_g1_batch_dev", dP.data_ptr(), dQ.data_ptr(), dQ2.data_ptr(), n, ok.data_ptr(), stream=s)
     assert (dn(ok).astype(bool) == engine.pairing_check2_fixed_g1_batch(P[:64], P[64:128], Q, Q2)).all()
     msgs = [b"m%d" % i * (i % 5) for i in range(40)]
     blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
@@ -173,10 +175,11 @@ def test_device_resident_entry_points_match_host_paths(engine):
     off[1:] = np.cumsum([len(x) for x in msgs])
     dst = b"QUUX-V01-CS02-with-BN254G2_XMD:SHA-256_SVDW_RO_"
     hq = torch.empty(40 * 128, dtype=torch.uint8, device=dev)
-    engine.dev("hash_to_g2_batch_dev", up(blob).data_ptr(), up(off.view(np.uint8)).data_ptr(), 40, dst, hq.data_ptr(), stream=s)
+    dblob, doff = up(blob), up(off.view(np.uint8))
+    engine.dev("hash_to_g2_batch_dev", dblob.data_ptr(), doff.data_ptr(), 40, dst, hq.data_ptr(), stream=s)
     assert (dn(hq).reshape(40, 128) == engine.hash_to_g2_batch(msgs, dst)).all()
     hp = torch.empty(40 * 64, dtype=torch.uint8, device=dev)
-    engine.dev("hash_to_g1_batch_dev", up(blob).data_ptr(), up(off.view(np.uint8)).data_ptr(), 40, dst, hp.data_ptr(), stream=s)
+    engine.dev("hash_to_g1_batch_dev", dblob.data_ptr(), doff.data_ptr(), 40, dst, hp.data_ptr(), stream=s)
     assert (dn(hp).reshape(40, 64) == engine.hash_to_g1_batch(msgs, dst)).all()
     m = 19
     lines = engine.g2_lines_create(Q.reshape(n, 128)[:m])
