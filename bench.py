@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairings in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--light", action="store_true", help="kernel sweep mode: skip e2e, cpu_baseline and the live IMAD peak")
+    ap.add_argument("--rows", default="full", choices=["none", "quick", "full"], help="the rest of the metric (BLS verifies/s, scalar mults/s, ...)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -175,12 +176,12 @@ def main():
     n = 1 << args.log2_batch
 
     # ---- synthetic inputs, generated on the GPU: P = A[i % m] + B[i // m], same for Q ----------------
-    from oracle import bn254_ref as o  # seeded SplitMix64 only; no oracle arithmetic on this path
+    from benchmarks.rows import SplitMix64, load_executed_imad, measure_rows  # the product arm imports nothing from oracle/
 
-    rng = o.SplitMix64(0xB2000254 + 2 + 1000 * rank)
+    rng = SplitMix64(0xB2000254 + 2 + 1000 * rank)
     m = 1 << (args.log2_batch // 2)
     mh = n // m
-    sc = [rng.scalar() for _ in range(2 * (m + mh))]
+    sc = [rng.scalar(bn254.R_MOD) for _ in range(2 * (m + mh))]
     sb = bn254.scalars_to_bytes(sc)
     g1, g2 = bn254.Generators()[2:]
     A1 = eng.g1_mul_base_batch(g1.raw, sb[:m]); B1 = eng.g1_mul_base_batch(g1.raw, sb[m:m + mh])
@@ -218,7 +219,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n * args.steps / (ms_max * 1e-3)
-    kernel_ms = ms / max(launches, 1)
+    # the dominant kernel alone, for the roofline: k_pair over the whole batch (BN254_IMPL=thread never routes a
+    # remainder to the lane-group kernel, so one step is exactly one k_pair launch)
+    os.environ["BN254_IMPL"] = "thread"
+    eng_t = bn254.Engine(local)
+    del os.environ["BN254_IMPL"]
+    eng_t.pair_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, dO.data_ptr(), stream)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng_t.launches
+    k0.record()
+    for _ in range(args.steps):
+        eng_t.pair_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, dO.data_ptr(), stream)
+    k1.record()
+    torch.cuda.synchronize()
+    assert eng_t.launches - l0 == args.steps
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    step_dev()  # leave the default path's output in dO for the verification below
+    torch.cuda.synchronize()
+
+    # ---- strong scaling: ONE 2^20 batch split over the N ranks (BASELINE configs[1] wording) ---------------------
+    ns = n // world
+    step_s = lambda: eng.pair_batch_dev(dP.data_ptr(), dQ.data_ptr(), ns, dO.data_ptr(), stream)
+    if world > 1:
+        step_s()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step_s()
+        s1.record()
+        barrier()
+        ts_ = torch.tensor([s0.elapsed_time(s1)], device="cuda")
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        strong_ms = float(ts_.item()) / args.steps
+        step_dev()
+        torch.cuda.synchronize()
+    else:
+        strong_ms = ms_max / args.steps
+    strong = {"workload": "ONE batch of 2^%d pairs split over %d GPU(s): %d pairs per GPU" % (args.log2_batch, world, ns),
+              "value": ns * world / (strong_ms * 1e-3), "unit": UNIT, "ms_per_step": strong_ms,
+              "efficiency_vs_weak": (ns * world / (strong_ms * 1e-3)) / value,
+              "note": "per-GPU remainder (batch mod one wave of %d threads) goes to the lane-group kernel when it is under 55 %% of a wave" % (148 * 3 * 128)}
 
     # ---- end to end through the host-buffer API --------------------------------------------------
     hP_np, hQ_np = hP.numpy(), hQ.numpy()
@@ -257,8 +299,12 @@ def main():
     ref = port.pair_batch(P[idx].reshape(-1), Q[idx].reshape(-1), len(idx), host_threads()).reshape(len(idx), 384)
     assert (dev_out[idx] == ref).all(), "GPU pairings differ from the oracle"
 
+    peak, peak_how = measure_imad_peak(local) if rank == 0 else (9.24e12, "")
+    rows = []
+    if args.rows != "none":
+        load_executed_imad(ROOT)
+        rows = measure_rows(eng, peak, rank=rank, world=world, dist=dist, quick=(args.rows == "quick"), cpu=True)
     if rank == 0:
-        peak, peak_how = measure_imad_peak(local)
         achieved = MACS_PER_PAIRING * n / (kernel_ms * 1e-3)
         threads = host_threads()
         sample = args.cpu_sample or max(threads * 1024, 4096)  # ~20 s of CPU time on the C restatement
@@ -273,14 +319,17 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 192, "d2h_bytes_per_step": n * 384},
             "gpu_launches": launches,
+            "strong_2p20": strong,
+            "rows": rows,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T limb-MAC/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PAIRING * n,
-                         "note": "algorithmic 2.081e6 32x32->64 MACs per pairing (SURVEY 8d) x %d per launch / %.1f ms kernel; "
+                         "kernel": "k_pair", "kernel_ms": kernel_ms,
+                         "note": "algorithmic 2.081e6 32x32->64 MACs per pairing (SURVEY 8d) x %d per k_pair launch / %.1f ms (timed alone on a thread-kernel context); "
                                  "peak = IMAD.WIDE rate %s; algorithmic HBM: %.2f GB/s of %.0f measured (not the bound); traffic = DRAM bytes per launch "
                                  "scaled from the ncu capture at 2^18 (local-memory stack spill, see profiles/r1)"
                                  % (n, kernel_ms, peak_how, BYTES_PER_PAIRING * n / (kernel_ms * 1e-3) / 1e9, 6472.1)},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d pairings on %d threads, oracle C restatement (gnark cannot run here: no Go)" % (sample, threads)},
+                             "sample": "%d pairings on %d threads, C restatement of gnark (gnark itself cannot run here: no Go)" % (sample, threads)},
         }
         print(json.dumps(line))
     if dist is not None:

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 # CTA lockstep barriers (the four warps of a CTA share instruction-cache lines).
 DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"]
 NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
-UNITS = ["k_pairing", "k_group", "k_gt", "k_hash", "k_vm", "k_fr", "engine"]
+UNITS = ["k_pairing", "k_group", "k_gt", "k_hash", "k_vm", "k_wvm", "k_fr", "engine"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for every unit, or {unit: flags}
     "": DEFAULT,
     "nolockstep": NOLS,
@@ -53,7 +53,20 @@ def unit_flags(unit):
     return flags + UNIT_FLAGS.get(unit, [])
 
 
+def ensure_generated():
+    """The warp-VM programs (wvm_prog_*.inc, ~8 MB of text) are generated, not committed: wvmgen.py rebuilds them from
+    the traced pairing formulas in a few seconds."""
+    outs = [os.path.join(CSRC, f) for f in ("wvm_prog_miller.inc", "wvm_prog_finalexp.inc", "wvm_prog_meta.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("wvmgen.py", "vmgen.py")]
+    if all(os.path.exists(o) for o in outs) and min(os.path.getmtime(o) for o in outs) >= max(os.path.getmtime(s) for s in srcs):
+        return
+    import sys
+
+    subprocess.check_call([sys.executable, os.path.join(CSRC, "wvmgen.py")])
+
+
 def build(force=False, verbose=False):
+    ensure_generated()
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)

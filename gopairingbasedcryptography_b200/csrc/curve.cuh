@@ -95,23 +95,6 @@ BN_HD void jac_to_aff(A& r, const J& p) {
 template <typename A>
 BN_HD bool aff_is_inf(const A& p) { return f_is_zero(p.x) && f_is_zero(p.y); }
 
-// [s]base, s = 256-bit little-endian unsigned (8 x u32); signed 4-bit fixed windows over an
-// on-the-fly table {1..8}*base kept in Jacobian-free affine form is overkill for a first version:
-// plain left-to-right double-and-add with a 2-bit window is used until the GLV kernel lands.
-template <typename J, typename A>
-BN_HD void scalar_mul(A& out, const A& base, const uint32_t* s) {
-  if (aff_is_inf(base)) { out = base; return; }
-  // table: 1P (affine), 2P, 3P as Jacobian -> kept Jacobian and added via full addition is costly;
-  // use affine 1P only (binary method).  Cost ~ 256 dbl + ~128 mixed add.
-  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
-  int top = 255;
-  while (top >= 0 && !((s[top >> 5] >> (top & 31)) & 1u)) top--;
-  for (int i = top; i >= 0; i--) {
-    jac_dbl(acc, acc);
-    if ((s[i >> 5] >> (i & 31)) & 1u) jac_add_aff(acc, acc, base);
-  }
-  jac_to_aff(out, acc);
-}
 // affine + affine with gnark Add semantics (infinity operands, doubling, P + (-P))
 template <typename J, typename A>
 BN_HD void aff_add(A& out, const A& a, const A& b) {

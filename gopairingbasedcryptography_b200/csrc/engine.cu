@@ -17,6 +17,7 @@
 #include "launch.h"
 
 namespace L = bn254::launch;
+std::atomic<uint64_t> bn254::launch::g_launches{0};
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -52,13 +53,14 @@ struct bn254_ctx {
   std::string err;
   Slot slot[2];
   size_t slot_bytes = 0;
-  uint64_t launches = 0;
   // lane-group (tower VM) kernels.  BN254_IMPL: "vm" = lane-group kernels always, "thread" = one-thread-per-pairing
   // kernels always, unset = thread kernels, except that launches of at most kVmAutoMax elements take the lane-group
   // kernels (lower latency: three lanes share one pairing)
-  int vm_mode = 0;  // 0 auto, 1 always, 2 never
+  int vm_mode = 0;  // 0 auto, 1 lane-group always, 2 never (thread kernels only), 3 warp-VM always
   int sms = 0;
   int vm_blocks_per_sm[3] = {0, 0, 0};
+  int wvm_blocks_per_sm[3] = {0, 0, 0};
+  size_t wvm_auto_max = 0;  // launches of at most this many items take the warp-VM kernels (one warp per item)
   void* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
   cudaEvent_t vm_dev_done = nullptr;
   // implicit fixed-base tables of the *_base_batch entry points: small LRU keyed by the base's bytes.  Entries are
@@ -87,7 +89,10 @@ int fail(bn254_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) 
 inline int cu_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? BN254_ERR_OOM : BN254_ERR_CUDA; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, cu_code(e_), #call, e_); } while (0)
 
-inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
+// Small launches are latency-bound: up to wvm_auto_max items run one WARP per item (warp-VM), up to kVmAutoMax three
+// lanes per item (lane-group VM), beyond that one thread per item.  BN254_IMPL = thread | vm | wvm forces one path.
+inline bool use_wvm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 3 || (ctx->vm_mode == 0 && n <= ctx->wvm_auto_max); }
+inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || ctx->vm_mode == 3 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
 inline size_t pt_bytes(int g) { return g == 1 ? BN254_G1_BYTES : BN254_G2_BYTES; }
 inline size_t jac_bytes(int g) { return g == 1 ? kG1Jac : kG2Jac; }
 inline int slot_index(const bn254_ctx* ctx, cudaStream_t s) { return s == ctx->slot[1].stream ? 1 : 0; }
@@ -160,6 +165,10 @@ int run_host_locked(bn254_ctx* ctx, const Operand* in, int nin, void* out, size_
   if (fixed >= ctx->slot_bytes) return fail(ctx, BN254_ERR_BAD_ARG, "element too large for staging");
   size_t chunk = std::min<size_t>({n, kMaxChunkItems, (ctx->slot_bytes - fixed) / per});
   if (chunk == 0) return fail(ctx, BN254_ERR_BAD_ARG, "element too large for staging");
+  // one-thread-per-item kernels: a chunk of whole waves (148 SMs x 3 CTAs x 128 threads) does not pay for a part-filled
+  // last wave in every chunk (131 072 = 2.31 waves ran as 3)
+  const size_t wave = (size_t)ctx->sms * 3 * L::kBlockThreads;
+  if (chunk < n && chunk > wave) chunk -= chunk % wave;
   // Caller buffers in page-locked memory (bn254_host_alloc, cudaHostRegister, torch pin_memory ...) are copied to /
   // from the device directly, chunk by chunk, on the slot's stream; pageable ones go through the pinned staging area.
   auto page_locked = [](const void* p) {
@@ -200,7 +209,6 @@ int run_host_locked(bn254_ctx* ctx, const Operand* in, int nin, void* out, size_
       }
       size_t oo = off, lo = out_item * c;
       if ((e = launch(d_in, c, s.d + oo, s)) != cudaSuccess) return e;
-      ctx->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       s.user_out = static_cast<char*>(out) + done * out_item;
       if (out_pinned) { e = cudaMemcpyAsync(s.user_out, s.d + oo, lo, cudaMemcpyDeviceToHost, s.stream); s.out_bytes = 0; }
@@ -243,7 +251,6 @@ int run_dev(bn254_ctx* ctx, size_t n, void* stream, LF launch) {
   sc.stream = (cudaStream_t)stream;
   cudaError_t e = launch(sc);
   sc.release();
-  ctx->launches++;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, cu_code(e), "device-pointer batch", e); }
   return BN254_OK;
@@ -257,6 +264,10 @@ cudaError_t vm_dev(bn254_ctx* ctx, int prog, const void* a, const void* b, size_
 }
 // `cold`: the scratch of the lane-group kernels for this launch site (slot's own, or the shared *_dev one)
 cudaError_t vm_any(bn254_ctx* ctx, Scratch& sc, int prog, const void* a, const void* b, size_t n, void* out) {
+  if (use_wvm(ctx, n)) {  // warp-VM: state in shared memory only, no scratch to share or order
+    L::wvm_run(prog, a, b, n, out, ctx->sms, ctx->wvm_blocks_per_sm, sc.stream);
+    return cudaSuccess;
+  }
   if (!sc.slot) return vm_dev(ctx, prog, a, b, n, out, sc.stream);
   L::vm_run(prog, a, b, n, out, sc.slot->vm_cold, ctx->sms, ctx->vm_blocks_per_sm, sc.stream);
   return cudaSuccess;
@@ -265,6 +276,20 @@ cudaError_t vm_any(bn254_ctx* ctx, Scratch& sc, int prog, const void* a, const v
 // ---- launch sequences shared by the host-buffer and device-pointer entry points ---------------------------------
 cudaError_t seq_pair(bn254_ctx* ctx, Scratch& sc, const void* P, const void* Q, size_t n, void* out) {
   if (use_vm(ctx, n)) return vm_any(ctx, sc, L::kVmPair, P, Q, n, out);
+  // Remainder-aware split (strong scaling: 2^20 pairs over 8 GPUs = 2.31 waves of one-thread-per-pairing CTAs, and a
+  // third, 31 %-full wave costs as much as a full one): whole waves go to the thread kernel, a SMALL remainder to the
+  // lane-group kernel, whose three-lanes-per-pairing passes finish a partial wave in ~1/3 of a thread-kernel wave.
+  // Only when the remainder fits ONE pass of the lane-group grid (measured: at 2^20 = 18 waves + 25 600 the two passes
+  // the remainder needs cost 8 ms more than the 19th partial wave; at 2^17 = 2 waves + 17 408 one pass saves a third wave).
+  const size_t wave = (size_t)L::pairing_wave_threads(ctx->sms);
+  const size_t rem = n % wave;
+  const size_t vm_pass = (size_t)ctx->sms * ctx->vm_blocks_per_sm[L::kVmPair] * L::kVmPairingsPerCta;
+  if (ctx->vm_mode == 0 && !sc.slot && n > wave && rem > 0 && rem <= vm_pass) {
+    const size_t whole = n - rem;
+    L::pair(P, Q, whole, out, sc.stream);
+    return vm_dev(ctx, L::kVmPair, static_cast<const char*>(P) + whole * BN254_G1_BYTES, static_cast<const char*>(Q) + whole * BN254_G2_BYTES, rem,
+                  static_cast<char*>(out) + whole * BN254_GT_BYTES, sc.stream);
+  }
   L::pair(P, Q, n, out, sc.stream);
   return cudaSuccess;
 }
@@ -416,8 +441,7 @@ int build_fixed_table(bn254_ctx* ctx, int group, const void* base, FixedTable* t
   if (e == cudaSuccess) {
     if (group == BN254_GROUP_GT) L::gt_exp(0, s.d, 0, s.d + 512, entries, dev, nullptr, s.stream);
     else L::scalar_mul(group, s.d, 0, s.d + 512, entries, dev, s.stream);
-    ctx->launches++;
-    e = cudaGetLastError();
+      e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   if (e != cudaSuccess) { cudaFree(dev); cudaGetLastError(); return fail(ctx, cu_code(e), "fixed-base table build", e); }
@@ -494,7 +518,6 @@ int hash_to_curve_host(bn254_ctx* ctx, int G, const uint8_t* msgs, const uint64_
       if ((e = cudaMemcpyAsync(s.d, s.h, o_out, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) return e;
       const uint8_t* d = reinterpret_cast<const uint8_t*>(s.d);
       L::hash_to_curve(G, d + o_msg, reinterpret_cast<const uint64_t*>(d + 256), c, d, (uint32_t)dst_len, s.d + o_out, s.stream);
-      ctx->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if ((e = cudaMemcpyAsync(s.h + o_out, s.d + o_out, out_item * c, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return e;
       pend[it].done = done; pend[it].c = c; pend[it].o_out = o_out; pend[it].live = true;
@@ -550,9 +573,13 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     return BN254_ERR_CUDA;
   }
   const char* impl = getenv("BN254_IMPL");
-  ctx->vm_mode = !impl ? 0 : (std::string(impl) == "vm" ? 1 : (std::string(impl) == "thread" ? 2 : 0));
+  ctx->vm_mode = !impl ? 0 : (std::string(impl) == "vm" ? 1 : (std::string(impl) == "thread" ? 2 : (std::string(impl) == "wvm" ? 3 : 0)));
   ctx->sms = prop.multiProcessorCount;
-  if (L::vm_prepare(ctx->vm_blocks_per_sm) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
+  if (L::vm_prepare(ctx->vm_blocks_per_sm) != cudaSuccess || L::wvm_prepare(ctx->wvm_blocks_per_sm) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
+  {  // crossover to the lane-group kernels: about two passes of the warp-VM grid (profiles/r2/latency_vs_batch.jsonl)
+    const char* wm = getenv("BN254_WVM_MAX");
+    ctx->wvm_auto_max = wm ? (size_t)atol(wm) : (size_t)2 * ctx->sms * ctx->wvm_blocks_per_sm[L::kVmPair] * L::wvm_items_per_cta();
+  }
   size_t cb = L::vm_cold_bytes(ctx->sms, ctx->vm_blocks_per_sm);
   if (cudaMalloc(&ctx->vm_cold_dev, cb) != cudaSuccess || cudaMalloc(&ctx->slot[0].vm_cold, cb) != cudaSuccess ||
       cudaMalloc(&ctx->slot[1].vm_cold, cb) != cudaSuccess ||
@@ -587,7 +614,7 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
 }
 
 const char* bn254_last_error(bn254_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t bn254_launch_count(bn254_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t bn254_launch_count(bn254_ctx*) { return L::g_launches.load(); }
 int bn254_sm_count(bn254_ctx* ctx) { return ctx ? ctx->sms : 0; }
 
 void* bn254_host_alloc(size_t bytes) {
@@ -708,7 +735,7 @@ int bn254_g2_lines_create(bn254_ctx* ctx, const void* Q, size_t m, bn254_lines**
   Slot& s = ctx->slot[0];
   memcpy(s.h, Q, m * BN254_G2_BYTES);
   cudaError_t e = cudaMemcpyAsync(s.d, s.h, m * BN254_G2_BYTES, cudaMemcpyHostToDevice, s.stream);
-  if (e == cudaSuccess) { L::g2_lines(s.d, m, Lt->table, Lt->qskip, s.stream); ctx->launches++; e = cudaGetLastError(); }
+  if (e == cudaSuccess) { L::g2_lines(s.d, m, Lt->table, Lt->qskip, s.stream); e = cudaGetLastError(); }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   if (e != cudaSuccess) { cudaFree(Lt->table); cudaFree(Lt->qskip); delete Lt; cudaGetLastError(); return fail(ctx, cu_code(e), "line table build", e); }
   *out = Lt;
@@ -844,7 +871,7 @@ int bn254_msm_table_create(bn254_ctx* ctx, int group, const void* points, size_t
     memcpy(s.h, points, len * B);
     e = cudaMemcpyAsync(s.d, s.h, len * B, cudaMemcpyHostToDevice, s.stream);
   }
-  if (e == cudaSuccess) { L::msm_tables(group, s.d, len, tables, zs, pf, s.stream); ctx->launches++; e = cudaGetLastError(); }
+  if (e == cudaSuccess) { L::msm_tables(group, s.d, len, tables, zs, pf, s.stream); e = cudaGetLastError(); }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   cudaFree(zs); cudaFree(pf);
   if (e != cudaSuccess) { cudaFree(tables); cudaGetLastError(); return fail(ctx, cu_code(e), "MSM table build", e); }
@@ -1016,7 +1043,6 @@ int bn254_fr_poly_from_roots(bn254_ctx* ctx, const void* roots, size_t n, void* 
   memcpy(s.h, roots, n * 32);
   cudaError_t e = cudaMemcpyAsync(s.d, s.h, n * 32, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess) e = L::fr_poly_from_roots(s.d, n, s.d + off, s.stream);
-  ctx->launches++;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(s.h + off, s.d + off, (n + 1) * 32, cudaMemcpyDeviceToHost, s.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);

@@ -176,13 +176,13 @@ cudaError_t fr_poly_from_roots(const void* roots, size_t n, void* coeffs, cudaSt
   if (n == 0 || smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_fr_poly_from_roots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_fr_poly_from_roots<<<1, 1024, smem, s>>>(roots, (int)n, coeffs);
+  BN_LAUNCH, k_fr_poly_from_roots<<<1, 1024, smem, s>>>(roots, (int)n, coeffs);
   return cudaSuccess;
 }
 void fr_quotient_coeffs(const void* f, size_t n, const void* ids, size_t nvec, void* out, cudaStream_t s) {
-  k_fr_quotient_coeffs<<<(unsigned)((nvec * 32 + 127) / 128), 128, 0, s>>>(f, (int)n, ids, nvec, out);
+  BN_LAUNCH, k_fr_quotient_coeffs<<<(unsigned)((nvec * 32 + 127) / 128), 128, 0, s>>>(f, (int)n, ids, nvec, out);
 }
-void fr_to_scalars(const void* in, size_t n, void* out, cudaStream_t s) { k_fr_to_scalars<<<grid_for(n), kBlock, 0, s>>>(in, n, out); }
+void fr_to_scalars(const void* in, size_t n, void* out, cudaStream_t s) { BN_LAUNCH, k_fr_to_scalars<<<grid_for(n), kBlock, 0, s>>>(in, n, out); }
 
 // ---- host side: Lagrange basis of a whole set with one inversion ------------------------------------------------
 // out[i] = Delta_{s_i, S}(x) = prod_{j: s_j != s_i} (x - s_j) / (s_i - s_j)   (utils/compute_lagrange_basis.go:8-30:

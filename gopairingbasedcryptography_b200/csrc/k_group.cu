@@ -216,43 +216,43 @@ cudaError_t group_init() {
 }
 #define BY_GROUP(g, call1, call2) do { if ((g) == 1) { call1; } else { call2; } } while (0)
 void scalar_mul(int g, const void* base, size_t base_stride, const void* scalars, size_t n, void* out, cudaStream_t s) {
-  BY_GROUP(g, (k_scalar_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)),
-           (k_scalar_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_scalar_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)),
+           (BN_LAUNCH, k_scalar_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)));
 }
 void fixed_mul(int g, const void* table, const void* scalars, size_t n, void* out, cudaStream_t s) {
-  BY_GROUP(g, (k_fixed_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G1Aff*>(table), scalars, n, out)),
-           (k_fixed_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G2Aff*>(table), scalars, n, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_fixed_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G1Aff*>(table), scalars, n, out)),
+           (BN_LAUNCH, k_fixed_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G2Aff*>(table), scalars, n, out)));
 }
 void aff_add(int g, const void* a, const void* b, size_t n, void* out, cudaStream_t s) {
-  BY_GROUP(g, (k_aff_add<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(a, b, n, out)),
-           (k_aff_add<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(a, b, n, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_aff_add<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(a, b, n, out)),
+           (BN_LAUNCH, k_aff_add<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(a, b, n, out)));
 }
 void subset_sum(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, cudaStream_t s) {
-  BY_GROUP(g, (k_subset_sum<G1Jac, G1Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G1Aff), s>>>(static_cast<const G1Aff*>(U), m, sel, n, out)),
-           (k_subset_sum<G2Jac, G2Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G2Aff), s>>>(static_cast<const G2Aff*>(U), m, sel, n, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_subset_sum<G1Jac, G1Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G1Aff), s>>>(static_cast<const G1Aff*>(U), m, sel, n, out)),
+           (BN_LAUNCH, k_subset_sum<G2Jac, G2Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G2Aff), s>>>(static_cast<const G2Aff*>(U), m, sel, n, out)));
 }
 void segment_sum(int g, const void* pts, size_t groups, int len, int chunk, void* out, cudaStream_t s) {
   size_t threads = groups * (size_t)((len + chunk - 1) / chunk);
-  BY_GROUP(g, (k_segment_sum<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, groups, len, chunk, out)),
-           (k_segment_sum<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, groups, len, chunk, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_segment_sum<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, groups, len, chunk, out)),
+           (BN_LAUNCH, k_segment_sum<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, groups, len, chunk, out)));
 }
 void msm_tables(int g, const void* pts, size_t len, void* tables, void* zs, void* pf, cudaStream_t s) {
   size_t threads = len * (size_t)kMsmWindows;
-  BY_GROUP(g, (k_msm_tables<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G1Aff*>(tables), static_cast<Fp*>(zs), static_cast<Fp*>(pf))),
-           (k_msm_tables<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G2Aff*>(tables), static_cast<Fp2*>(zs), static_cast<Fp2*>(pf))));
+  BY_GROUP(g, (BN_LAUNCH, k_msm_tables<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G1Aff*>(tables), static_cast<Fp*>(zs), static_cast<Fp*>(pf))),
+           (BN_LAUNCH, k_msm_tables<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G2Aff*>(tables), static_cast<Fp2*>(zs), static_cast<Fp2*>(pf))));
 }
 void msm_partial(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s) {
   size_t threads = nvec * ((len + chunk - 1) / chunk);
-  BY_GROUP(g, (k_msm_partial<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
-           (k_msm_partial<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
+  BY_GROUP(g, (BN_LAUNCH, k_msm_partial<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
+           (BN_LAUNCH, k_msm_partial<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
 }
 void jac_sum(int g, const void* in, size_t groups, int len, int chunk, void* out_j, void* out_a, cudaStream_t s) {
   size_t threads = groups * (size_t)((len + chunk - 1) / chunk);
-  BY_GROUP(g, (k_jac_sum<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Jac*>(in), groups, len, chunk, static_cast<G1Jac*>(out_j), out_a)),
-           (k_jac_sum<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Jac*>(in), groups, len, chunk, static_cast<G2Jac*>(out_j), out_a)));
+  BY_GROUP(g, (BN_LAUNCH, k_jac_sum<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Jac*>(in), groups, len, chunk, static_cast<G1Jac*>(out_j), out_a)),
+           (BN_LAUNCH, k_jac_sum<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Jac*>(in), groups, len, chunk, static_cast<G2Jac*>(out_j), out_a)));
 }
 void neg_points(int g, const void* in, size_t n, void* out, cudaStream_t s) {
-  BY_GROUP(g, (k_neg_points<G1Aff><<<grid_for(n), kBlock, 0, s>>>(in, n, out)), (k_neg_points<G2Aff><<<grid_for(n), kBlock, 0, s>>>(in, n, out)));
+  BY_GROUP(g, (BN_LAUNCH, k_neg_points<G1Aff><<<grid_for(n), kBlock, 0, s>>>(in, n, out)), (BN_LAUNCH, k_neg_points<G2Aff><<<grid_for(n), kBlock, 0, s>>>(in, n, out)));
 }
 
 }  // namespace launch

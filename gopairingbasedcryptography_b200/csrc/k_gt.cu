@@ -83,17 +83,17 @@ cudaError_t gt_init() {
 }
 int gt_wave_threads(int sms) { return sms * BN254_MIN_BLOCKS * kBlock; }
 void gt_exp(int cyclo, const void* x, size_t x_stride, const void* k, size_t n, void* out, void* tabmem, cudaStream_t s) {
-  if (cyclo) k_gt_exp<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(x, x_stride, k, n, out, static_cast<Fp12*>(tabmem));
-  else k_gt_exp<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(x, x_stride, k, n, out, static_cast<Fp12*>(tabmem));
+  if (cyclo) BN_LAUNCH, k_gt_exp<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(x, x_stride, k, n, out, static_cast<Fp12*>(tabmem));
+  else BN_LAUNCH, k_gt_exp<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(x, x_stride, k, n, out, static_cast<Fp12*>(tabmem));
 }
 void gt_fixed_exp(const void* table, const void* k, size_t n, void* out, cudaStream_t s) {
-  k_gt_fixed_exp<<<grid_for(n), kBlock, kTowerSmem, s>>>(static_cast<const Fp12*>(table), k, n, out);
+  BN_LAUNCH, k_gt_fixed_exp<<<grid_for(n), kBlock, kTowerSmem, s>>>(static_cast<const Fp12*>(table), k, n, out);
 }
 void gt_mul(int mode, const void* a, size_t a_stride, const void* b, size_t b_stride, size_t n, void* out, cudaStream_t s) {
-  if (mode == 0) k_gt_mul<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
-  else k_gt_mul<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
+  if (mode == 0) BN_LAUNCH, k_gt_mul<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
+  else BN_LAUNCH, k_gt_mul<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
 }
-void fp_mul(const void* a, const void* b, size_t n, void* out, cudaStream_t s) { k_fp_mul<<<grid_for(n), kBlock, 0, s>>>(a, b, n, out); }
+void fp_mul(const void* a, const void* b, size_t n, void* out, cudaStream_t s) { BN_LAUNCH, k_fp_mul<<<grid_for(n), kBlock, 0, s>>>(a, b, n, out); }
 
 }  // namespace launch
 }  // namespace bn254

@@ -23,8 +23,8 @@ namespace launch {
 
 cudaError_t hash_init() { return cudaSuccess; }  // no tower scratch: launched without dynamic shared memory (G1: 90 registers, 5 CTAs per SM)
 void hash_to_curve(int g, const uint8_t* msgs, const uint64_t* off, size_t n, const uint8_t* dst, uint32_t dst_len, void* out, cudaStream_t s) {
-  if (g == 1) k_hash_to_curve<1><<<grid_for(n), kBlock, 0, s>>>(msgs, off, n, dst, dst_len, out);
-  else k_hash_to_curve<2><<<grid_for(n), kBlock, 0, s>>>(msgs, off, n, dst, dst_len, out);
+  if (g == 1) BN_LAUNCH, k_hash_to_curve<1><<<grid_for(n), kBlock, 0, s>>>(msgs, off, n, dst, dst_len, out);
+  else BN_LAUNCH, k_hash_to_curve<2><<<grid_for(n), kBlock, 0, s>>>(msgs, off, n, dst, dst_len, out);
 }
 
 }  // namespace launch

@@ -248,10 +248,10 @@ __global__ void k_gt_is_one(const void* x, size_t n, uint8_t* ok) {
 
 template <int MODE>
 void launch_multi_pair(const void* P, const void* Q, size_t n, int k, void* out, cudaStream_t s) {
-  if (k == 1) k_multi_pair_c<MODE, 1><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
-  else if (k == 2) k_multi_pair_c<MODE, 2><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
-  else if (k == 3) k_multi_pair_c<MODE, 3><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
-  else k_multi_pair<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, k, out);
+  if (k == 1) BN_LAUNCH, k_multi_pair_c<MODE, 1><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
+  else if (k == 2) BN_LAUNCH, k_multi_pair_c<MODE, 2><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
+  else if (k == 3) BN_LAUNCH, k_multi_pair_c<MODE, 3><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
+  else BN_LAUNCH, k_multi_pair<MODE><<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, k, out);
 }
 
 }  // namespace
@@ -277,7 +277,7 @@ cudaError_t pairing_init() {
 int pairing_wave_threads(int sms) { return sms * BN254_MIN_BLOCKS * kBlock; }
 
 void pair(const void* P, const void* Q, size_t n, void* out, cudaStream_t s) {
-  k_pair<<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
+  BN_LAUNCH, k_pair<<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
 }
 void multi_pair(int mode, const void* P, const void* Q, size_t n, int k, void* out, cudaStream_t s) {
   if (mode == 0) launch_multi_pair<0>(P, Q, n, k, out, s);
@@ -285,27 +285,27 @@ void multi_pair(int mode, const void* P, const void* Q, size_t n, int k, void* o
   else launch_multi_pair<2>(P, Q, n, k, out, s);
 }
 void mp_partial(const void* P, const void* Q, size_t n, int k, int nchunks, void* partial, cudaStream_t s) {
-  k_mp_partial<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(P, Q, n, k, nchunks, partial);
+  BN_LAUNCH, k_mp_partial<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(P, Q, n, k, nchunks, partial);
 }
 void mp_combine(int mode, const void* partial, size_t n, int nchunks, void* out, cudaStream_t s) {
-  if (mode == 0) k_mp_combine<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
-  else if (mode == 1) k_mp_combine<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
-  else k_mp_combine<2><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
+  if (mode == 0) BN_LAUNCH, k_mp_combine<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
+  else if (mode == 1) BN_LAUNCH, k_mp_combine<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
+  else BN_LAUNCH, k_mp_combine<2><<<grid_for(n), kBlock, kTowerSmem, s>>>(partial, n, nchunks, out);
 }
 void g2_lines(const void* Q, size_t m, void* table, uint8_t* qskip, cudaStream_t s) {
-  k_g2_lines<<<grid_for(m), kBlock, kTowerSmem, s>>>(Q, m, static_cast<Fp2*>(table), qskip);
+  BN_LAUNCH, k_g2_lines<<<grid_for(m), kBlock, kTowerSmem, s>>>(Q, m, static_cast<Fp2*>(table), qskip);
 }
 void miller_lines(const void* P, const void* table, const uint8_t* qskip, size_t n, int m, int nchunks, void* partial, cudaStream_t s) {
-  k_miller_lines<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(P, static_cast<const Fp2*>(table), qskip, n, m, nchunks, partial);
+  BN_LAUNCH, k_miller_lines<<<dim3(grid_for(n), (unsigned)nchunks), kBlock, kTowerSmem, s>>>(P, static_cast<const Fp2*>(table), qskip, n, m, nchunks, partial);
 }
-void final_exp(const void* in, size_t n, void* out, cudaStream_t s) { k_final_exp<<<grid_for(n), kBlock, kTowerSmem, s>>>(in, n, out); }
+void final_exp(const void* in, size_t n, void* out, cudaStream_t s) { BN_LAUNCH, k_final_exp<<<grid_for(n), kBlock, kTowerSmem, s>>>(in, n, out); }
 void check2_fixed_g1(const void* P01, const void* Q0, const void* Q1, size_t n, uint8_t* ok, cudaStream_t s) {
-  k_check2_fixed_g1<<<grid_for(n), kBlock, kTowerSmem, s>>>(P01, Q0, Q1, n, ok);
+  BN_LAUNCH, k_check2_fixed_g1<<<grid_for(n), kBlock, kTowerSmem, s>>>(P01, Q0, Q1, n, ok);
 }
 void pack_check2(const void* P01, const void* Q0, const void* Q1, size_t n, void* P, void* Q, cudaStream_t s) {
-  k_pack_check2<<<grid_for(n), kBlock, 0, s>>>(P01, Q0, Q1, n, P, Q);
+  BN_LAUNCH, k_pack_check2<<<grid_for(n), kBlock, 0, s>>>(P01, Q0, Q1, n, P, Q);
 }
-void gt_is_one(const void* x, size_t n, uint8_t* ok, cudaStream_t s) { k_gt_is_one<<<grid_for(n), kBlock, 0, s>>>(x, n, ok); }
+void gt_is_one(const void* x, size_t n, uint8_t* ok, cudaStream_t s) { BN_LAUNCH, k_gt_is_one<<<grid_for(n), kBlock, 0, s>>>(x, n, ok); }
 
 }  // namespace launch
 }  // namespace bn254

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(32 * kVmWarps) k_vm(const void* in0, const voi
   }
 }
 
+static_assert(kVmNP == launch::kVmPairingsPerCta, "launch.h out of date");
 static_assert(VmProgPair::ncold <= kVmColdSlots && VmProgMiller::ncold <= kVmColdSlots && VmProgFinalExp::ncold <= kVmColdSlots,
               "a generated program uses more cold slots than the global scratch reserves per pairing");
 
@@ -119,7 +120,7 @@ template <typename PROG>
 void vm_launch(const void* a, const void* b, size_t n, void* out, void* cold, int sms, int blocks_per_sm, cudaStream_t s) {
   size_t want = (n + kVmNP - 1) / kVmNP;
   unsigned grid = (unsigned)(want < (size_t)sms * blocks_per_sm ? want : (size_t)sms * blocks_per_sm);
-  k_vm<PROG><<<grid, 32 * kVmWarps, vm_smem_bytes<PROG>(), s>>>(a, b, n, out, static_cast<uint4*>(cold));
+  BN_LAUNCH, k_vm<PROG><<<grid, 32 * kVmWarps, vm_smem_bytes<PROG>(), s>>>(a, b, n, out, static_cast<uint4*>(cold));
 }
 
 }  // namespace

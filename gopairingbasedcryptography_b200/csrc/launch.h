@@ -6,7 +6,13 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace bn254 { namespace launch {
+
+// kernel launches issued by this library in this process (bn254_launch_count): every <<<>>> below counts one
+extern std::atomic<uint64_t> g_launches;
+#define BN_LAUNCH (::bn254::launch::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 constexpr int kBlockThreads = 128;        // CTA size of every thread kernel
 constexpr int kMpChunk = 8;               // pairs per thread in split multi-pairings
@@ -71,8 +77,14 @@ void fr_to_scalars_host(const void* in, size_t n, void* out);
 
 // ---- lane-group (tower VM) kernels ------------------------------------------------------------------------------
 enum { kVmPair = 0, kVmMiller = 1, kVmFinalExp = 2 };
+constexpr int kVmPairingsPerCta = 40;  // 4 warps x 10 lane groups of 3 (k_vm.cu asserts it)
 cudaError_t vm_prepare(int* blocks_per_sm /* [3] */);
 size_t vm_cold_bytes(int sms, const int* blocks_per_sm);
 void vm_run(int prog, const void* a, const void* b, size_t n, void* out, void* cold, int sms, const int* blocks_per_sm, cudaStream_t s);
+
+// ---- warp-VM kernels (k_wvm.cu): one warp per item, the latency path; same program ids as the lane-group kernels ----
+cudaError_t wvm_prepare(int* blocks_per_sm /* [3] */);
+int wvm_items_per_cta();
+void wvm_run(int prog, const void* a, const void* b, size_t n, void* out, int sms, const int* blocks_per_sm, cudaStream_t s);
 
 } }  // namespace bn254::launch

@@ -1,0 +1,141 @@
+// Warp-VM interpreter: ONE WARP per pairing, one Fp-level micro-op per lane per round (wvmgen.py).
+// Every Fp value is a 32-byte slot in the warp's shared-memory slice.  Three op classes, one class per round:
+//   MUL  d = (s0 +- s1) * (s2 +- s3)       operands canonical, the +- pre-additions unreduced (< 2p), Montgomery product
+//   LIN  d = sum_i c_i * s_i  (|c_i| <= 31, sum |c_i| <= 200, <= 15 terms)   9-limb accumulator, one small reduction
+//   INV  d = s0^(p-2)                      lane-local Fermat chain (one per final exponentiation)
+// A slot read in round r is never written in round r (the allocator recycles a slot only after the round of its last
+// use), so lanes need no ordering inside a round; one __syncwarp() separates rounds.
+//
+// Replaces (reference side): the same gnark calls as pairing.cuh -- bn254.Pair / MillerLoop / FinalExponentiation with
+// the 1-element slices of the reference's 60 call sites and the small batches of BASELINE configs 0 and 4.
+#pragma once
+#include "tower.cuh"
+
+namespace bn254 { namespace wvm {
+
+enum : unsigned { OP_NOP = 0, OP_MUL = 1, OP_LIN = 2, OP_INV = 3 };
+constexpr int kLanes = 32;
+
+#if defined(__CUDACC__)
+BN_D Fp ld_slot(const Fp* slots, unsigned s) { return fp_ld(slots[s]); }
+BN_D void st_slot(Fp* slots, unsigned s, const Fp& v) {
+  uint4* p = reinterpret_cast<uint4*>(&slots[s]);
+  const uint4* d = reinterpret_cast<const uint4*>(&v);
+  p[0] = d[0]; p[1] = d[1];
+}
+BN_D void round_sync() { __syncwarp(); }
+BN_D unsigned warp_max(unsigned x) { return __reduce_max_sync(0xffffffffu, x); }
+#else
+BN_D Fp ld_slot(const Fp* slots, unsigned s) { return slots[s]; }
+BN_D void st_slot(Fp* slots, unsigned s, const Fp& v) { slots[s] = v; }
+BN_D void round_sync() {}
+#endif
+
+// s (canonical) -> s or p - s; p - s lies in [1, p], which the unreduced pre-addition and the LIN accumulator accept
+BN_HD Fp cond_neg(const Fp& s, bool neg) {
+  Fp d;
+  d.l[0] = sub_cc(P0, s.l[0]); d.l[1] = subc_cc(P1, s.l[1]); d.l[2] = subc_cc(P2, s.l[2]); d.l[3] = subc_cc(P3, s.l[3]);
+  d.l[4] = subc_cc(P4, s.l[4]); d.l[5] = subc_cc(P5, s.l[5]); d.l[6] = subc_cc(P6, s.l[6]); d.l[7] = subc(P7, s.l[7]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) d.l[i] = neg ? d.l[i] : s.l[i];
+  return d;
+}
+
+// acc (9 limbs) += c * v, 0 <= c <= 31
+BN_HD void lin_acc(uint32_t* acc, const Fp& v, uint32_t c) {
+  uint64_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint64_t t = (uint64_t)v.l[k] * c + acc[k] + carry;
+    acc[k] = (uint32_t)t;
+    carry = t >> 32;
+  }
+  acc[8] += (uint32_t)carry;
+}
+// v (9 limbs, v < 256 p) -> v mod p, canonical.  Quotient estimate from the top bits as in fp_reduce_small (tower.cuh),
+// with the product widened to 64 bits: q_est in {q - 1, q}, so one conditional subtraction finishes.
+BN_HD Fp lin_reduce(const uint32_t* v) {
+  uint32_t hi = (v[8] << 11) | (v[7] >> 21);                 // floor(v / 2^245) < 2^17
+  uint32_t q = (uint32_t)(((uint64_t)hi * 43336u) >> 24);   // 43336 = floor(2^269 / p)
+  uint32_t qp[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += (uint64_t)q * p_limb(i); qp[i] = (uint32_t)c; c >>= 32; }
+  qp[8] = (uint32_t)c;
+  Fp w;
+  w.l[0] = sub_cc(v[0], qp[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) w.l[i] = subc_cc(v[i], qp[i]);
+  (void)subc(v[8], qp[8]);  // v - q p < 2p: the ninth limb is zero
+  fp_reduce_once(w);
+  return w;
+}
+BN_NOINLINE Fp fp_inv_wvm(Fp a) { return fp_inv(a); }
+
+// One op.  rec = 16 u16 fields in two uint4 (little-endian pairs).  Returns true when `out` must be stored to slot dst.
+// nmax: warp-uniform bound on the LIN term count of this round (so the term loop's exit is a uniform branch).
+BN_HD unsigned field(const uint4& w0, const uint4& w1, int i) {
+  const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  return (ws[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+}
+BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned nmax, unsigned& dst, Fp& out) {
+  const unsigned h = field(w0, w1, 0);
+  const unsigned op = h & 3u, x = h >> 12;
+  dst = (h >> 2) & 1023u;
+  if (op == OP_MUL) {
+    Fp a = ld_slot(slots, field(w0, w1, 1)), a1 = ld_slot(slots, field(w0, w1, 2));
+    Fp b = ld_slot(slots, field(w0, w1, 3)), b1 = ld_slot(slots, field(w0, w1, 4));
+    a = fp_add_noreduce(a, cond_neg(a1, (x & 1u) != 0));
+    b = fp_add_noreduce(b, cond_neg(b1, (x & 2u) != 0));
+    out = fp_mul(a, b);
+    return true;
+  }
+  if (op == OP_LIN) {
+    uint32_t acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+      if ((unsigned)i >= nmax) break;
+      unsigned f = field(w0, w1, 1 + i);
+      bool live = (unsigned)i < x;
+      int c = (int)(f >> 10);
+      c = c >= 32 ? c - 64 : c;
+      Fp v = ld_slot(slots, live ? (f & 1023u) : 0u);  // slot 0 holds zero
+      v = cond_neg(v, c < 0);
+      lin_acc(acc, v, live ? (uint32_t)(c < 0 ? -c : c) : 0u);
+    }
+    out = lin_reduce(acc);
+    return true;
+  }
+  if (op == OP_INV) {
+    out = fp_inv_wvm(ld_slot(slots, field(w0, w1, 1)));
+    return true;
+  }
+  return false;
+}
+
+// Run a program for the pairing this warp owns.  prog: rounds x 32 lanes x 2 uint4.
+BN_HD void run(Fp* slots, const uint4* __restrict__ prog, int rounds, int lane) {
+  const uint4* p = prog + (size_t)lane * 2;
+  uint4 w0 = p[0], w1 = p[1];
+  for (int r = 0; r < rounds; r++) {
+    uint4 n0 = w0, n1 = w1;
+    if (r + 1 < rounds) { n0 = p[(size_t)(r + 1) * kLanes * 2]; n1 = p[(size_t)(r + 1) * kLanes * 2 + 1]; }  // prefetch
+    unsigned h = w0.x & 0xFFFFu;
+    unsigned nterms = (h & 3u) == OP_LIN ? (h >> 12) : 0u;
+#if defined(__CUDACC__)
+    unsigned nmax = warp_max(nterms);
+#else
+    unsigned nmax = 15;
+#endif
+    unsigned dst = 0;
+    Fp out;
+    bool st = exec_op(slots, w0, w1, nmax, dst, out);
+    if (st) st_slot(slots, dst, out);
+    round_sync();
+    w0 = n0; w1 = n1;
+  }
+}
+
+} }  // namespace bn254::wvm

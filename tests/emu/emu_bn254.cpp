@@ -32,9 +32,9 @@ void emu_multi_pair(const void* P, const void* Q, size_t n, size_t k, int mode, 
 }
 void emu_final_exp(const void* in, size_t n, void* out) { for (size_t i = 0; i < n; i++) { Fp12 f = ld<Fp12>(in, i); final_exp(f, f); st(out, i, f); } }
 void emu_g1_mul(const void* base, size_t stride, const void* s, size_t n, void* out) {
-  for (size_t i = 0; i < n; i++) { G1Aff b = ld<G1Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); scalar_mul<G1Jac, G1Aff>(r, b, k); st(out, i, r); } }
+  for (size_t i = 0; i < n; i++) { G1Aff b = ld<G1Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); Fp beta = GLV_BETA; scalar_mul_glv<G1Jac, G1Aff>(r, b, k, beta); st(out, i, r); } }
 void emu_g2_mul(const void* base, size_t stride, const void* s, size_t n, void* out) {
-  for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); scalar_mul<G2Jac, G2Aff>(r, b, k); st(out, i, r); } }
+  for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32); Fp beta = GLV_BETA_G2; scalar_mul_glv<G2Jac, G2Aff>(r, b, k, beta); st(out, i, r); } }
 void emu_g1_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G1Aff r; aff_add<G1Jac, G1Aff>(r, ld<G1Aff>(a, i), ld<G1Aff>(b, i)); st(out, i, r); } }
 void emu_g2_add(const void* a, const void* b, size_t n, void* out) { for (size_t i = 0; i < n; i++) { G2Aff r; aff_add<G2Jac, G2Aff>(r, ld<G2Aff>(a, i), ld<G2Aff>(b, i)); st(out, i, r); } }
 void emu_gt_exp(const void* x, size_t stride, const void* s, size_t n, void* out) {
@@ -148,3 +148,59 @@ extern "C" void emu_hash_to_field(const unsigned char* msg, size_t len, const un
   Fp u[4]; hash_to_field<4>(u, msg, len, dst, (uint32_t)dst_len); for (int i = 0; i < 4; i++) st(out, i, u[i]); }
 
 extern "C" void emu_fp2_mul_xi(const void* a, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, fp2_mul_xi_i(ld<Fp2>(a, i))); }
+
+// ---- warp-VM programs (wvmgen.py / wvm.cuh) on the host: 32 lanes per round, all lanes load before any lane stores ----
+#include "../../gopairingbasedcryptography_b200/csrc/wvm.cuh"
+#include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_meta.cuh"
+namespace {
+const uint32_t kWvmMillerH[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_miller.inc"
+};
+const uint32_t kWvmFinalExpH[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_finalexp.inc"
+};
+void wvm_rounds(Fp* slots, const uint32_t* prog, int rounds) {
+  for (int r = 0; r < rounds; r++) {
+    unsigned dst[32]; Fp val[32]; bool st_[32];
+    for (int j = 0; j < 32; j++) {
+      uint4 w0, w1;
+      memcpy(&w0, prog + ((size_t)r * 32 + j) * 8, 16);
+      memcpy(&w1, prog + ((size_t)r * 32 + j) * 8 + 4, 16);
+      st_[j] = wvm::exec_op(slots, w0, w1, 15, dst[j], val[j]);
+    }
+    for (int j = 0; j < 32; j++) if (st_[j]) slots[dst[j]] = val[j];
+  }
+}
+}
+extern "C" {
+// mode 0: Miller loop, 1: pairing (Miller program, then the final-exponentiation program), 2: final exponentiation
+void emu_wvm(const void* in0, const void* in1, size_t n, int mode, void* out) {
+  using namespace wvm;
+  for (size_t i = 0; i < n; i++) {
+    Fp slots[1024];
+    memset(slots, 0, sizeof(slots));
+    Fp v[12];
+    if (mode != 2) {
+      for (int k = 0; k < MILLER_NCONST; k++) slots[MILLER_CONST_SLOT[k]] = MILLER_CONST_VAL[k];
+      memcpy(&slots[MILLER_IN[0]], (const char*)in0 + i * 64, 32);
+      memcpy(&slots[MILLER_IN[1]], (const char*)in0 + i * 64 + 32, 32);
+      for (int k = 0; k < 4; k++) memcpy(&slots[MILLER_IN[2 + k]], (const char*)in1 + i * 128 + k * 32, 32);
+      wvm_rounds(slots, kWvmMillerH, MILLER_ROUNDS);
+      for (int k = 0; k < 12; k++) v[k] = slots[MILLER_OUT[k]];
+    } else {
+      for (int k = 0; k < 12; k++) memcpy(&v[k], (const char*)in0 + i * 384 + k * 32, 32);
+    }
+    if (mode >= 1) {
+      for (int k = 0; k < FINALEXP_NCONST; k++) slots[FINALEXP_CONST_SLOT[k]] = FINALEXP_CONST_VAL[k];
+      for (int k = 0; k < 12; k++) slots[FINALEXP_IN[k]] = v[k];
+      wvm_rounds(slots, kWvmFinalExpH, FINALEXP_ROUNDS);
+      for (int k = 0; k < 12; k++) v[k] = slots[FINALEXP_OUT[k]];
+    }
+    memcpy((char*)out + i * 384, v, 384);
+  }
+}
+// the LIN reduction on its own: v = sum c_i * s_i over 9 limbs, any total below 256 p
+void emu_wvm_lin_reduce(const void* v9, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { uint32_t v[9]; memcpy(v, (const char*)v9 + i * 36, 36); st(out, i, wvm::lin_reduce(v)); }
+}
+}

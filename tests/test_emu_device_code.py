@@ -23,6 +23,9 @@ CSRC = os.path.join(HERE, "..", "gopairingbasedcryptography_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
+    from gopairingbasedcryptography_b200 import _build
+
+    _build.ensure_generated()  # the warp-VM programs are generated sources
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL"] + EMU_FLAGS +
@@ -260,3 +263,66 @@ def test_xi_multiplication_fast_path(emu):
     for i, (x, y) in enumerate(pairs):
         e = o.fp2_mul_xi((x, y))
         assert z[64 * i:64 * i + 64].tobytes() == o.fp_to_mont_bytes(e[0]) + o.fp_to_mont_bytes(e[1]), (x, y)
+
+
+def test_warp_vm_programs_on_host(emu):
+    """The warp-VM (one warp per pairing, Fp-level ops: wvmgen.py programs run by wvm.cuh's exec_op) with lock-step
+    round semantics: Miller-only + final-exp-only == pairing == oracle, final exponentiation of an arbitrary Fp12."""
+    n = 3
+    P, Q, _, _ = common.points(n, seed=321)
+    ref = port.pair_batch(P, Q, n)
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_wvm(vp(P), vp(Q), sz(n), 1, vp(out))
+    assert (out == ref).all()
+    ml = np.zeros(384 * n, np.uint8)
+    emu.emu_wvm(vp(P), vp(Q), sz(n), 0, vp(ml))
+    fe = np.zeros(384 * n, np.uint8)
+    emu.emu_wvm(vp(ml), None, sz(n), 2, vp(fe))
+    assert (fe == ref).all()
+    assert (port.final_exp_batch(ml, n) == ref).all()  # the Miller value itself is a valid input of the oracle's FE
+    rng = o.SplitMix64(78)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(12)), dtype=np.uint8).copy()
+    emu.emu_wvm(vp(x), None, sz(1), 2, vp(fe))
+    assert (fe[:384] == port.final_exp_batch(x, 1)).all()
+
+
+def test_warp_vm_lin_reduction_bounds(emu):
+    """lin_reduce accepts any 9-limb v < 256 p: multiples of p and their neighbours up to the bound, and random values."""
+    rng = o.SplitMix64(79)
+    vals = []
+    for q in list(range(0, 256, 5)) + [1, 2, 199, 200, 254, 255]:
+        for d in (-1, 0, 1, o.P - 1, rng.fp()):
+            v = q * o.P + d
+            if 0 <= v < 256 * o.P:
+                vals.append(v)
+    vals += [rng.u256() * 256 % (256 * o.P) for _ in range(5000)]
+    buf = np.frombuffer(b"".join(v.to_bytes(36, "little") for v in vals), dtype=np.uint8).copy()
+    out = np.zeros(32 * len(vals), np.uint8)
+    emu.emu_wvm_lin_reduce(vp(buf), sz(len(vals)), vp(out))
+    got = [int.from_bytes(out[32 * i:32 * i + 32].tobytes(), "little") for i in range(len(vals))]
+    assert got == [v % o.P for v in vals]
+
+
+def test_warp_vm_python_evaluator_matches_oracle():
+    """wvmgen's own integer evaluator on the scheduled programs (independent of the C++ interpreter)."""
+    import sys
+
+    sys.path.insert(0, CSRC)
+    import wvmgen as w
+
+    rng = o.SplitMix64(6)
+    Pt, Qt = o.g1_mul(o.G1_GEN, rng.scalar()), o.g2_mul(o.G2_GEN, rng.scalar())
+    words, meta = w.build("miller")
+    init = {s: v for s, v in meta["consts"]}
+    ins = meta["in_slots"]
+    init.update({ins[0]: Pt[0], ins[1]: Pt[1], ins[2]: Qt[0][0], ins[3]: Qt[0][1], ins[4]: Qt[1][0], ins[5]: Qt[1][1]})
+    slots = w.evaluate(words, meta["nslots"], init)
+    ml = [slots[s] for s in meta["out_slots"]]
+    words, meta = w.build("finalexp")
+    init = {s: v for s, v in meta["consts"]}
+    init.update({s: v for s, v in zip(meta["in_slots"], ml)})
+    slots = w.evaluate(words, meta["nslots"], init)
+    got = [slots[s] for s in meta["out_slots"]]
+    e = o.pair([Pt], [Qt])
+    want = [e[c][b][a] for c in (0, 1) for b in (0, 1, 2) for a in (0, 1)]
+    assert got == want
