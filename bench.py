@@ -260,7 +260,7 @@ def main():
     strong = {"workload": "ONE batch of 2^%d pairs split over %d GPU(s): %d pairs per GPU" % (args.log2_batch, world, ns),
               "value": ns * world / (strong_ms * 1e-3), "unit": UNIT, "ms_per_step": strong_ms,
               "efficiency_vs_weak": (ns * world / (strong_ms * 1e-3)) / value,
-              "note": "per-GPU remainder (batch mod one wave of %d threads) goes to the lane-group kernel when it is under 55 %% of a wave" % (148 * 3 * 128)}
+              "note": "CTAs are scheduled one by one, so a part-filled last wave costs its share only (2^17 pairs: 45.9 ms against 43.1 ideal)"}
 
     # ---- end to end through the host-buffer API --------------------------------------------------
     hP_np, hQ_np = hP.numpy(), hQ.numpy()

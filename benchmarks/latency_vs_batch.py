@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Device-resident time of pair / miller(k=1) / final_exp for small batches: thread kernels vs lane-group (VM) kernels.
-   python benchmarks/latency_vs_batch.py  -> one JSON line per (impl, op, n); decides the small-batch routing threshold."""
+"""Device-resident time of pair / miller(k=1) / final_exp for small batches: thread kernels, lane-group (K = 3 VM) kernels,
+warp-VM kernels (one warp per item) and the default context's automatic routing.
+   python benchmarks/latency_vs_batch.py  -> one JSON line per (impl, n); decides the small-batch routing thresholds."""
 import json
 import os
 import sys
@@ -18,7 +19,10 @@ os.environ["BN254_IMPL"] = "thread"
 engs["thread"] = bn254.Engine(0)
 os.environ["BN254_IMPL"] = "vm"
 engs["vm"] = bn254.Engine(0)
+os.environ["BN254_IMPL"] = "wvm"
+engs["wvm"] = bn254.Engine(0)
 os.environ.pop("BN254_IMPL", None)
+engs["auto"] = bn254.Engine(0)
 rng = o.SplitMix64(5)
 N = 1 << 16
 sb = bn254.scalars_to_bytes([rng.scalar() for _ in range(4096)])
@@ -47,8 +51,10 @@ def t(fn):
     return a.elapsed_time(b) / 3
 
 
-for n in (64, 256, 1024, 4096, 8192, 16384, 32768, 65536):
+for n in (1, 64, 192, 1024, 2048, 3072, 4096, 6144, 8192, 16384, 32768, 65536):
     for name, eng in engs.items():
+        if (name == "wvm" and n > 16384) or (name == "thread" and n < 64):
+            continue
         r = {"impl": name, "n": n,
              "pair_ms": round(t(lambda: eng.pair_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, dO.data_ptr(), s)), 3),
              "miller_ms": round(t(lambda: eng.miller_loop_batch_dev(dP.data_ptr(), dQ.data_ptr(), n, 1, dO.data_ptr(), s)), 3),

@@ -201,7 +201,7 @@ def measure_rows(eng, peak, rank=0, world=1, dist=None, quick=False, cpu=True):
     add("gt_fixed_exp", "exps/s", ng, ds, es, ng * 32, ng * 384, base_gt, "GT.Exp of ONE base (waters05 e(g1,g2)^alpha): fixed-base table handle")
 
     # ---- BLS verify (BASELINE metric: BLS verifies/sec) ----------------------------------------------------------
-    nb = 1 << (12 if quick else 16)
+    nb = 1 << (12 if quick else 17)  # 2.3 waves: a part-filled last wave is part of any real batch
     sk = sb[:1]
     pk = eng.g1_fixed_mul_batch(t_g1, sk)[0]
     hm = Qn[:nb]

@@ -276,20 +276,9 @@ cudaError_t vm_any(bn254_ctx* ctx, Scratch& sc, int prog, const void* a, const v
 // ---- launch sequences shared by the host-buffer and device-pointer entry points ---------------------------------
 cudaError_t seq_pair(bn254_ctx* ctx, Scratch& sc, const void* P, const void* Q, size_t n, void* out) {
   if (use_vm(ctx, n)) return vm_any(ctx, sc, L::kVmPair, P, Q, n, out);
-  // Remainder-aware split (strong scaling: 2^20 pairs over 8 GPUs = 2.31 waves of one-thread-per-pairing CTAs, and a
-  // third, 31 %-full wave costs as much as a full one): whole waves go to the thread kernel, a SMALL remainder to the
-  // lane-group kernel, whose three-lanes-per-pairing passes finish a partial wave in ~1/3 of a thread-kernel wave.
-  // Only when the remainder fits ONE pass of the lane-group grid (measured: at 2^20 = 18 waves + 25 600 the two passes
-  // the remainder needs cost 8 ms more than the 19th partial wave; at 2^17 = 2 waves + 17 408 one pass saves a third wave).
-  const size_t wave = (size_t)L::pairing_wave_threads(ctx->sms);
-  const size_t rem = n % wave;
-  const size_t vm_pass = (size_t)ctx->sms * ctx->vm_blocks_per_sm[L::kVmPair] * L::kVmPairingsPerCta;
-  if (ctx->vm_mode == 0 && !sc.slot && n > wave && rem > 0 && rem <= vm_pass) {
-    const size_t whole = n - rem;
-    L::pair(P, Q, whole, out, sc.stream);
-    return vm_dev(ctx, L::kVmPair, static_cast<const char*>(P) + whole * BN254_G1_BYTES, static_cast<const char*>(Q) + whole * BN254_G2_BYTES, rem,
-                  static_cast<char*>(out) + whole * BN254_GT_BYTES, sc.stream);
-  }
+  // (A remainder-aware split -- whole waves on the thread kernel, the remainder on the lane-group kernel -- was measured
+  // and dropped: CTAs are scheduled one by one, not wave by wave, so 2^17 pairs = 2.31 "waves" take 45.9 ms, not three
+  // waves' 53 ms, and the split version took 48.2 ms.  profiles/r2/strong_scaling_split.jsonl)
   L::pair(P, Q, n, out, sc.stream);
   return cudaSuccess;
 }
@@ -370,6 +359,17 @@ cudaError_t seq_gt_exp(bn254_ctx* ctx, Scratch& sc, int cyclo, const void* x, si
     L::gt_exp(cyclo, static_cast<const char*>(x) + off * stride * BN254_GT_BYTES, stride, static_cast<const char*>(k) + off * BN254_SCALAR_BYTES, c,
               static_cast<char*>(out) + off * BN254_GT_BYTES, tab, sc.stream);
   }
+  return cudaSuccess;
+}
+// Waters hash: plain subset sum for small batches, byte-window tables (built per call, 8192 short sums) from 2048 selectors on
+constexpr size_t kSubsetTabMin = 2048;
+cudaError_t seq_subset_sum(bn254_ctx*, Scratch& sc, int g, const void* U, int m, const uint8_t* sel, size_t n, void* out) {
+  if (n < kSubsetTabMin || m < 16) { L::subset_sum(g, U, m, sel, n, out, sc.stream); return cudaSuccess; }
+  size_t need = (size_t)((m + 7) / 8) * 256 * pt_bytes(g);
+  void* table;
+  cudaError_t e;
+  if ((e = sc.reserve(al256(need))) != cudaSuccess || (e = sc.get(need, &table)) != cudaSuccess) return e;
+  L::subset_sum_tab(g, U, m, sel, n, out, table, sc.stream);
   return cudaSuccess;
 }
 // out[g] = sum of `len` consecutive affine points per group: passes of 32-way partial sums
@@ -576,9 +576,10 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   ctx->vm_mode = !impl ? 0 : (std::string(impl) == "vm" ? 1 : (std::string(impl) == "thread" ? 2 : (std::string(impl) == "wvm" ? 3 : 0)));
   ctx->sms = prop.multiProcessorCount;
   if (L::vm_prepare(ctx->vm_blocks_per_sm) != cudaSuccess || L::wvm_prepare(ctx->wvm_blocks_per_sm) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
-  {  // crossover to the lane-group kernels: about two passes of the warp-VM grid (profiles/r2/latency_vs_batch.jsonl)
+  {  // crossover to the lane-group kernels: one pass of the warp-VM grid, 148 SMs x 4 CTAs x 4 warps = 2368 items
+     // (profiles/r2/latency_vs_batch.jsonl: 2048 items 4.2 ms vs 5.8 ms, 3072 items 6.1 ms vs 5.8 ms)
     const char* wm = getenv("BN254_WVM_MAX");
-    ctx->wvm_auto_max = wm ? (size_t)atol(wm) : (size_t)2 * ctx->sms * ctx->wvm_blocks_per_sm[L::kVmPair] * L::wvm_items_per_cta();
+    ctx->wvm_auto_max = wm ? (size_t)atol(wm) : (size_t)ctx->sms * ctx->wvm_blocks_per_sm[L::kVmPair] * L::wvm_items_per_cta();
   }
   size_t cb = L::vm_cold_bytes(ctx->sms, ctx->vm_blocks_per_sm);
   if (cudaMalloc(&ctx->vm_cold_dev, cb) != cudaSuccess || cudaMalloc(&ctx->slot[0].vm_cold, cb) != cudaSuccess ||
@@ -905,16 +906,15 @@ int bn254_msm_batch_dev(bn254_ctx* ctx, const bn254_msm_table* T, const void* d_
     if (!ctx || !U || m == 0 || (m + 1) * BYTES > L::subset_sum_max_bytes()) return fail(ctx, BN254_ERR_BAD_ARG, "bad subset-sum arguments"); \
     int mm = (int)m;                                                                                                     \
     return run_host(ctx, {{U, (m + 1) * BYTES, true}, {sel, (m + 7) / 8, false}}, out, BYTES, n,                         \
-                    [mm](const void* const* d, size_t c, void* o, Slot& sl) {                                            \
-                      L::subset_sum(G, d[0], mm, static_cast<const uint8_t*>(d[1]), c, o, sl.stream);                    \
-                      return cudaSuccess;                                                                                \
+                    [mm, ctx](const void* const* d, size_t c, void* o, Slot& sl) {                                       \
+                      Scratch sc; sc.slot = &sl; sc.stream = sl.stream;                                                  \
+                      return seq_subset_sum(ctx, sc, G, d[0], mm, static_cast<const uint8_t*>(d[1]), c, o);              \
                     });                                                                                                  \
   }                                                                                                                      \
   int name##_dev(bn254_ctx* ctx, const void* dU, size_t m, const void* d_sel, size_t n, void* d_out, void* stream) {     \
     if (!ctx || !dU || m == 0 || (m + 1) * BYTES > L::subset_sum_max_bytes()) return fail(ctx, BN254_ERR_BAD_ARG, "bad subset-sum arguments"); \
     return run_dev(ctx, n, stream, [&](Scratch& sc) {                                                                    \
-      L::subset_sum(G, dU, (int)m, static_cast<const uint8_t*>(d_sel), n, d_out, sc.stream);                             \
-      return cudaSuccess;                                                                                                \
+      return seq_subset_sum(ctx, sc, G, dU, (int)m, static_cast<const uint8_t*>(d_sel), n, d_out);                       \
     });                                                                                                                  \
   }
 SUBSET_SUM_ENTRY(bn254_g1_subset_sum_batch, 1, BN254_G1_BYTES)

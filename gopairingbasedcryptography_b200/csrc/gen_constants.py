@@ -169,6 +169,7 @@ def main():
         w("static constexpr uint32_t P%d = 0x%08xu;" % (i, (P >> (32 * i)) & 0xFFFFFFFF))
     w("static constexpr uint32_t P_INV32 = 0x%08xu;  // -p^-1 mod 2^32" % ((-pow(P, -1, 1 << 32)) % (1 << 32)))
     w("#define BN254_FP_ONE %s" % fp_init(1))
+    w("#define BN254_FP_R3 %s  // R^3 mod p as plain limbs: (x R)^-1 * R^3 / R = x^-1 R (binary inversion, wvm.cuh)" % fp_init(pow(2, 512, P)))
     w("#define BN254_FP_R2 {{%s}}" % limbs32(MONT * MONT % P))
     w("BN_CONST uint32_t FP_PM2[8] = {%s};  // p-2, inversion exponent" % limbs32(P - 2))
     for i in range(16):

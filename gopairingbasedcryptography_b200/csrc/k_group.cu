@@ -76,6 +76,50 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum(const A
   jac_to_aff(r, acc);
   store_struct(out, i, r);
 }
+// Byte-window form of the same subset sum for large batches: table[b * 256 + v] = sum of the points U[1 + 8b + i] whose
+// bit (7 - i) is set in v (affine; v = 0 -> infinity), built once per call by 256 threads per selector byte; an
+// identity then costs ceil(m/8) mixed additions instead of ~m/2 (Waters05, m = 256: 32 instead of ~128).
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_table(const A* U, int m, A* table) {
+  cta_lockstep_set(false);
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int nbytes = (m + 7) / 8;
+  if (t >= nbytes * 256) return;
+  int b = t >> 8, v = t & 255;
+  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
+  for (int i = 0; i < 8; i++) {
+    int j = 8 * b + i;
+    if (j < m && ((v >> (7 - i)) & 1)) {
+      A e = U[j + 1];
+      if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+    }
+  }
+  A r;
+  jac_to_aff(r, acc);
+  table[t] = r;
+}
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum_tab(const A* U, const A* __restrict__ table, int m, const uint8_t* sel, size_t n, void* out) {
+  cta_lockstep_set(false);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int nbytes = (m + 7) / 8;
+  const uint8_t* bits = sel + i * (size_t)nbytes;
+  J acc;
+  A u0 = U[0];
+  if (aff_is_inf(u0)) { f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z); }
+  else { acc.x = u0.x; acc.y = u0.y; f_set_one(acc.z); }
+  for (int b = 0; b < nbytes; b++) {
+    int v = bits[b];
+    if (v) {
+      A e; load_struct(e, table, (size_t)b * 256 + v);
+      if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+    }
+  }
+  A r;
+  jac_to_aff(r, acc);
+  store_struct(out, i, r);
+}
 // out[g] = sum of the `len` consecutive points of group g, processed as ceil(len/32)-way partial sums per pass
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const void* pts, size_t groups, int len, int chunk, void* out) {
@@ -230,6 +274,13 @@ void aff_add(int g, const void* a, const void* b, size_t n, void* out, cudaStrea
 void subset_sum(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, cudaStream_t s) {
   BY_GROUP(g, (BN_LAUNCH, k_subset_sum<G1Jac, G1Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G1Aff), s>>>(static_cast<const G1Aff*>(U), m, sel, n, out)),
            (BN_LAUNCH, k_subset_sum<G2Jac, G2Aff><<<grid_for(n), kBlock, (size_t)(m + 1) * sizeof(G2Aff), s>>>(static_cast<const G2Aff*>(U), m, sel, n, out)));
+}
+void subset_sum_tab(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, void* table, cudaStream_t s) {
+  int tt = ((m + 7) / 8) * 256;
+  BY_GROUP(g, (BN_LAUNCH, k_subset_table<G1Jac, G1Aff><<<grid_for(tt), kBlock, 0, s>>>(static_cast<const G1Aff*>(U), m, static_cast<G1Aff*>(table))),
+           (BN_LAUNCH, k_subset_table<G2Jac, G2Aff><<<grid_for(tt), kBlock, 0, s>>>(static_cast<const G2Aff*>(U), m, static_cast<G2Aff*>(table))));
+  BY_GROUP(g, (BN_LAUNCH, k_subset_sum_tab<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G1Aff*>(U), static_cast<const G1Aff*>(table), m, sel, n, out)),
+           (BN_LAUNCH, k_subset_sum_tab<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G2Aff*>(U), static_cast<const G2Aff*>(table), m, sel, n, out)));
 }
 void segment_sum(int g, const void* pts, size_t groups, int len, int chunk, void* out, cudaStream_t s) {
   size_t threads = groups * (size_t)((len + chunk - 1) / chunk);

@@ -48,6 +48,8 @@ void scalar_mul(int g, const void* base, size_t base_stride, const void* scalars
 void fixed_mul(int g, const void* table, const void* scalars, size_t n, void* out, cudaStream_t s);
 void aff_add(int g, const void* a, const void* b, size_t n, void* out, cudaStream_t s);
 void subset_sum(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, cudaStream_t s);
+// byte-window form: builds table (ceil(m/8) x 256 affine points, caller scratch) then ceil(m/8) additions per selector
+void subset_sum_tab(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, void* table, cudaStream_t s);
 void segment_sum(int g, const void* pts, size_t groups, int len, int chunk, void* out, cudaStream_t s);
 size_t subset_sum_max_bytes();
 // shared-point MSM: out[v] = sum_j [s[v*len + j]] P_j over per-point window tables (built by msm_tables)

@@ -1,8 +1,8 @@
 // Warp-VM interpreter: ONE WARP per pairing, one Fp-level micro-op per lane per round (wvmgen.py).
 // Every Fp value is a 32-byte slot in the warp's shared-memory slice.  Three op classes, one class per round:
 //   MUL  d = (s0 +- s1) * (s2 +- s3)       operands canonical, the +- pre-additions unreduced (< 2p), Montgomery product
-//   LIN  d = sum_i c_i * s_i  (|c_i| <= 31, sum |c_i| <= 200, <= 15 terms)   9-limb accumulator, one small reduction
-//   INV  d = s0^(p-2)                      lane-local Fermat chain (one per final exponentiation)
+//   LIN  d = sum_i c_i * s_i  (|c_i| <= 31, sum |c_i| <= 120, <= 15 terms)   carry-free column sums, one small reduction
+//   INV  d = s0^-1                         lane-local binary extended Euclid (one per final exponentiation)
 // A slot read in round r is never written in round r (the allocator recycles a slot only after the round of its last
 // use), so lanes need no ordering inside a round; one __syncwarp() separates rounds.
 //
@@ -31,7 +31,7 @@ BN_D void st_slot(Fp* slots, unsigned s, const Fp& v) { slots[s] = v; }
 BN_D void round_sync() {}
 #endif
 
-// s (canonical) -> s or p - s; p - s lies in [1, p], which the unreduced pre-addition and the LIN accumulator accept
+// s (canonical) -> s or p - s; p - s lies in [1, p], which the unreduced pre-addition of a MUL operand accepts
 BN_HD Fp cond_neg(const Fp& s, bool neg) {
   Fp d;
   d.l[0] = sub_cc(P0, s.l[0]); d.l[1] = subc_cc(P1, s.l[1]); d.l[2] = subc_cc(P2, s.l[2]); d.l[3] = subc_cc(P3, s.l[3]);
@@ -41,20 +41,26 @@ BN_HD Fp cond_neg(const Fp& s, bool neg) {
   return d;
 }
 
-// acc (9 limbs) += c * v, 0 <= c <= 31
-BN_HD void lin_acc(uint32_t* acc, const Fp& v, uint32_t c) {
-  uint64_t carry = 0;
+// LIN accumulator: eight independent 64-bit column sums (no carry chain between limbs: a lone warp has nothing else
+// to hide a dependent chain behind).  A negative term c * v enters as |c| * ~v (per-limb complement) and the count
+// K = sum |c| over the negative terms is kept: sum |c| ~v = K (2^256 - 1) - sum |c| v, corrected once at the end.
+// The accumulator starts at 128 p, so the total stays positive: 0 < 128 p + sum c_i s_i < 256 p  (sum |c_i| <= 120).
+struct LinAcc { uint64_t col[8]; uint32_t k; };
+BN_HD void lin_init(LinAcc& a) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    uint64_t t = (uint64_t)v.l[k] * c + acc[k] + carry;
-    acc[k] = (uint32_t)t;
-    carry = t >> 32;
-  }
-  acc[8] += (uint32_t)carry;
+  for (int i = 0; i < 8; i++) a.col[i] = (uint64_t)p_limb(i) << 7;  // 128 p, limb by limb (carries resolved at the end)
+  a.k = 0;
 }
-// v (9 limbs, v < 256 p) -> v mod p, canonical.  Quotient estimate from the top bits as in fp_reduce_small (tower.cuh),
-// with the product widened to 64 bits: q_est in {q - 1, q}, so one conditional subtraction finishes.
-BN_HD Fp lin_reduce(const uint32_t* v) {
+BN_HD void lin_acc(LinAcc& a, const Fp& v, int c) {
+  const uint32_t mask = c < 0 ? 0xFFFFFFFFu : 0u;
+  const uint32_t m = (uint32_t)(c < 0 ? -c : c);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.col[i] += (uint64_t)(v.l[i] ^ mask) * m;
+  a.k += mask & m;
+}
+// columns -> 9 limbs, minus K (2^256 - 1), reduced mod p.  Quotient estimate from the top bits as in fp_reduce_small
+// (tower.cuh) with the product widened to 64 bits: for v < 256 p, q_est is q or q - 1, one conditional subtraction ends it.
+BN_HD Fp lin_reduce9(const uint32_t* v) {
   uint32_t hi = (v[8] << 11) | (v[7] >> 21);                 // floor(v / 2^245) < 2^17
   uint32_t q = (uint32_t)(((uint64_t)hi * 43336u) >> 24);   // 43336 = floor(2^269 / p)
   uint32_t qp[9];
@@ -70,7 +76,56 @@ BN_HD Fp lin_reduce(const uint32_t* v) {
   fp_reduce_once(w);
   return w;
 }
-BN_NOINLINE Fp fp_inv_wvm(Fp a) { return fp_inv(a); }
+BN_HD Fp lin_finish(const LinAcc& a) {
+  uint32_t v[9];
+  uint64_t c = a.k;  // + K
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += a.col[i]; v[i] = (uint32_t)c; c >>= 32; }
+  v[8] = (uint32_t)c - a.k;  // - K 2^256
+  return lin_reduce9(v);
+}
+
+// Inversion for the warp-VM: binary extended Euclid on one lane (variable time is free here -- the other lanes idle
+// during the INV round either way) instead of the 380 dependent Montgomery products of the Fermat chain.
+//   input a R (Montgomery form) -> (a R)^-1 mod p by Stein's algorithm -> times R^3 / R = a^-1 R.   inv(0) = 0.
+BN_HD bool u256_is_one(const uint32_t* x) { uint32_t o = x[0] ^ 1u; for (int i = 1; i < 8; i++) o |= x[i]; return o == 0; }
+BN_HD bool u256_geq(const uint32_t* a, const uint32_t* b) {
+  for (int i = 7; i >= 0; i--) if (a[i] != b[i]) return a[i] > b[i];
+  return true;
+}
+BN_HD void u256_sub(uint32_t* a, const uint32_t* b) {
+  uint64_t bw = 0;
+  for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - b[i] - bw; a[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+}
+BN_HD void u256_half_mod(uint32_t* x) {  // x / 2 mod p for x < p
+  uint64_t c = 0;
+  uint32_t t[9];
+  uint32_t odd = 0u - (x[0] & 1u);
+  for (int i = 0; i < 8; i++) { c += (uint64_t)x[i] + (p_limb(i) & odd); t[i] = (uint32_t)c; c >>= 32; }
+  t[8] = (uint32_t)c;
+  for (int i = 0; i < 8; i++) x[i] = (t[i] >> 1) | (t[i + 1] << 31);
+}
+BN_HD void u256_sub_mod(uint32_t* a, const uint32_t* b) {  // a - b mod p, a, b < p
+  uint64_t bw = 0;
+  for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - b[i] - bw; a[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+  if (bw) { uint64_t c = 0; for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + p_limb(i); a[i] = (uint32_t)c; c >>= 32; } }
+}
+BN_NOINLINE Fp fp_inv_wvm(Fp a) {
+  if (fp_is_zero(a)) return a;
+  uint32_t u[8], v[8], x1[8], x2[8];
+  for (int i = 0; i < 8; i++) { u[i] = a.l[i]; v[i] = p_limb(i); x1[i] = i == 0; x2[i] = 0; }
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1u)) { for (int i = 0; i < 7; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31); u[7] >>= 1; u256_half_mod(x1); }
+    while (!(v[0] & 1u)) { for (int i = 0; i < 7; i++) v[i] = (v[i] >> 1) | (v[i + 1] << 31); v[7] >>= 1; u256_half_mod(x2); }
+    if (u256_geq(u, v)) { u256_sub(u, v); u256_sub_mod(x1, x2); }
+    else { u256_sub(v, u); u256_sub_mod(x2, x1); }
+  }
+  Fp r;
+  const uint32_t* x = u256_is_one(u) ? x1 : x2;
+  for (int i = 0; i < 8; i++) r.l[i] = x[i];
+  Fp r3 = BN254_FP_R3;
+  return fp_mul(r, r3);  // (a R)^-1 * R^3 / R = a^-1 R
+}
 
 // One op.  rec = 16 u16 fields in two uint4 (little-endian pairs).  Returns true when `out` must be stored to slot dst.
 // nmax: warp-uniform bound on the LIN term count of this round (so the term loop's exit is a uniform branch).
@@ -91,9 +146,8 @@ BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned n
     return true;
   }
   if (op == OP_LIN) {
-    uint32_t acc[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) acc[k] = 0;
+    LinAcc acc;
+    lin_init(acc);
 #pragma unroll
     for (int i = 0; i < 15; i++) {
       if ((unsigned)i >= nmax) break;
@@ -102,10 +156,9 @@ BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned n
       int c = (int)(f >> 10);
       c = c >= 32 ? c - 64 : c;
       Fp v = ld_slot(slots, live ? (f & 1023u) : 0u);  // slot 0 holds zero
-      v = cond_neg(v, c < 0);
-      lin_acc(acc, v, live ? (uint32_t)(c < 0 ? -c : c) : 0u);
+      lin_acc(acc, v, live ? c : 0);
     }
-    out = lin_reduce(acc);
+    out = lin_finish(acc);
     return true;
   }
   if (op == OP_INV) {

@@ -30,12 +30,12 @@ P = g.P
 LANES = 32
 TMAX = int(os.environ.get("WVM_TMAX", "8"))       # terms per LIN op (encoding limit: 15); 8 measured best by the cost model
 CMAX = 31                                         # |coefficient| limit (6-bit signed field)
-CSUM_MAX = 200                                    # sum |c| per LIN: accumulator stays below 256 p
+CSUM_MAX = 120                                    # sum |c| per LIN: 128 p + sum c_i s_i stays inside (0, 256 p)
 SHARE = os.environ.get("WVM_SHARE", "1") == "1"   # materialise values with several consumers instead of inlining their forms
 POLICY = os.environ.get("WVM_POLICY", "fill12")
 SHARE_MIN = int(os.environ.get("WVM_SHARE_MIN", "3"))  # ... when the form has at least this many terms
 OP_NOP, OP_MUL, OP_LIN, OP_INV = 0, 1, 2, 3
-COST = {OP_MUL: 1.0, OP_LIN: 0.8, OP_INV: 330.0}
+COST = {OP_MUL: 1.0, OP_LIN: 0.35, OP_INV: 40.0}
 INV2 = pow(2, -1, P)
 
 

@@ -391,30 +391,64 @@ class Waters05Params:
         self.dev = torch.device("cuda", engine.device)
         with torch.cuda.device(self.dev):
             self.d_U = _up(U, torch, self.dev)
+            self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
             torch.cuda.synchronize()
+        self._out = None
+
+    def pinned_out(self, n):
+        """Page-locked result buffers (c1, c2, c3), grown on demand and reused by every call."""
+        torch = _torch()
+        if self._out is None or self._out[0].shape[0] < n:
+            self._out = tuple(torch.empty((n, w), dtype=torch.uint8).pin_memory() for w in (GT_BYTES, G1_BYTES, G2_BYTES))
+        return self._out
 
 
-def waters05_encrypt_batch_dev(params, ids, msgs, ts):
+def waters05_encrypt_batch_dev(params, ids, msgs, ts, chunk=1 << 16):
     """Waters05 Encrypt (ibe/waters05_ibe/waters05_ibe.go:206-244) for n (identity, message) pairs, device-resident:
         c1 = e(g1^alpha, g2)^t * M   fixed-base GT table + GT product
         c2 = [t] g1                  fixed-base G1 table
-        c3 = [t] (U' + sum_{bits} U_j)   Waters hash as one Jacobian subset sum, then a GLV multiplication
-    ids: (n, m/8) identity bit strings (MSB first per byte, waters05_ibe.go:302-313); msgs: (n, 384); ts: (n, 32).
-    One upload (ids, messages, scalars), five launches on one stream, one download -> (c1 (n,384), c2 (n,64), c3 (n,128))."""
+        c3 = [t] (U' + sum_{bits} U_j)   Waters hash as one Jacobian subset sum (byte-window tables), then a GLV multiplication
+    ids: (n, m/8) identity bit strings (MSB first per byte, waters05_ibe.go:302-313); msgs: (n, 384); ts: (n, 32) --
+    numpy arrays or page-locked torch tensors (then the uploads are asynchronous).
+    The batch runs in chunks on two streams: upload, five launches and the download of chunk i overlap the work of chunk
+    i+1; the ciphertexts land in page-locked buffers owned by `params` (valid until the next call).
+    Returns (c1 (n,384), c2 (n,64), c3 (n,128)) as numpy views."""
     torch = _torch()
     e, dev = params.engine, params.dev
-    n = np.ascontiguousarray(ts).reshape(-1, 32).shape[0]
+    as_t = lambda x, w: (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))).reshape(-1, w).view(torch.uint8)
+    t_ts = as_t(ts, 32)
+    n = t_ts.shape[0]
+    t_ids, t_m = as_t(ids, (params.m + 7) // 8), as_t(msgs, GT_BYTES)
+    o1, o2, o3 = params.pinned_out(n)
     with torch.cuda.device(dev):
-        s = torch.cuda.current_stream().cuda_stream
-        d_ids, d_m, d_t = _up(ids, torch, dev), _up(msgs, torch, dev), _up(ts, torch, dev)
-        et = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
-        c1 = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
-        c2 = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
-        h = torch.empty((n, G2_BYTES), dtype=torch.uint8, device=dev)
-        c3 = torch.empty((n, G2_BYTES), dtype=torch.uint8, device=dev)
-        e.dev("gt_fixed_exp_batch_dev", params.t_gt, d_t.data_ptr(), n, et.data_ptr(), stream=s)
-        e.dev("gt_mul_batch_dev", et.data_ptr(), 1, d_m.data_ptr(), 1, n, c1.data_ptr(), stream=s)
-        e.dev("g1_fixed_mul_batch_dev", params.t_g1, d_t.data_ptr(), n, c2.data_ptr(), stream=s)
-        e.dev("g2_subset_sum_batch_dev", params.d_U.data_ptr(), params.m, d_ids.data_ptr(), n, h.data_ptr(), stream=s)
-        e.dev("g2_mul_batch_dev", h.data_ptr(), 1, d_t.data_ptr(), n, c3.data_ptr(), stream=s)
-        return c1.cpu().numpy(), c2.cpu().numpy(), c3.cpu().numpy()
+        streams = params.streams
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
+        keep = []
+        for ci, lo in enumerate(range(0, n, chunk)):
+            hi = min(n, lo + chunk)
+            c = hi - lo
+            st = streams[ci & 1]
+            with torch.cuda.stream(st):
+                s = st.cuda_stream
+                d_ids = t_ids[lo:hi].to(dev, non_blocking=True)
+                d_m = t_m[lo:hi].to(dev, non_blocking=True)
+                d_t = t_ts[lo:hi].to(dev, non_blocking=True)
+                et = torch.empty((c, GT_BYTES), dtype=torch.uint8, device=dev)
+                c1 = torch.empty((c, GT_BYTES), dtype=torch.uint8, device=dev)
+                c2 = torch.empty((c, G1_BYTES), dtype=torch.uint8, device=dev)
+                h = torch.empty((c, G2_BYTES), dtype=torch.uint8, device=dev)
+                c3 = torch.empty((c, G2_BYTES), dtype=torch.uint8, device=dev)
+                e.dev("gt_fixed_exp_batch_dev", params.t_gt, d_t.data_ptr(), c, et.data_ptr(), stream=s)
+                e.dev("gt_mul_batch_dev", et.data_ptr(), 1, d_m.data_ptr(), 1, c, c1.data_ptr(), stream=s)
+                e.dev("g1_fixed_mul_batch_dev", params.t_g1, d_t.data_ptr(), c, c2.data_ptr(), stream=s)
+                e.dev("g2_subset_sum_batch_dev", params.d_U.data_ptr(), params.m, d_ids.data_ptr(), c, h.data_ptr(), stream=s)
+                e.dev("g2_mul_batch_dev", h.data_ptr(), 1, d_t.data_ptr(), c, c3.data_ptr(), stream=s)
+                o1[lo:hi].copy_(c1, non_blocking=True)
+                o2[lo:hi].copy_(c2, non_blocking=True)
+                o3[lo:hi].copy_(c3, non_blocking=True)
+                keep.append((d_ids, d_m, d_t, et, c1, c2, h, c3))  # referenced until both streams have drained
+        for st in streams:
+            st.synchronize()
+    return o1[:n].numpy(), o2[:n].numpy(), o3[:n].numpy()

@@ -199,8 +199,15 @@ void emu_wvm(const void* in0, const void* in1, size_t n, int mode, void* out) {
     memcpy((char*)out + i * 384, v, 384);
   }
 }
-// the LIN reduction on its own: v = sum c_i * s_i over 9 limbs, any total below 256 p
+// the LIN reduction on its own: any 9-limb total below 256 p
 void emu_wvm_lin_reduce(const void* v9, size_t n, void* out) {
-  for (size_t i = 0; i < n; i++) { uint32_t v[9]; memcpy(v, (const char*)v9 + i * 36, 36); st(out, i, wvm::lin_reduce(v)); }
+  for (size_t i = 0; i < n; i++) { uint32_t v[9]; memcpy(v, (const char*)v9 + i * 36, 36); st(out, i, wvm::lin_reduce9(v)); }
 }
+// one LIN op: out = sum_i c[i] * s[i] mod p over nterms Montgomery operands (coefficients as int32)
+void emu_wvm_lin(const void* s, const int* c, size_t nterms, void* out) {
+  wvm::LinAcc acc; wvm::lin_init(acc);
+  for (size_t i = 0; i < nterms; i++) wvm::lin_acc(acc, ld<Fp>(s, i), c[i]);
+  st(out, 0, wvm::lin_finish(acc));
+}
+void emu_wvm_inv(const void* a, size_t n, void* z) { for (size_t i = 0; i < n; i++) st(z, i, wvm::fp_inv_wvm(ld<Fp>(a, i))); }
 }

@@ -326,3 +326,34 @@ def test_warp_vm_python_evaluator_matches_oracle():
     e = o.pair([Pt], [Qt])
     want = [e[c][b][a] for c in (0, 1) for b in (0, 1, 2) for a in (0, 1)]
     assert got == want
+
+
+def test_warp_vm_lin_op_and_inversion(emu):
+    """The carry-free LIN accumulator (negative terms as complements, sum |c| <= 120) and the binary-Euclid inversion
+    against Python integers, including the extreme coefficient patterns and inv(0) = 0."""
+    rng = o.SplitMix64(80)
+    R = 1 << 256
+    cases = [([o.P - 1] * 8, [15] * 8), ([o.P - 1] * 8, [-15] * 8), ([0] * 4, [-30] * 4), ([1, o.P - 1], [31, -31]), ([5], [1]), ([7], [-1])]
+    for _ in range(300):
+        k = 1 + rng.next() % 8
+        cs = []
+        budget = 120
+        for _ in range(k):
+            c = int(rng.next() % 63) - 31
+            c = max(-budget, min(budget, c)) if budget else 0
+            budget -= abs(c)
+            cs.append(c)
+        cases.append(([rng.fp() for _ in range(k)], cs))
+    for vals, cs in cases:
+        buf = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
+        carr = (ctypes.c_int * len(cs))(*cs)
+        out = np.zeros(32, np.uint8)
+        emu.emu_wvm_lin(vp(buf), carr, sz(len(cs)), vp(out))
+        assert int.from_bytes(out.tobytes(), "little") == sum(c * v for c, v in zip(cs, vals)) % o.P, (vals, cs)
+    xs = [0, 1, 2, o.P - 1, (1 << 255) % o.P] + [rng.fp() for _ in range(200)]
+    buf = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in xs), dtype=np.uint8).copy()
+    out = np.zeros(32 * len(xs), np.uint8)
+    emu.emu_wvm_inv(vp(buf), sz(len(xs)), vp(out))
+    for i, x in enumerate(xs):  # Montgomery in, Montgomery out: (a R) -> a^-1 R
+        want = 0 if x == 0 else pow(x * pow(R, -1, o.P) % o.P, -1, o.P) * R % o.P
+        assert int.from_bytes(out[32 * i:32 * i + 32].tobytes(), "little") == want

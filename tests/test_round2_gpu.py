@@ -364,3 +364,72 @@ def test_bsw07_device_pipeline_matches_host_pipeline(engine):
     folded = schemes.bsw07_policy_lines(engine, dj, djp, d, deltas)
     got2 = schemes.bsw07_decrypt_batch_dev(engine, cy, cyp, folded, c, ct, None)
     assert (got2 == want).all()
+
+
+def test_warp_vm_kernels(engine):
+    """BN254_IMPL=wvm: one warp per item (the latency path), through the same C ABI: pair / miller / final-exp / small
+    multi-pairings and checks, ragged sizes, infinity operands, and a batch larger than one pass of the persistent grid."""
+    import os
+
+    from gopairingbasedcryptography_b200 import bn254
+
+    old = os.environ.get("BN254_IMPL")
+    os.environ["BN254_IMPL"] = "wvm"
+    try:
+        eng = bn254.Engine(0)
+    finally:
+        if old is None:
+            del os.environ["BN254_IMPL"]
+        else:
+            os.environ["BN254_IMPL"] = old
+    for n in (1, 5, 4 * 37 + 3, 5000):
+        P, Q, _, _ = common.points(n, seed=1200 + n, threads=8)
+        if n > 3:
+            P, Q = common.with_infinities(P, Q)
+        ref = port.pair_batch(P, Q, n, 8)
+        assert (eng.pair_batch(P, Q).reshape(-1) == ref).all(), n
+        if n <= 200:
+            ml = eng.miller_loop_batch(P, Q, 1)
+            assert (eng.final_exp_batch(ml).reshape(-1) == ref).all(), n
+    rng = o.SplitMix64(13)
+    x = np.frombuffer(b"".join(o.fp_to_mont_bytes(rng.fp()) for _ in range(36)), dtype=np.uint8).copy()
+    assert (eng.final_exp_batch(x).reshape(-1) == port.final_exp_batch(x, 3)).all()
+    zero_and_one = np.zeros(768, np.uint8)
+    zero_and_one[384:416] = np.frombuffer(o.fp_to_mont_bytes(1), dtype=np.uint8)
+    assert (eng.final_exp_batch(zero_and_one).reshape(-1) == port.final_exp_batch(zero_and_one, 2)).all()  # FE(0) = 0, FE(1) = 1
+    for k, n in ((2, 100), (3, 64), (7, 9)):
+        P, Q, _, _ = common.points(n * k, seed=1250 + k, threads=8)
+        P, Q = common.with_infinities(P, Q)
+        ref = port.multi_pair_batch(P, Q, n, k, 8)
+        assert (eng.multi_pair_batch(P, Q, k).reshape(-1) == ref).all(), k
+        okr = port.pairing_check_batch(P, Q, n, k, 8).astype(bool)
+        assert (eng.pairing_check_batch(P, Q, k) == okr).all()
+    # BLS shape through the fixed-G1 check
+    n = 50
+    P, Q, _, _ = common.points(2 * n + 2, seed=1300, threads=8)
+    P, Q = P.reshape(-1, 64), Q.reshape(-1, 128)
+    got = eng.pairing_check2_fixed_g1_batch(P[0], P[1], Q[2:2 + n], Q[2 + n:2 + 2 * n])
+    Pc = np.tile(np.concatenate([P[0], P[1]]), n)
+    Qc = np.concatenate([Q[2:2 + n], Q[2 + n:2 + 2 * n]], axis=1).reshape(-1)
+    assert (got == port.pairing_check_batch(Pc, Qc, n, 2, 8).astype(bool)).all()
+    eng.close()
+
+
+def test_subset_sum_byte_window_tables(engine):
+    """From 2048 selectors on the Waters hash runs from byte-window tables (one mixed addition per selector byte): same
+    points as the plain per-bit sum, for G1 and G2, m not a multiple of 8, an infinity among the points, all-zero and
+    all-one selectors."""
+    n = 3000
+    P, Q, _, _ = common.points(70, seed=1400, threads=8)
+    rng = np.random.default_rng(5)
+    for m, pts, item, f in ((20, P, 64, engine.g1_subset_sum_batch), (64, Q, 128, engine.g2_subset_sum_batch)):
+        U = pts.reshape(-1, item)[: m + 1].copy()
+        U[4] = 0  # point at infinity
+        row = (m + 7) // 8
+        sel = rng.integers(0, 256, size=(n, row), dtype=np.uint8)
+        sel[0] = 0
+        sel[1] = 255
+        tab = f(U, sel)            # n >= 2048: table path
+        plain = np.concatenate([f(U, sel[i:i + 1000]) for i in range(0, n, 1000)])  # chunks below the threshold: per-bit path
+        assert (tab == plain).all()
+        assert (tab[0] == U[0]).all()
