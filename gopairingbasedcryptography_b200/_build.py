@@ -23,6 +23,8 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "nolockstep": NOLS,
     "karatsuba_mulx": DEFAULT + ["-DBN254_KARATSUBA_MULX"],
     "ool_jac": DEFAULT + ["-DBN254_OOL_JAC"],
+    "wvmprof": DEFAULT + ["-DBN254_WVM_PROFILE"],
+    "wvmprof_noinline": DEFAULT + ["-DBN254_WVM_PROFILE"],  # built after `WVM_TINLINE=0 python csrc/wvmgen.py` (program-shape experiment)
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
 }
@@ -50,10 +52,12 @@ def is_stale():
 def unit_flags(unit):
     v = VARIANTS[VARIANT]
     flags = list(v.get(unit, v.get("*", DEFAULT)) if isinstance(v, dict) else v)
-    return flags + UNIT_FLAGS.get(unit, [])
+    return flags + UNIT_FLAGS.get(unit, []) + os.environ.get("BN254_EXTRA_FLAGS", "").split()
 
 
 def ensure_generated():
+    if os.environ.get("BN254_KEEP_GENERATED"):
+        return
     """The warp-VM programs (wvm_prog_*.inc, ~8 MB of text) are generated, not committed: wvmgen.py rebuilds them from
     the traced pairing formulas in a few seconds."""
     outs = [os.path.join(CSRC, f) for f in ("wvm_prog_miller.inc", "wvm_prog_finalexp.inc", "wvm_prog_meta.cuh")]

@@ -103,6 +103,14 @@ cudaError_t wvm_prepare(int* blocks_per_sm) {
   return e;
 }
 int wvm_items_per_cta() { return kWvmWarps; }
+#ifdef BN254_WVM_PROFILE
+extern "C" void bn254_wvm_profile(unsigned long long* out8) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, wvm::wvm_prof, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(wvm::wvm_prof, z, sizeof(z));
+}
+#endif
 void wvm_run(int prog, const void* a, const void* b, size_t n, void* out, int sms, const int* blocks_per_sm, cudaStream_t s) {
   if (prog == kVmMiller) launch_one<0>(a, b, n, out, sms, blocks_per_sm[kVmMiller], s);
   else if (prog == kVmPair) launch_one<1>(a, b, n, out, sms, blocks_per_sm[kVmPair], s);

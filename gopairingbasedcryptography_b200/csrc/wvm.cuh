@@ -58,31 +58,67 @@ BN_HD void lin_acc(LinAcc& a, const Fp& v, int c) {
   for (int i = 0; i < 8; i++) a.col[i] += (uint64_t)(v.l[i] ^ mask) * m;
   a.k += mask & m;
 }
-// columns -> 9 limbs, minus K (2^256 - 1), reduced mod p.  Quotient estimate from the top bits as in fp_reduce_small
-// (tower.cuh) with the product widened to 64 bits: for v < 256 p, q_est is q or q - 1, one conditional subtraction ends it.
-BN_HD Fp lin_reduce9(const uint32_t* v) {
-  uint32_t hi = (v[8] << 11) | (v[7] >> 21);                 // floor(v / 2^245) < 2^17
-  uint32_t q = (uint32_t)(((uint64_t)hi * 43336u) >> 24);   // 43336 = floor(2^269 / p)
-  uint32_t qp[9];
-  uint64_t c = 0;
+// One pass: quotient estimate from the two top columns (the lower columns cannot move it by more than one unit of
+// 2^224, i.e. 2^-21 of the estimate's own unit), then columns - q p with signed 64-bit carries, then at most two
+// conditional subtractions (q_est in {q - 2, q - 1, q}).
+#ifndef WVM_FINISH_ONEPASS
+#define WVM_FINISH_ONEPASS 0
+#endif
+#ifndef WVM_LIN_BATCH
+#define WVM_LIN_BATCH 0
+#endif
+#ifndef WVM_AHEAD
+#define WVM_AHEAD 1
+#endif
+#if WVM_FINISH_ONEPASS
+BN_HD Fp lin_finish(const LinAcc& a) {
+  uint64_t top = a.col[7] + (a.col[6] >> 32) - ((uint64_t)a.k << 32);     // floor(v / 2^224) up to the lower carries
+  uint32_t hi = (uint32_t)(top >> 21);                                   // floor(v / 2^245) < 2^17
+  uint32_t q = (uint32_t)(((uint64_t)hi * 43336u) >> 24);                // 43336 = floor(2^269 / p)
+  Fp w;
+  int64_t c = (int64_t)a.k;                                              // + K at limb 0 (see lin_acc)
 #pragma unroll
-  for (int i = 0; i < 8; i++) { c += (uint64_t)q * p_limb(i); qp[i] = (uint32_t)c; c >>= 32; }
-  qp[8] = (uint32_t)c;
+  for (int i = 0; i < 8; i++) {
+    c += (int64_t)a.col[i] - (int64_t)((uint64_t)q * p_limb(i));
+    w.l[i] = (uint32_t)c;
+    c >>= 32;                                                            // arithmetic: the running value may dip below zero
+  }
+  // c - K is the ninth limb of v - q p, 0 by construction (0 <= v - q p < 3p < 2^256)
+  fp_reduce_once(w);
+  fp_reduce_once(w);
+  return w;
+}
+#else
+// two passes: carry propagation of the columns (plus K, minus K 2^256), then the quotient estimate of fp_reduce_small
+// (tower.cuh) with the product widened to 64 bits -- for v < 256 p, q_est is q or q - 1 -- and one conditional subtraction
+BN_HD Fp lin_finish(const LinAcc& a) {
+  uint32_t v[9];
+  uint64_t c = a.k;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += a.col[i]; v[i] = (uint32_t)c; c >>= 32; }
+  v[8] = (uint32_t)c - a.k;
+  uint32_t hi = (v[8] << 11) | (v[7] >> 21);
+  uint32_t q = (uint32_t)(((uint64_t)hi * 43336u) >> 24);
+  uint32_t qp[9];
+  uint64_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { d += (uint64_t)q * p_limb(i); qp[i] = (uint32_t)d; d >>= 32; }
+  qp[8] = (uint32_t)d;
   Fp w;
   w.l[0] = sub_cc(v[0], qp[0]);
 #pragma unroll
   for (int i = 1; i < 8; i++) w.l[i] = subc_cc(v[i], qp[i]);
-  (void)subc(v[8], qp[8]);  // v - q p < 2p: the ninth limb is zero
+  (void)subc(v[8], qp[8]);
   fp_reduce_once(w);
   return w;
 }
-BN_HD Fp lin_finish(const LinAcc& a) {
-  uint32_t v[9];
-  uint64_t c = a.k;  // + K
-#pragma unroll
-  for (int i = 0; i < 8; i++) { c += a.col[i]; v[i] = (uint32_t)c; c >>= 32; }
-  v[8] = (uint32_t)c - a.k;  // - K 2^256
-  return lin_reduce9(v);
+#endif
+BN_HD Fp lin_reduce9(const uint32_t* v) {  // test hook: reduce a plain 9-limb value below 256 p through the same path
+  LinAcc a;
+  for (int i = 0; i < 8; i++) a.col[i] = v[i];
+  a.col[7] += (uint64_t)v[8] << 32;
+  a.k = 0;
+  return lin_finish(a);
 }
 
 // Inversion for the warp-VM: binary extended Euclid on one lane (variable time is free here -- the other lanes idle
@@ -127,6 +163,9 @@ BN_NOINLINE Fp fp_inv_wvm(Fp a) {
   return fp_mul(r, r3);  // (a R)^-1 * R^3 / R = a^-1 R
 }
 
+// (A Montgomery product on carry-free 64-bit column accumulators -- every partial product split into halves, no carry
+// chain -- was measured for the lone-warp case and is SLOWER: 2 390 cycles per MUL round against 1 250 for fp_mul's two
+// carry chains per row; its ~600 instructions are issue-bound on a single warp.  profiles/r2/wvm_round_costs.jsonl)
 // One op.  rec = 16 u16 fields in two uint4 (little-endian pairs).  Returns true when `out` must be stored to slot dst.
 // nmax: warp-uniform bound on the LIN term count of this round (so the term loop's exit is a uniform branch).
 BN_HD unsigned field(const uint4& w0, const uint4& w1, int i) {
@@ -146,18 +185,37 @@ BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned n
     return true;
   }
   if (op == OP_LIN) {
+    // terms in batches of four: the four slot loads of a batch are in flight together, the batch loop's exit is
+    // warp-uniform; unused term fields are zero = coefficient 0 on slot 0
     LinAcc acc;
     lin_init(acc);
+    (void)x;
+#if !WVM_LIN_BATCH
 #pragma unroll
-    for (int i = 0; i < 15; i++) {
+    for (int i = 0; i < 15; i++) {  // term by term; the exit is warp-uniform, unused fields are coefficient 0 on slot 0
       if ((unsigned)i >= nmax) break;
       unsigned f = field(w0, w1, 1 + i);
-      bool live = (unsigned)i < x;
       int c = (int)(f >> 10);
       c = c >= 32 ? c - 64 : c;
-      Fp v = ld_slot(slots, live ? (f & 1023u) : 0u);  // slot 0 holds zero
-      lin_acc(acc, v, live ? c : 0);
+      lin_acc(acc, ld_slot(slots, f & 1023u), c);
     }
+#else
+#pragma unroll
+    for (int g = 0; g < 16; g += 4) {
+      if ((unsigned)g >= nmax) break;
+      Fp v[4];
+      int c[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        unsigned f = g + i < 15 ? field(w0, w1, 1 + g + i) : 0u;
+        c[i] = (int)(f >> 10);
+        c[i] = c[i] >= 32 ? c[i] - 64 : c[i];
+        v[i] = ld_slot(slots, f & 1023u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) lin_acc(acc, v[i], c[i]);
+    }
+#endif
     out = lin_finish(acc);
     return true;
   }
@@ -169,12 +227,32 @@ BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned n
 }
 
 // Run a program for the pairing this warp owns.  prog: rounds x 32 lanes x 2 uint4.
+#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long wvm_prof[8];  // cycles and rounds per op class (debug build: profiles/r2/wvm_round_costs.json)
+#endif
 BN_HD void run(Fp* slots, const uint4* __restrict__ prog, int rounds, int lane) {
+  // the program words of round r + kAhead are requested in round r: a LIN round is shorter than an L2 round trip, and a
+  // one-round prefetch left every LIN round waiting ~500 cycles for its own instructions (measured)
+  constexpr int kAhead = WVM_AHEAD;
   const uint4* p = prog + (size_t)lane * 2;
-  uint4 w0 = p[0], w1 = p[1];
+  uint4 q0[kAhead], q1[kAhead];
+#pragma unroll
+  for (int k = 0; k < kAhead; k++) {
+    int rr = k < rounds ? k : rounds - 1;
+    q0[k] = p[(size_t)rr * kLanes * 2]; q1[k] = p[(size_t)rr * kLanes * 2 + 1];
+  }
   for (int r = 0; r < rounds; r++) {
-    uint4 n0 = w0, n1 = w1;
-    if (r + 1 < rounds) { n0 = p[(size_t)(r + 1) * kLanes * 2]; n1 = p[(size_t)(r + 1) * kLanes * 2 + 1]; }  // prefetch
+    uint4 w0 = q0[0], w1 = q1[0];
+#pragma unroll
+    for (int k = 0; k + 1 < kAhead; k++) { q0[k] = q0[k + 1]; q1[k] = q1[k + 1]; }
+    {
+      int rr = r + kAhead < rounds ? r + kAhead : rounds - 1;
+      q0[kAhead - 1] = p[(size_t)rr * kLanes * 2]; q1[kAhead - 1] = p[(size_t)rr * kLanes * 2 + 1];
+    }
+#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
+    long long t0_ = clock64();
+    unsigned cls_ = __reduce_max_sync(0xffffffffu, w0.x & 3u);
+#endif
     unsigned h = w0.x & 0xFFFFu;
     unsigned nterms = (h & 3u) == OP_LIN ? (h >> 12) : 0u;
 #if defined(__CUDACC__)
@@ -187,7 +265,9 @@ BN_HD void run(Fp* slots, const uint4* __restrict__ prog, int rounds, int lane) 
     bool st = exec_op(slots, w0, w1, nmax, dst, out);
     if (st) st_slot(slots, dst, out);
     round_sync();
-    w0 = n0; w1 = n1;
+#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
+    if (lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) { wvm_prof[cls_] += (unsigned long long)(clock64() - t0_); wvm_prof[4 + cls_] += 1; }
+#endif
   }
 }
 

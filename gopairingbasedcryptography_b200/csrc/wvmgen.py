@@ -33,6 +33,12 @@ CMAX = 31                                         # |coefficient| limit (6-bit s
 CSUM_MAX = 120                                    # sum |c| per LIN: 128 p + sum c_i s_i stays inside (0, 256 p)
 SHARE = os.environ.get("WVM_SHARE", "1") == "1"   # materialise values with several consumers instead of inlining their forms
 POLICY = os.environ.get("WVM_POLICY", "fill12")
+DUP_MAX = int(os.environ.get("WVM_DUP_MAX", "6"))   # a LIN of at most this many terms may be duplicated into several consumers
+# term cap when LIN -> LIN chains are collapsed (0 = off).  Measured on B200 (benchmarks/wvm_ab.py, profiles/r2/wvm_ab.jsonl):
+# collapsing helps the Miller program (0.705 -> 0.672 ms) and hurts the final exponentiation (0.76 -> 0.86 ms).
+TINLINE_ENV = os.environ.get("WVM_TINLINE")
+TINLINE_BY_PROGRAM = {"miller": 15, "finalexp": 0, "pair": 0}
+TINLINE = 0
 SHARE_MIN = int(os.environ.get("WVM_SHARE_MIN", "3"))  # ... when the form has at least this many terms
 OP_NOP, OP_MUL, OP_LIN, OP_INV = 0, 1, 2, 3
 COST = {OP_MUL: 1.0, OP_LIN: 0.35, OP_INV: 40.0}
@@ -296,6 +302,46 @@ def lower(t, low, in_forms):
     return val
 
 
+def inline_lins(low, outputs, tmax):
+    """Collapse LIN -> LIN chains: a LIN term that is itself a LIN with no other consumer (or with at most two terms)
+    is replaced by its own terms, as long as the merged op still fits one record.  Fewer dependent rounds; the
+    absorbed node dies when nothing else reads it."""
+    def users_of():
+        cnt = {}
+        for b in low.bases:
+            if b.kind != "op":
+                continue
+            ds = b.src if b.op in (OP_MUL, OP_INV) else tuple(low.bases[k] for k, _ in b.terms)
+            for d in set(x.id for x in ds):
+                cnt[d] = cnt.get(d, 0) + 1
+        for o_ in outputs:
+            cnt[o_.id] = cnt.get(o_.id, 0) + 2  # outputs are never absorbed
+        return cnt
+    changed, total = True, 0
+    while changed:
+        changed = False
+        cnt = users_of()
+        for b in low.bases:
+            if b.kind != "op" or b.op != OP_LIN:
+                continue
+            f = dict(b.terms)
+            for k, c in list(f.items()):
+                d = low.bases[k]
+                if d.kind != "op" or d.op != OP_LIN or d is b:
+                    continue
+                if not (cnt.get(k, 0) == 1 or len(d.terms) <= DUP_MAX):
+                    continue
+                g2 = dict(f)
+                del g2[k]
+                g2 = low.f_add(g2, dict(d.terms), c)
+                if len(g2) <= tmax and g2 and all(abs(v) <= CMAX for v in g2.values()) and sum(abs(v) for v in g2.values()) <= CSUM_MAX:
+                    f = g2
+                    changed = True
+                    total += 1
+            b.terms = tuple(sorted(f.items()))
+    return total
+
+
 def schedule(low, outputs):
     """Critical-path list scheduling into class-uniform rounds of <= LANES ops."""
     live = set()
@@ -482,6 +528,9 @@ def build(name):
                 b.users.append(c)
                 b = c
             outputs.append(b)
+    tinline = int(TINLINE_ENV) if TINLINE_ENV is not None else TINLINE_BY_PROGRAM[name]
+    if tinline:
+        inline_lins(low, outputs, tinline)
     rounds, live = schedule(low, outputs)
     consts = [b for b in low.bases if b.kind == "const" and (b.id in live or b is low.zero)]
     pinned = [low.zero] + [b for b in consts if b is not low.zero] + pinned_in
