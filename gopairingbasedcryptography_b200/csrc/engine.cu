@@ -60,6 +60,7 @@ struct bn254_ctx {
   int sms = 0;
   int vm_blocks_per_sm[3] = {0, 0, 0};
   int wvm_blocks_per_sm[3] = {0, 0, 0};
+  bool g2_glv = false;  // BN254_G2_LADDER=glv: 2-dimensional GLV on G2 instead of the 4-dimensional GLS ladder
   size_t wvm_auto_max = 0;  // launches of at most this many items take the warp-VM kernels (one warp per item)
   void* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
   cudaEvent_t vm_dev_done = nullptr;
@@ -361,6 +362,22 @@ cudaError_t seq_gt_exp(bn254_ctx* ctx, Scratch& sc, int cyclo, const void* x, si
   }
   return cudaSuccess;
 }
+// G1: 2-dimensional GLV ladder.  G2: 4-dimensional GLS ladder with its per-thread table in a scratch slice; sub-batches
+// keep the scratch under 1 GiB.  BN254_G2_LADDER=glv keeps the 2-dimensional ladder (A/B measurements).
+cudaError_t seq_scalar_mul(bn254_ctx* ctx, Scratch& sc, int g, const void* base, size_t stride, const void* scalars, size_t n, void* out) {
+  if (g == 1 || ctx->g2_glv) { L::scalar_mul(g, base, stride, scalars, n, out, sc.stream); return cudaSuccess; }
+  const size_t per = L::g2_gls_scratch_bytes(1);
+  const size_t sub = std::max<size_t>(1, std::min<size_t>(n, (size_t(1) << 30) / per));
+  void* scratch;
+  cudaError_t e;
+  if ((e = sc.reserve(al256(sub * per))) != cudaSuccess || (e = sc.get(sub * per, &scratch)) != cudaSuccess) return e;
+  for (size_t off = 0; off < n; off += sub) {
+    size_t c = std::min(sub, n - off);
+    L::scalar_mul_g2_gls(static_cast<const char*>(base) + off * stride * BN254_G2_BYTES, stride, static_cast<const char*>(scalars) + off * BN254_SCALAR_BYTES, c,
+                         static_cast<char*>(out) + off * BN254_G2_BYTES, scratch, sc.stream);
+  }
+  return cudaSuccess;
+}
 // Waters hash: plain subset sum for small batches, byte-window tables (built per call, 8192 short sums) from 2048 selectors on
 constexpr size_t kSubsetTabMin = 2048;
 cudaError_t seq_subset_sum(bn254_ctx*, Scratch& sc, int g, const void* U, int m, const uint8_t* sel, size_t n, void* out) {
@@ -574,6 +591,7 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
   }
   const char* impl = getenv("BN254_IMPL");
   ctx->vm_mode = !impl ? 0 : (std::string(impl) == "vm" ? 1 : (std::string(impl) == "thread" ? 2 : (std::string(impl) == "wvm" ? 3 : 0)));
+  { const char* gl = getenv("BN254_G2_LADDER"); ctx->g2_glv = gl && std::string(gl) == "glv"; }
   ctx->sms = prop.multiProcessorCount;
   if (L::vm_prepare(ctx->vm_blocks_per_sm) != cudaSuccess || L::wvm_prepare(ctx->wvm_blocks_per_sm) != cudaSuccess) { bn254_ctx_destroy(ctx); return BN254_ERR_CUDA; }
   {  // crossover to the lane-group kernels: one pass of the warp-VM grid, 148 SMs x 4 CTAs x 4 warps = 2368 items
@@ -780,13 +798,13 @@ int bn254_final_exp_batch(bn254_ctx* ctx, const void* in, size_t n, void* out) {
 #define MUL_ENTRY(name, G, BYTES)                                                                                     \
   int name(bn254_ctx* ctx, const void* base, const void* scalars, size_t n, void* out) {                              \
     return run_host(ctx, {{base, BYTES, false}, {scalars, BN254_SCALAR_BYTES, false}}, out, BYTES, n,                 \
-                    [](const void* const* d, size_t c, void* o, Slot& sl) {                                           \
-                      L::scalar_mul(G, d[0], 1, d[1], c, o, sl.stream);                                               \
-                      return cudaSuccess;                                                                             \
+                    [ctx](const void* const* d, size_t c, void* o, Slot& sl) {                                        \
+                      Scratch sc; sc.slot = &sl; sc.stream = sl.stream;                                               \
+                      return seq_scalar_mul(ctx, sc, G, d[0], 1, d[1], c, o);                                         \
                     });                                                                                               \
   }                                                                                                                   \
   int name##_dev(bn254_ctx* ctx, const void* d_base, size_t stride, const void* d_s, size_t n, void* d_out, void* stream) { \
-    return run_dev(ctx, n, stream, [&](Scratch& sc) { L::scalar_mul(G, d_base, stride, d_s, n, d_out, sc.stream); return cudaSuccess; }); \
+    return run_dev(ctx, n, stream, [&](Scratch& sc) { return seq_scalar_mul(ctx, sc, G, d_base, stride, d_s, n, d_out); }); \
   }
 MUL_ENTRY(bn254_g1_mul_batch, 1, BN254_G1_BYTES)
 MUL_ENTRY(bn254_g2_mul_batch, 2, BN254_G2_BYTES)
@@ -802,9 +820,9 @@ MUL_ENTRY(bn254_g2_mul_batch, 2, BN254_G2_BYTES)
     CU(cudaSetDevice(ctx->device));                                                                                   \
     Operand in[2] = {{base, BYTES, true}, {scalars, BN254_SCALAR_BYTES, false}};                                      \
     if (n < kFixedMin)                                                                                                \
-      return run_host_locked(ctx, in, 2, out, BYTES, n, [](const void* const* d, size_t c, void* o, Slot& sl) {       \
-        L::scalar_mul(G, d[0], 0, d[1], c, o, sl.stream);                                                             \
-        return cudaSuccess;                                                                                           \
+      return run_host_locked(ctx, in, 2, out, BYTES, n, [ctx](const void* const* d, size_t c, void* o, Slot& sl) {    \
+        Scratch sc; sc.slot = &sl; sc.stream = sl.stream;                                                             \
+        return seq_scalar_mul(ctx, sc, G, d[0], 0, d[1], c, o);                                                       \
       });                                                                                                             \
     const void* table = nullptr;                                                                                      \
     int rc = cached_table(ctx, G, base, &table);                                                                      \

@@ -157,6 +157,50 @@ def main():
         assert (k1 + k2 * lam - k) % R == 0
         worst = max(worst, abs(k1).bit_length(), abs(k2).bit_length())
     assert worst <= 131, worst
+    # ---- 4-dimensional GLS decomposition on G2 (Galbraith-Scott): psi = twist . Frobenius . untwist acts on G2 as
+    # multiplication by lam4 = p mod r = 6 x0^2, a root of X^4 - X^2 + 1; k = k0 + k1 lam4 + k2 lam4^2 + k3 lam4^3 with
+    # |k_j| < 2^67 by Babai rounding against the basis below (rows are lattice vectors: sum row_j lam4^j = 0 mod r;
+    # their determinant is -3r -- an index-3 sublattice, which costs nothing but a slightly larger bound)
+    lam4 = P % R
+    assert lam4 == 6 * X0 * X0 and (lam4**4 - lam4**2 + 1) % R == 0
+    psi_pt = ((G2X[0], -G2X[1] % P), (G2Y[0], -G2Y[1] % P))          # conjugates
+    psi_pt = (f2mul(psi_pt[0], g1[2]), f2mul(psi_pt[1], g1[3]))      # psi(x, y) = (conj(x) xi^((p-1)/3), conj(y) xi^((p-1)/2))
+    assert psi_pt == ec_mul((G2X, G2Y), lam4, fp2_ops), "psi is not multiplication by p mod r on G2"
+    x = X0
+    B4 = [[x + 1, x, x, -2 * x], [2 * x + 1, -x, -(x + 1), -x], [2 * x, 2 * x + 1, 2 * x + 1, 2 * x + 1], [x - 1, 4 * x + 2, -(2 * x - 1), x - 1]]
+    for row in B4:
+        assert sum(c * lam4**j for j, c in enumerate(row)) % R == 0
+    from fractions import Fraction
+
+    def mat_inv(M):
+        n = len(M)
+        A = [[Fraction(v) for v in r] + [Fraction(int(i == j)) for j in range(n)] for i, r in enumerate(M)]
+        for i in range(n):
+            pv = next(r for r in range(i, n) if A[r][i] != 0)
+            A[i], A[pv] = A[pv], A[i]
+            d = A[i][i]
+            A[i] = [v / d for v in A[i]]
+            for r in range(n):
+                if r != i and A[r][i] != 0:
+                    f = A[r][i]
+                    A[r] = [a - f * b for a, b in zip(A[r], A[i])]
+        return [r[n:] for r in A]
+
+    row0 = mat_inv(B4)[0]                       # (k, 0, 0, 0) B^-1 = k row0, row0_i = alpha_i / (3r)
+    alphas = [int(r_ * 3 * R) for r_ in row0]
+    assert all(Fraction(a, 3 * R) == r_ for a, r_ in zip(alphas, row0))
+    g4 = [(abs(a) << 256) // (3 * R) for a in alphas]
+    s4 = [1 if a >= 0 else -1 for a in alphas]
+    # k_j = [j == 0] k + sum_i c_i M4[i][j] (mod 2^256, two's complement), c_i = floor(k g4_i / 2^256)
+    M4 = [[(-s4[i] * B4[i][j]) & M256 for j in range(4)] for i in range(4)]
+    worst4 = 0
+    for k in [0, 1, 2, R - 1, R - 2, R, R + 1, 1 << 128, lam4, (1 << 256) - 1] + [rnd.randrange(1 << 256) for _ in range(20000)]:
+        c = [(k * gi) >> 256 for gi in g4]
+        kv = [((k if j == 0 else 0) + sum(c[i] * M4[i][j] for i in range(4))) & M256 for j in range(4)]
+        kv = [v - (1 << 256) if v >> 255 else v for v in kv]
+        assert sum(kj * lam4**j for j, kj in enumerate(kv)) % R == k % R
+        worst4 = max(worst4, max(abs(v).bit_length() for v in kv))
+    assert worst4 <= 67, worst4
     ate_naf = naf(6 * X0 + 2)
     x0_naf3 = naf(X0, 3)
 
@@ -194,6 +238,11 @@ def main():
     w("BN_CONST Fp GLV_BETA_G2 = %s;  // same on the twist (G2)" % fp_init(beta_g2))
     for name, v in glv.items():
         w("BN_CONST uint32_t GLV_%s[8] = {%s};" % (name, limbs32(v)))
+    for i in range(4):
+        w("BN_CONST uint32_t GLS4_G%d[8] = {%s};" % (i, limbs32(g4[i])))
+        for j in range(4):
+            w("BN_CONST uint32_t GLS4_M%d%d[8] = {%s};" % (i, j, limbs32(M4[i][j])))
+    w("static constexpr int GLS4_MAX_BITS = %d;  // |k_j| < 2^GLS4_MAX_BITS for every 256-bit scalar" % (worst4 + 1))
     w("static constexpr int GLV_MAX_BITS = %d;  // |k1|, |k2| < 2^GLV_MAX_BITS for every 256-bit scalar" % (worst + 1))
     w("static constexpr int ATE_NAF_LEN = %d;" % len(ate_naf))
     w("BN_CONST signed char ATE_NAF[%d] = {%s};" % (len(ate_naf), ",".join(map(str, ate_naf))))

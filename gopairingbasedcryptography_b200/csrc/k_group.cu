@@ -22,6 +22,20 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul(const v
   scalar_mul_glv<J, A>(r, b, s, beta);
   store_struct(out, i, r);
 }
+// G2 variable base by the 4-dimensional GLS ladder (curve.cuh); scratch: one kGlsSliceFp2 x 64 B slice per thread
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_scalar_mul_g2_gls(const void* base, size_t base_stride, const void* scalars, size_t n, void* out, Fp2* scratch) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  G2Aff b;
+  bool plain = i < n;
+  if (plain) { load_struct(b, base, i * base_stride); plain = !aff_is_inf(b); }
+  cta_lockstep_set(__syncthreads_and(plain) != 0);
+  if (i >= n) return;
+  uint32_t s[8];
+  load_scalar(s, scalars, i);
+  G2Aff r;
+  scalar_mul_gls4(r, b, s, scratch + i * (size_t)kGlsSliceFp2);
+  store_struct(out, i, r);
+}
 // fixed base: 32 windowed mixed additions from a precomputed affine table (L2-resident, 0.5-1 MB)
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A* table, const void* scalars, size_t n, void* out) {
@@ -259,6 +273,10 @@ cudaError_t group_init() {
   return e;
 }
 #define BY_GROUP(g, call1, call2) do { if ((g) == 1) { call1; } else { call2; } } while (0)
+size_t g2_gls_scratch_bytes(size_t n) { return n * (size_t)kGlsSliceFp2 * sizeof(Fp2); }
+void scalar_mul_g2_gls(const void* base, size_t base_stride, const void* scalars, size_t n, void* out, void* scratch, cudaStream_t s) {
+  BN_LAUNCH, k_scalar_mul_g2_gls<<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out, static_cast<Fp2*>(scratch));
+}
 void scalar_mul(int g, const void* base, size_t base_stride, const void* scalars, size_t n, void* out, cudaStream_t s) {
   BY_GROUP(g, (BN_LAUNCH, k_scalar_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)),
            (BN_LAUNCH, k_scalar_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(base, base_stride, scalars, n, out)));

@@ -45,6 +45,9 @@ int pairing_wave_threads(int sms);  // threads of one full wave of the pairing k
 
 // ---- group family (g = 1: G1, 2: G2) ----------------------------------------------------------------------------
 void scalar_mul(int g, const void* base, size_t base_stride, const void* scalars, size_t n, void* out, cudaStream_t s);
+// G2 by the 4-dimensional GLS ladder; scratch = g2_gls_scratch_bytes(n) bytes of device memory, private to the launch
+size_t g2_gls_scratch_bytes(size_t n);
+void scalar_mul_g2_gls(const void* base, size_t base_stride, const void* scalars, size_t n, void* out, void* scratch, cudaStream_t s);
 void fixed_mul(int g, const void* table, const void* scalars, size_t n, void* out, cudaStream_t s);
 void aff_add(int g, const void* a, const void* b, size_t n, void* out, cudaStream_t s);
 void subset_sum(int g, const void* U, int m, const uint8_t* sel, size_t n, void* out, cudaStream_t s);

@@ -103,6 +103,9 @@ void emu_g1_mul_glv(const void* base, size_t stride, const void* s, size_t n, vo
 void emu_g2_mul_glv(const void* base, size_t stride, const void* s, size_t n, void* out) {
   for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32);
     Fp beta = GLV_BETA_G2; scalar_mul_glv<G2Jac, G2Aff>(r, b, k, beta); st(out, i, r); } }
+void emu_g2_mul_gls4(const void* base, size_t stride, const void* s, size_t n, void* out) {
+  for (size_t i = 0; i < n; i++) { G2Aff b = ld<G2Aff>(base, i * stride), r; uint32_t k[8]; memcpy(k, (const char*)s + 32 * i, 32);
+    Fp2 slice[kGlsSliceFp2]; scalar_mul_gls4(r, b, k, slice); st(out, i, r); } }
 // fixed base: table built with the GLV routine exactly as the engine does (scalars d << 8w)
 void emu_g1_mul_fixed(const void* base1, const void* s, size_t n, void* out) {
   static G1Aff table[kFixedWindows * kFixedEntries];

@@ -193,6 +193,16 @@ def test_glv_and_fixed_base_scalar_mul(emu):
     out = np.zeros(128 * n, np.uint8)
     emu.emu_g2_mul_glv(vp(Q), sz(1), vp(sb), sz(n), vp(out))
     assert (out == port.g2_mul_batch(Q, sb, n)).all()
+    # G2 by the 4-dimensional GLS ladder (psi endomorphism, 67-bit sub-scalars, 15-entry table), incl. an infinity base
+    Q2 = Q.copy()
+    Q2[128 * 5:128 * 6] = 0
+    lam4 = o.P % o.R
+    ks4 = ks + [lam4, lam4 - 1, lam4 * lam4 % o.R, pow(lam4, 3, o.R), (1 << 67) - 1, 1 << 66]
+    sb4 = common.scalar_bytes(ks4)
+    Q4 = np.concatenate([Q2, Q2[: 128 * (len(ks4) - n)]])
+    out = np.zeros(128 * len(ks4), np.uint8)
+    emu.emu_g2_mul_gls4(vp(Q4), sz(1), vp(sb4), sz(len(ks4)), vp(out))
+    assert (out == port.g2_mul_batch(Q4, sb4, len(ks4))).all()
     g1, _ = port.generators()
     out = np.zeros(64 * n, np.uint8)
     emu.emu_g1_mul_fixed(vp(g1), vp(sb), sz(n), vp(out))
