@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 # CTA lockstep barriers (the four warps of a CTA share instruction-cache lines).
 DEFAULT = ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"]
 NOLS = [f for f in DEFAULT if f != "-DBN254_CTA_LOCKSTEP"]
-UNITS = ["k_pairing", "k_group", "k_gt", "k_hash", "k_vm", "k_wvm", "k_fr", "engine"]
+UNITS = ["k_pairing", "k_group_mul", "k_group_fixed", "k_group_add", "k_gt", "k_hash", "k_vm", "k_wvm", "k_fr", "engine"]
 VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for every unit, or {unit: flags}
     "": DEFAULT,
     "nolockstep": NOLS,

@@ -1,0 +1,147 @@
+// Group family, table-driven kernels: fixed-base window tables, shared-point MSM (tables, partial sums, Jacobian tree).
+#include "kcommon.cuh"
+#include "curve.cuh"
+
+namespace bn254 {
+namespace {
+// fixed base: 32 windowed mixed additions from a precomputed affine table (L2-resident, 0.5-1 MB)
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A* table, const void* scalars, size_t n, void* out) {
+  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(scalars) + i * 32);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  A r;
+  scalar_mul_fixed<J, A>(r, table, s);
+  store_struct(out, i, r);
+}
+// ---- shared-point MSM (AFP25 / GWWW25: many coefficient vectors over the SAME tau-power points) ------------------
+// bibe/afp25_bibe/afp25_bibe_utils.go:45-55 computes sum_j [c_j] T_j as len independent ScalarMultiplications plus len
+// affine Adds (one inversion each), once per ciphertext, always over the public tau-power points.  Here the points get
+// per-point window tables once -- tables[(j * 32 + w) * 255 + d - 1] = [d * 2^(8w)] P_j, affine -- and every term of
+// every vector is 32 mixed additions with no doubling: 352 Fp-mul per term instead of ~2 300 for a GLV ladder.
+//
+// Table build: one thread per (point, window).  B = [2^(8w)] P by doublings, normalised once; the 255 multiples by
+// repeated mixed addition, kept Jacobian (X, Y in the table slot, Z in a scratch row) and normalised together with
+// ONE inversion per thread (Montgomery's trick over the 255 Z values, prefix products in a second scratch row).
+template <typename T> struct field_of;
+template <> struct field_of<G1Aff> { typedef Fp type; };
+template <> struct field_of<G2Aff> { typedef Fp2 type; };
+constexpr int kMsmWindows = launch::kMsmWindows;
+static_assert(kMsmWindows == kFixedWindows && launch::kMsmWindowBits == 8, "byte windows");
+
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_msm_tables(const void* pts, size_t len, A* tables,
+                                                                         typename field_of<A>::type* zs, typename field_of<A>::type* pf) {
+  typedef typename field_of<A>::type F;
+  cta_lockstep_set(false);
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len * (size_t)kMsmWindows) return;
+  size_t j = t / kMsmWindows;
+  int w = (int)(t % kMsmWindows);
+  A p; load_struct(p, pts, j);
+  A* row = tables + t * kFixedEntries;
+  F* zrow = zs + t * kFixedEntries;
+  F* prow = pf + t * kFixedEntries;
+  A zero; f_set_zero(zero.x); f_set_zero(zero.y);
+  if (aff_is_inf(p)) { for (int d = 0; d < kFixedEntries; d++) row[d] = zero; return; }
+  J b; b.x = p.x; b.y = p.y; f_set_one(b.z);
+  for (int i = 0; i < 8 * w; i++) jac_dbl(b, b);
+  A ba; jac_to_aff(ba, b);
+  if (aff_is_inf(ba)) { for (int d = 0; d < kFixedEntries; d++) row[d] = zero; return; }  // only off the prime-order subgroup
+  J acc; acc.x = ba.x; acc.y = ba.y; f_set_one(acc.z);
+  F run; f_set_one(run);
+  for (int d = 1; d <= kFixedEntries; d++) {
+    if (d > 1) jac_add_aff(acc, acc, ba);
+    bool inf = jac_is_inf(acc);  // d * B = 0: only for points of small order (never in G1 or the G2 subgroup)
+    A e; e.x = acc.x; e.y = acc.y;
+    F z = acc.z;
+    if (inf) { e = zero; f_set_one(z); }
+    row[d - 1] = e; zrow[d - 1] = z;
+    run = f_mul(run, z);
+    prow[d - 1] = run;
+  }
+  F inv = f_inv(run);
+  for (int d = kFixedEntries; d >= 1; d--) {
+    F zi = inv;
+    if (d > 1) { F pr = prow[d - 2]; zi = f_mul(inv, pr); }
+    F z = zrow[d - 1];
+    inv = f_mul(inv, z);
+    F zi2 = f_sqr(zi);
+    A e = row[d - 1];
+    e.x = f_mul(e.x, zi2);
+    e.y = f_mul(e.y, f_mul(zi2, zi));
+    row[d - 1] = e;  // (0, 0) stays (0, 0)
+  }
+}
+// partial[v * nchunks + c] = sum over the chunk's points j of sum_w tables[j][w][byte_w(s[v][j])] (Jacobian)
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_msm_partial(const A* __restrict__ tables, const void* scalars, size_t nvec, size_t len, int chunk, J* partial) {
+  cta_lockstep_set(false);
+  size_t nch = (len + chunk - 1) / chunk;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nvec * nch) return;
+  size_t v = t / nch, c = t % nch;
+  size_t first = c * (size_t)chunk, last = first + chunk < len ? first + chunk : len;
+  J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
+  for (size_t j = first; j < last; j++) {
+    uint32_t s[8];
+    load_scalar(s, scalars, v * len + j);
+    const A* tj = tables + j * (size_t)kMsmWindows * kFixedEntries;
+    for (int w = 0; w < kMsmWindows; w++) {
+      int d = (int)((s[w >> 2] >> ((w & 3) * 8)) & 0xFFu);
+      if (d) {
+        A e; load_struct(e, tj, (size_t)w * kFixedEntries + d - 1);
+        if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
+      }
+    }
+  }
+  partial[t] = acc;
+}
+// out[g * nch + c] = sum of the c-th chunk of group g's `len` Jacobian points; the last pass (nch == 1) may write affine
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_jac_sum(const J* in, size_t groups, int len, int chunk, J* out_j, void* out_a) {
+  cta_lockstep_set(false);
+  int nch = (len + chunk - 1) / chunk;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= groups * (size_t)nch) return;
+  size_t g = t / nch;
+  int c = (int)(t % nch);
+  int first = c * chunk, cnt = min(chunk, len - first);
+  J acc = in[g * (size_t)len + first];
+  for (int j = 1; j < cnt; j++) { J e = in[g * (size_t)len + first + j]; jac_add(acc, acc, e); }
+  if (out_a) { A r; jac_to_aff(r, acc); store_struct(out_a, t, r); }
+  else out_j[t] = acc;
+}
+
+}  // namespace
+
+namespace launch {
+
+static_assert(bn254::kFixedWindows == launch::kFixedWindows && bn254::kFixedEntries == launch::kFixedEntries, "launch.h out of date");
+#define BY_GROUP(g, call1, call2) do { if ((g) == 1) { call1; } else { call2; } } while (0)
+void fixed_mul(int g, const void* table, const void* scalars, size_t n, void* out, cudaStream_t s) {
+  BY_GROUP(g, (BN_LAUNCH, k_fixed_mul<G1Jac, G1Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G1Aff*>(table), scalars, n, out)),
+           (BN_LAUNCH, k_fixed_mul<G2Jac, G2Aff><<<grid_for(n), kBlock, 0, s>>>(static_cast<const G2Aff*>(table), scalars, n, out)));
+}
+void msm_tables(int g, const void* pts, size_t len, void* tables, void* zs, void* pf, cudaStream_t s) {
+  size_t threads = len * (size_t)kMsmWindows;
+  BY_GROUP(g, (BN_LAUNCH, k_msm_tables<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G1Aff*>(tables), static_cast<Fp*>(zs), static_cast<Fp*>(pf))),
+           (BN_LAUNCH, k_msm_tables<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(pts, len, static_cast<G2Aff*>(tables), static_cast<Fp2*>(zs), static_cast<Fp2*>(pf))));
+}
+void msm_partial(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s) {
+  size_t threads = nvec * ((len + chunk - 1) / chunk);
+  BY_GROUP(g, (BN_LAUNCH, k_msm_partial<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
+           (BN_LAUNCH, k_msm_partial<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
+}
+void jac_sum(int g, const void* in, size_t groups, int len, int chunk, void* out_j, void* out_a, cudaStream_t s) {
+  size_t threads = groups * (size_t)((len + chunk - 1) / chunk);
+  BY_GROUP(g, (BN_LAUNCH, k_jac_sum<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Jac*>(in), groups, len, chunk, static_cast<G1Jac*>(out_j), out_a)),
+           (BN_LAUNCH, k_jac_sum<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Jac*>(in), groups, len, chunk, static_cast<G2Jac*>(out_j), out_a)));
+}
+
+}  // namespace launch
+}  // namespace bn254
