@@ -15,6 +15,10 @@ import numpy as np  # noqa: E402
 from benchmarks.rows import SplitMix64, scalar_block  # noqa: E402
 from gopairingbasedcryptography_b200 import bn254, schemes  # noqa: E402
 
+import faulthandler  # noqa: E402
+
+faulthandler.dump_traceback_later(int(os.environ.get("BN254_DRIVER_WATCHDOG_S", "600")), exit=True)
+T0 = __import__("time").time()
 eng = bn254.Engine(0)
 n = 148 * 3 * 128
 R = bn254.R_MOD
@@ -26,6 +30,7 @@ units = []
 
 
 def mark(kernel, count, what):
+    print("%7.1f s  %s" % (__import__("time").time() - T0, kernel), file=sys.stderr, flush=True)
     units.append({"kernel": kernel, "units": count, "what": what})
 
 
@@ -66,4 +71,14 @@ ew.pair_batch(P[:2368], Q[:2368]); mark("k_wvm<1>", 2368, "pairings, one warp ea
 os.environ["BN254_IMPL"] = "vm"
 ev = bn254.Engine(0)
 ev.pair_batch(P[:17760], Q[:17760]); mark("k_vm<", 17760, "pairings, three lanes each (one pass of the grid)")
-print(json.dumps(units))
+print(json.dumps(units), flush=True)
+# explicit teardown, handles before their contexts (timestamps on stderr: a profiler attached to this process waits for it)
+import time  # noqa: E402
+
+for name in ("key", "table", "t3", "t2", "t1", "ev", "ew", "eng"):
+    t0 = time.time()
+    obj = globals().pop(name)
+    if hasattr(obj, "close"):
+        obj.close()
+    del obj
+    print("closed %s in %.2f s" % (name, time.time() - t0), file=sys.stderr, flush=True)

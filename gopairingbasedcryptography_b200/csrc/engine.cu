@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -69,6 +70,8 @@ struct bn254_ctx {
   // (host-buffer entry points return synchronously), so a table is never rebuilt under a running kernel.
   std::vector<FixedTable> cache;
   uint64_t clock = 0;
+  // device allocations of live table / line handles: released with the context if the caller never destroyed them
+  std::set<void*> handle_mem;
 };
 
 namespace {
@@ -555,6 +558,26 @@ int hash_to_curve_host(bn254_ctx* ctx, int G, const uint8_t* msgs, const uint64_
 
 }  // namespace
 
+// Live contexts.  Table / line handles point at their context; destroying a handle AFTER its context (a garbage-collected
+// host language gives no destruction order) must not touch the freed context: the handle's device memory went with the
+// context's device allocations, so only the host struct is released.
+static std::mutex g_live_mu;
+static std::set<bn254_ctx*> g_live;
+// Runs `release` under the context lock when the handle's context is still alive; returns false when it is gone.
+template <typename F>
+static bool with_live_ctx(bn254_ctx* ctx, F release) {
+  std::lock_guard<std::mutex> reg(g_live_mu);
+  if (!g_live.count(ctx)) return false;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  release();
+  return true;
+}
+
+static void release_handle_mem(bn254_ctx* ctx, void* p) {  // under ctx->mu
+  if (p && ctx->handle_mem.erase(p)) cudaFree(p);
+}
+
 extern "C" {
 
 int bn254_device_count(void) {
@@ -611,12 +634,14 @@ int bn254_ctx_create(int device, bn254_ctx** out) {
     }
     cudaGetLastError();
   }
+  { std::lock_guard<std::mutex> reg(g_live_mu); g_live.insert(ctx); }
   *out = ctx;
   return BN254_OK;
 }
 
 void bn254_ctx_destroy(bn254_ctx* ctx) {
   if (!ctx) return;
+  { std::lock_guard<std::mutex> reg(g_live_mu); g_live.erase(ctx); }  // no-op for a half-built context
   cudaSetDevice(ctx->device);
   for (int i = 0; i < 2; i++) {
     Slot& s = ctx->slot[i];
@@ -628,6 +653,7 @@ void bn254_ctx_destroy(bn254_ctx* ctx) {
   }
   if (ctx->vm_cold_dev) cudaFree(ctx->vm_cold_dev);
   for (FixedTable& t : ctx->cache) cudaFree(t.dev);
+  for (void* p : ctx->handle_mem) cudaFree(p);
   if (ctx->vm_dev_done) cudaEventDestroy(ctx->vm_dev_done);
   delete ctx;
 }
@@ -757,15 +783,13 @@ int bn254_g2_lines_create(bn254_ctx* ctx, const void* Q, size_t m, bn254_lines**
   if (e == cudaSuccess) { L::g2_lines(s.d, m, Lt->table, Lt->qskip, s.stream); e = cudaGetLastError(); }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   if (e != cudaSuccess) { cudaFree(Lt->table); cudaFree(Lt->qskip); delete Lt; cudaGetLastError(); return fail(ctx, cu_code(e), "line table build", e); }
+  ctx->handle_mem.insert(Lt->table); ctx->handle_mem.insert(Lt->qskip);
   *out = Lt;
   return BN254_OK;
 }
 void bn254_g2_lines_destroy(bn254_lines* Lt) {
   if (!Lt) return;
-  std::lock_guard<std::mutex> lk(Lt->ctx->mu);
-  cudaSetDevice(Lt->ctx->device);
-  cudaFree(Lt->table);
-  cudaFree(Lt->qskip);
+  with_live_ctx(Lt->ctx, [&] { release_handle_mem(Lt->ctx, Lt->table); release_handle_mem(Lt->ctx, Lt->qskip); });
   delete Lt;
 }
 size_t bn254_g2_lines_count(const bn254_lines* Lt) { return Lt ? Lt->m : 0; }
@@ -843,14 +867,13 @@ int bn254_fixed_base_create(bn254_ctx* ctx, int group, const void* base, bn254_f
   bn254_fixed_base* h = new bn254_fixed_base{ctx, FixedTable()};
   int rc = build_fixed_table(ctx, group, base, &h->t);
   if (rc) { delete h; return rc; }
+  ctx->handle_mem.insert(h->t.dev);
   *out = h;
   return BN254_OK;
 }
 void bn254_fixed_base_destroy(bn254_fixed_base* h) {
   if (!h) return;
-  std::lock_guard<std::mutex> lk(h->ctx->mu);
-  cudaSetDevice(h->ctx->device);
-  cudaFree(h->t.dev);
+  with_live_ctx(h->ctx, [&] { release_handle_mem(h->ctx, h->t.dev); });
   delete h;
 }
 int bn254_fixed_base_group(const bn254_fixed_base* h) { return h ? h->t.group : 0; }
@@ -894,14 +917,13 @@ int bn254_msm_table_create(bn254_ctx* ctx, int group, const void* points, size_t
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   cudaFree(zs); cudaFree(pf);
   if (e != cudaSuccess) { cudaFree(tables); cudaGetLastError(); return fail(ctx, cu_code(e), "MSM table build", e); }
+  ctx->handle_mem.insert(tables);
   *out = new bn254_msm_table{ctx, group, len, tables};
   return BN254_OK;
 }
 void bn254_msm_table_destroy(bn254_msm_table* T) {
   if (!T) return;
-  std::lock_guard<std::mutex> lk(T->ctx->mu);
-  cudaSetDevice(T->ctx->device);
-  cudaFree(T->tables);
+  with_live_ctx(T->ctx, [&] { release_handle_mem(T->ctx, T->tables); });
   delete T;
 }
 size_t bn254_msm_table_len(const bn254_msm_table* T) { return T ? T->len : 0; }

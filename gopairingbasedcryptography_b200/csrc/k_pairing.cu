@@ -1,6 +1,8 @@
 // Pairing-family kernels: Pair, multi-pairing, PairingCheck, Miller loop, final exponentiation, G2 line tables.
 // One batch element per thread.  AoS operands are read with 128-bit loads; every element is 64/128/384 B so a warp
 // touches a contiguous 2-12 KB span (fully used sectors).
+#include <stdlib.h>
+
 #include "kcommon.cuh"
 #include "pairing.cuh"
 
@@ -74,7 +76,15 @@ __device__ __forceinline__ void cta_store(void* base, size_t first, size_t n_lef
   int total = (int)min((size_t)kBlock, n_left) * Q4;
   for (int w = threadIdx.x; w < total; w += kBlock) dst[w] = stage[w];
 }
-__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P, const void* Q, size_t n, void* out) {
+// Start stagger (cycles, CTA-uniform): see launch::pair.
+__device__ __forceinline__ void cta_stagger(unsigned stagger, unsigned mode) {
+  if (stagger == 0) return;
+  unsigned slot = mode == 0 ? blockIdx.x % 3u : ((blockIdx.x * 2654435761u) >> 16) % 16u;
+  long long wait = (long long)slot * stagger, t0 = clock64();
+  while (clock64() - t0 < wait) { }
+}
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_pair(const void* P, const void* Q, size_t n, void* out, unsigned stagger, unsigned stagger_mode) {
+  cta_stagger(stagger, stagger_mode);
   size_t first = (size_t)blockIdx.x * blockDim.x;
   size_t i = first + threadIdx.x;
   G1Aff p; G2Aff q; G2Proj T;
@@ -277,7 +287,9 @@ cudaError_t pairing_init() {
 int pairing_wave_threads(int sms) { return sms * BN254_MIN_BLOCKS * kBlock; }
 
 void pair(const void* P, const void* Q, size_t n, void* out, cudaStream_t s) {
-  BN_LAUNCH, k_pair<<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out);
+  static const unsigned stagger = getenv("BN254_STAGGER") ? (unsigned)atoi(getenv("BN254_STAGGER")) : 0u;
+  static const unsigned mode = getenv("BN254_STAGGER_MODE") ? (unsigned)atoi(getenv("BN254_STAGGER_MODE")) : 0u;
+  BN_LAUNCH, k_pair<<<grid_for(n), kBlock, kTowerSmem, s>>>(P, Q, n, out, stagger, mode);
 }
 void multi_pair(int mode, const void* P, const void* Q, size_t n, int k, void* out, cudaStream_t s) {
   if (mode == 0) launch_multi_pair<0>(P, Q, n, k, out, s);

@@ -48,7 +48,9 @@ extern "C" {
 
 typedef struct bn254_ctx bn254_ctx;
 
-/* lifecycle: one context per GPU ordinal */
+/* lifecycle: one context per GPU ordinal.  bn254_ctx_destroy also releases the device memory of every table / line
+ * handle created on the context that is still alive; destroying such a handle AFTERWARDS is allowed (a garbage-collected
+ * host gives no destruction order) and only frees the handle itself.  Using it in any other call is an error. */
 int bn254_ctx_create(int device, bn254_ctx** out);
 void bn254_ctx_destroy(bn254_ctx* ctx);
 const char* bn254_last_error(bn254_ctx* ctx); /* text of the last failure on this context */

@@ -433,3 +433,33 @@ def test_subset_sum_byte_window_tables(engine):
         plain = np.concatenate([f(U, sel[i:i + 1000]) for i in range(0, n, 1000)])  # chunks below the threshold: per-bit path
         assert (tab == plain).all()
         assert (tab[0] == U[0]).all()
+
+
+def test_handles_may_outlive_their_context():
+    """A garbage-collected host destroys objects in no particular order: table / line handles destroyed AFTER their
+    context must neither hang nor crash (round 2: an interpreter with module-scope handles never exited), and the
+    context's destruction releases their device memory."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from gopairingbasedcryptography_b200 import bn254
+eng = bn254.Engine(0)
+g1 = np.frombuffer(bn254.Generators()[2].raw, dtype=np.uint8).copy()
+g2 = np.frombuffer(bn254.Generators()[3].raw, dtype=np.uint8).copy()
+s = bn254.scalars_to_bytes(list(range(2, 66)))
+t1 = eng.fixed_base_create(1, g1)
+P = eng.g1_fixed_mul_batch(t1, s)
+Q = eng.g2_mul_base_batch(g2, s)
+lines = eng.g2_lines_create(Q[:5])
+msm = eng.msm_table_create(1, P[:8])
+eng.close()                       # context first ...
+for h in (t1, lines, msm):        # ... handles afterwards
+    h.close()
+print("ok")
+""" % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-800:]
