@@ -289,6 +289,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(t.item())
 
+    # ---- ONE process driving all N GPUs (the Go host's shape): rank 0 opens a context on every GPU of the job and
+    # splits the same 2^20-pair host batch ceil(n/N) per device from N host threads (sharding.DevicePool); the other
+    # ranks wait at the barrier with their GPUs idle.  Host buffers, copies inside the timed region.
+    one_process = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            from gopairingbasedcryptography_b200.sharding import DevicePool
+
+            pool_out = torch.empty((n, 384), dtype=torch.uint8).pin_memory().numpy()
+            with DevicePool(devices=range(world)) as pool:
+                pool.pair_batch(hP_np, hQ_np, out=pool_out)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    pool.pair_batch(hP_np, hQ_np, out=pool_out)
+                dt = (time.perf_counter() - t0) / args.steps
+            assert (pool_out == out_host).all(), "one-process dispatcher and single-GPU path disagree"
+            one_process = {"contexts": world, "host_threads": world, "value": n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
+                           "workload": "the same ONE batch of 2^%d pairs, host buffers, split over %d GPUs by ONE process" % (args.log2_batch, world),
+                           "parity": "== the single-GPU result on all %d pairings" % n}
+            del pool_out
+        barrier()
+
     # ---- verification (outside the timed regions): sampled bit-exact parity + device == host path ----
     from oracle import port
 
@@ -319,7 +342,7 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 192, "d2h_bytes_per_step": n * 384},
             "gpu_launches": launches,
-            "strong_2p20": strong,
+            "strong_2p20": dict(strong, one_process=one_process),
             "rows": rows,
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T limb-MAC/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PAIRING * n,

@@ -22,16 +22,26 @@ imad = {}
 NAMES = {"k_pair": "pair", "k_check2_fixed_g1": "bls_verify", "k_scalar_mul<bn254::G1Jac": "g1_var", "k_scalar_mul_g2_gls": "g2_var",
          "k_fixed_mul<G1": "g1_fixed", "k_fixed_mul<G2": "g2_fixed", "k_gt_exp<0>": "gt_exp", "k_gt_exp<1>": "gt_cyclo_exp", "k_gt_fixed_exp": "gt_fixed_exp",
          "k_miller_lines": "bsw07_decrypt_policy_lines"}
-for (i, name), m in rows.items():
+def short_name(name):
     short = name.replace("void <unnamed>::", "").replace("void bn254::<unnamed>::", "").split("(")[0]
-    short = short.replace("bn254::", "")
-    u = next((x for x in units if x["kernel"].replace("bn254::", "") in short and x.get("used") is None and m.get("launch__grid_size", 0) > 8), None)
+    return short.replace("bn254::", "")
+
+
+# a unit count belongs to the LARGEST launch of its kernel (table builds launch the same kernels on small grids)
+owner = {}
+for u in units:
+    key = u["kernel"].replace("bn254::", "")
+    cands = [(m.get("launch__grid_size", 0), k) for k, m in rows.items() if key in short_name(k[1]) and k not in owner]
+    if cands:
+        owner[max(cands)[1]] = u
+for (i, name), m in rows.items():
+    short = short_name(name)
+    u = owner.get((i, name))
     t = m.get("gpu__time_duration.sum", 0) / 1e6
     fm = m.get("sm__inst_executed_pipe_fmaheavy.sum", float("nan")) * 32
     dram = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
     extra = ""
-    if u is not None and m.get("launch__grid_size", 0) >= 16:
-        u["used"] = True
+    if u is not None:
         extra = "%9d %14.4g %12.4g" % (u["units"], fm / u["units"], dram / u["units"])
         for k_, row in NAMES.items():
             if k_.replace("bn254::", "") in short:

@@ -581,6 +581,13 @@ class G2Lines:
             pass
 
 
+def device_count():
+    """Number of CUDA devices the library sees (bn254_device_count); contexts can only be created on B200s."""
+    fn = _native.lib().bn254_device_count
+    fn.restype = ctypes.c_int
+    return int(fn())
+
+
 _default = None
 _default_lock = threading.Lock()
 
