@@ -138,6 +138,11 @@ def measure_rows(eng, peak, rank=0, world=1, dist=None, quick=False, cpu=True):
         return {"value": n_units / dt, "unit": "units/s", "cores": T, "kind": "port", "sample": sample + "; C restatement of gnark (gnark itself cannot run here: no Go)"}
 
     up = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1).view(np.uint8)).to(dev)
+    # the e2e legs hand the library PAGE-LOCKED caller buffers (north_star: pinned host buffers): operands and result are
+    # copied to / from the device directly; pageable buffers would add a staging memcpy and, for fresh result arrays,
+    # first-touch page faults to every call
+    hpin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hout = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8).pin_memory().numpy()
     port = None
     if cpu:
         from oracle import port  # checker / CPU baseline only
@@ -149,31 +154,34 @@ def measure_rows(eng, peak, rank=0, world=1, dist=None, quick=False, cpu=True):
     Pn = eng.g1_fixed_mul_batch(t_g1, sb)  # 2n points
     Qn = eng.g2_fixed_mul_batch(t_g2, sb[:n])
     dP, dQ, dS = up(Pn), up(Qn), up(sb)
+    Pn_h, Qn_h, sb_h = hpin(Pn), hpin(Qn), hpin(sb)
+    h1, h2 = hout(2 * n * 64), hout(n * 128)
     o1 = torch.empty(2 * n * 64, dtype=torch.uint8, device=dev)
     o2 = torch.empty(n * 128, dtype=torch.uint8, device=dev)
 
     # ---- scalar multiplication -----------------------------------------------------------------------------------
     cs = 4096
     ds = dev_time(lambda: eng.dev("g1_fixed_mul_batch_dev", t_g1, dS.data_ptr(), 2 * n, o1.data_ptr(), stream=stream))
-    es, out = host_time(lambda: eng.g1_fixed_mul_batch(t_g1, sb))
+    es, out = host_time(lambda: eng.g1_fixed_mul_batch(t_g1, sb_h, out=h1))
     add("g1_fixed", "scalar-mults/s", 2 * n, ds, es, 2 * n * 32, 2 * n * 64,
         cpu_base(lambda: port.g1_mul_base_batch(g1, sb[:cs].reshape(-1), cs, T), cs, "%d G1 ScalarMultiplicationBase on %d threads" % (cs, T)),
         "ScalarMultiplicationBase through an explicit 32x255 window-table handle")
     ds = dev_time(lambda: eng.dev("g2_fixed_mul_batch_dev", t_g2, dS.data_ptr(), n, o2.data_ptr(), stream=stream))
-    es, out = host_time(lambda: eng.g2_fixed_mul_batch(t_g2, sb[:n]))
+    es, out = host_time(lambda: eng.g2_fixed_mul_batch(t_g2, sb_h[:n], out=h2))
     add("g2_fixed", "scalar-mults/s", n, ds, es, n * 32, n * 128,
         cpu_base(lambda: port.g2_mul_base_batch(g2, sb[:cs].reshape(-1), cs, T), cs, "%d G2 ScalarMultiplicationBase on %d threads" % (cs, T)))
     sb2 = np.roll(sb, 1, axis=0)
     dS2 = up(sb2)
+    sb2_h = hpin(sb2)
     ds = dev_time(lambda: eng.dev("g1_mul_batch_dev", dP.data_ptr(), 1, dS2.data_ptr(), n, o1.data_ptr(), stream=stream))
-    es, out = host_time(lambda: eng.g1_mul_batch(Pn[:n], sb2[:n]))
+    es, out = host_time(lambda: eng.g1_mul_batch(Pn_h[:n], sb2_h[:n], out=h1[:n * 64]))
     if cpu:
         assert (out[:64].reshape(-1) == port.g1_mul_batch(Pn[:64].reshape(-1), sb2[:64].reshape(-1), 64, T)).all()
     add("g1_var", "scalar-mults/s", n, ds, es, n * 96, n * 64,
         cpu_base(lambda: port.g1_mul_batch(Pn[:cs].reshape(-1), sb2[:cs].reshape(-1), cs, T), cs, "%d G1 ScalarMultiplication on %d threads" % (cs, T)),
         "G1Affine.ScalarMultiplication, 2-dim GLV, lane-uniform ladder")
     ds = dev_time(lambda: eng.dev("g2_mul_batch_dev", dQ.data_ptr(), 1, dS2.data_ptr(), n, o2.data_ptr(), stream=stream))
-    es, out = host_time(lambda: eng.g2_mul_batch(Qn, sb2[:n]))
+    es, out = host_time(lambda: eng.g2_mul_batch(Qn_h, sb2_h[:n], out=h2))
     if cpu:
         assert (out[:64].reshape(-1) == port.g2_mul_batch(Qn[:64].reshape(-1), sb2[:64].reshape(-1), 64, T)).all()
     add("g2_var", "scalar-mults/s", n, ds, es, n * 160, n * 128,
@@ -184,20 +192,21 @@ def measure_rows(eng, peak, rank=0, world=1, dist=None, quick=False, cpu=True):
     ng = 1 << (12 if quick else 16)
     gt = eng.pair_batch(Pn[:ng], Qn[:ng])
     dG = up(gt)
+    gt_h, hG = hpin(gt), hout(ng * 384)
     oG = torch.empty(ng * 384, dtype=torch.uint8, device=dev)
     cg = 512
     ds = dev_time(lambda: eng.dev("gt_cyclo_exp_batch_dev", dG.data_ptr(), 1, dS.data_ptr(), ng, oG.data_ptr(), stream=stream), reps=2)
-    es, out = host_time(lambda: eng.gt_cyclo_exp_batch(gt, sb[:ng]))
+    es, out = host_time(lambda: eng.gt_cyclo_exp_batch(gt_h, sb_h[:ng], out=hG))
     if cpu:
         assert (out[:16].reshape(-1) == port.gt_exp_batch(gt[:16].reshape(-1), sb[:16].reshape(-1), 16, T)).all()
     base_gt = cpu_base(lambda: port.gt_exp_batch(gt[:cg].reshape(-1), sb[:cg].reshape(-1), cg, T), cg, "%d generic GT.Exp (gnark's E12.Exp shape) on %d threads" % (cg, T))
     add("gt_cyclo_exp", "exps/s", ng, ds, es, ng * 416, ng * 384, base_gt, "GT.Exp for elements of GT proper: GLV split of the exponent, Granger-Scott squarings")
     ds = dev_time(lambda: eng.dev("gt_exp_batch_dev", dG.data_ptr(), 1, dS.data_ptr(), ng, oG.data_ptr(), stream=stream), reps=2)
-    es, out = host_time(lambda: eng.gt_exp_batch(gt, sb[:ng]))
+    es, out = host_time(lambda: eng.gt_exp_batch(gt_h, sb_h[:ng], out=hG))
     add("gt_exp", "exps/s", ng, ds, es, ng * 416, ng * 384, base_gt, "GT.Exp generic Fp12 ladder (no subgroup assumption)")
     t_gt = eng.fixed_base_create(3, gt[0])
     ds = dev_time(lambda: eng.dev("gt_fixed_exp_batch_dev", t_gt, dS.data_ptr(), ng, oG.data_ptr(), stream=stream))
-    es, out = host_time(lambda: eng.gt_fixed_exp_batch(t_gt, sb[:ng]))
+    es, out = host_time(lambda: eng.gt_fixed_exp_batch(t_gt, sb_h[:ng], out=hG))
     add("gt_fixed_exp", "exps/s", ng, ds, es, ng * 32, ng * 384, base_gt, "GT.Exp of ONE base (waters05 e(g1,g2)^alpha): fixed-base table handle")
 
     # ---- BLS verify (BASELINE metric: BLS verifies/sec) ----------------------------------------------------------
@@ -211,7 +220,8 @@ def measure_rows(eng, peak, rank=0, world=1, dist=None, quick=False, cpu=True):
     okd = torch.empty(nb, dtype=torch.uint8, device=dev)
     ds = dev_time(lambda: eng.dev("pairing_check2_fixed_g1_batch_dev", d01.data_ptr(), dH.data_ptr(), dSig.data_ptr(), nb, okd.data_ptr(), stream=stream), reps=2)
     assert bool(okd.all().item())
-    es, ok = host_time(lambda: eng.pairing_check2_fixed_g1_batch(pk, negg1, hm, sig))
+    hm_h, sig_h, ok_h = hpin(hm), hpin(sig), hout(nb)
+    es, ok = host_time(lambda: eng.pairing_check2_fixed_g1_batch(pk, negg1, hm_h, sig_h, out=ok_h))
     assert ok.all()
     cb = 1024
     base = None

@@ -100,14 +100,7 @@ class Engine:
         raise EngineError("%s: %s" % (_ERRORS.get(rc, rc), self._lib.bn254_last_error(self._h).decode()))
 
     def _call(self, name, bufs, sizes, out_bytes, n, out_dtype=np.uint8, pre_sizes=None, mid_sizes=None, out=None):
-        if out is None:
-            out = np.empty(n * out_bytes, dtype=np.uint8)
-        else:  # caller-owned result buffer (page-locked memory is filled by direct device->host copies)
-            if not isinstance(out, np.ndarray) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
-                raise ValueError("out must be a writable C-contiguous numpy array (a strided view would be copied, not filled)")
-            out = out.reshape(-1).view(np.uint8)
-            if out.size != n * out_bytes:
-                raise ValueError("invalid inputs sizes")
+        out = self._out(out, n * out_bytes)
         fn = getattr(self._lib, name)
         if pre_sizes is not None:  # (ctx, buf0, size..., buf1, size..., out) argument order
             args = [self._h, bufs[0].ctypes.data_as(ctypes.c_void_p)] + [ctypes.c_size_t(s) for s in pre_sizes]
@@ -117,6 +110,19 @@ class Engine:
         args.append(out.ctypes.data_as(ctypes.c_void_p))
         fn.restype = ctypes.c_int
         self._check(fn(*args))
+        return out
+
+    @staticmethod
+    def _out(out, nbytes):
+        """Result buffer: a fresh array, or the caller's (`out=`; page-locked memory -- bn254_host_alloc,
+        torch.Tensor.pin_memory -- is filled by direct device->host copies, no staging memcpy, no page faults)."""
+        if out is None:
+            return np.empty(nbytes, dtype=np.uint8)
+        if not isinstance(out, np.ndarray) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+            raise ValueError("out must be a writable C-contiguous numpy array (a strided view would be copied, not filled)")
+        out = out.reshape(-1).view(np.uint8)
+        if out.size != nbytes:
+            raise ValueError("invalid inputs sizes")
         return out
 
     # ---- pairings -------------------------------------------------------------------------
@@ -179,31 +185,31 @@ class Engine:
         return self._call("bn254_final_exp_batch", [f], [n], GT_BYTES, n).reshape(n, GT_BYTES)
 
     # ---- groups ---------------------------------------------------------------------------
-    def _mul(self, name, base, scalars, pt_bytes, broadcast):
+    def _mul(self, name, base, scalars, pt_bytes, broadcast, out=None):
         base, scalars = _u8(base, pt_bytes, "base"), _u8(scalars, SCALAR_BYTES, "scalars")
         n = scalars.size // SCALAR_BYTES
         if (broadcast and base.size != pt_bytes) or (not broadcast and base.size // pt_bytes != n):
             raise ValueError("invalid inputs sizes")
-        return self._call(name, [base, scalars], [n], pt_bytes, n).reshape(n, pt_bytes)
+        return self._call(name, [base, scalars], [n], pt_bytes, n, out=out).reshape(n, pt_bytes)
 
-    def g1_mul_batch(self, base, scalars):
-        return self._mul("bn254_g1_mul_batch", base, scalars, G1_BYTES, False)
+    def g1_mul_batch(self, base, scalars, out=None):
+        return self._mul("bn254_g1_mul_batch", base, scalars, G1_BYTES, False, out)
 
-    def g2_mul_batch(self, base, scalars):
-        return self._mul("bn254_g2_mul_batch", base, scalars, G2_BYTES, False)
+    def g2_mul_batch(self, base, scalars, out=None):
+        return self._mul("bn254_g2_mul_batch", base, scalars, G2_BYTES, False, out)
 
-    def g1_mul_base_batch(self, base1, scalars):
-        return self._mul("bn254_g1_mul_base_batch", base1, scalars, G1_BYTES, True)
+    def g1_mul_base_batch(self, base1, scalars, out=None):
+        return self._mul("bn254_g1_mul_base_batch", base1, scalars, G1_BYTES, True, out)
 
-    def g2_mul_base_batch(self, base1, scalars):
-        return self._mul("bn254_g2_mul_base_batch", base1, scalars, G2_BYTES, True)
+    def g2_mul_base_batch(self, base1, scalars, out=None):
+        return self._mul("bn254_g2_mul_base_batch", base1, scalars, G2_BYTES, True, out)
 
-    def _binary(self, name, a, b, item):
+    def _binary(self, name, a, b, item, out=None):
         a, b = _u8(a, item, "a"), _u8(b, item, "b")
         if a.size != b.size:
             raise ValueError("invalid inputs sizes")
         n = a.size // item
-        return self._call(name, [a, b], [n], item, n).reshape(n, item)
+        return self._call(name, [a, b], [n], item, n, out=out).reshape(n, item)
 
     def g1_add_batch(self, a, b):
         return self._binary("bn254_g1_add_batch", a, b, G1_BYTES)
@@ -244,57 +250,58 @@ class Engine:
         return self._segment_sum("bn254_g2_sum_batch", pts, length, G2_BYTES)
 
     # ---- GT -------------------------------------------------------------------------------
-    def gt_exp_batch(self, x, k):
+    def gt_exp_batch(self, x, k, out=None):
         x, k = _u8(x, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
         n = k.size // SCALAR_BYTES
         if x.size // GT_BYTES != n:
             raise ValueError("invalid inputs sizes")
-        return self._call("bn254_gt_exp_batch", [x, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+        return self._call("bn254_gt_exp_batch", [x, k], [n], GT_BYTES, n, out=out).reshape(n, GT_BYTES)
 
-    def gt_exp_base_batch(self, x1, k):
+    def gt_exp_base_batch(self, x1, k, out=None):
         x1, k = _u8(x1, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
         n = k.size // SCALAR_BYTES
         if x1.size != GT_BYTES:
             raise ValueError("invalid inputs sizes")
-        return self._call("bn254_gt_exp_base_batch", [x1, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+        return self._call("bn254_gt_exp_base_batch", [x1, k], [n], GT_BYTES, n, out=out).reshape(n, GT_BYTES)
 
-    def gt_cyclo_exp_batch(self, x, k):
+    def gt_cyclo_exp_batch(self, x, k, out=None):
         """x[i]^k[i] for x in the cyclotomic subgroup (pairing outputs and their products/powers)."""
         x, k = _u8(x, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
         n = k.size // SCALAR_BYTES
         if x.size // GT_BYTES != n:
             raise ValueError("invalid inputs sizes")
-        return self._call("bn254_gt_cyclo_exp_batch", [x, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+        return self._call("bn254_gt_cyclo_exp_batch", [x, k], [n], GT_BYTES, n, out=out).reshape(n, GT_BYTES)
 
-    def gt_cyclo_exp_base_batch(self, x1, k):
+    def gt_cyclo_exp_base_batch(self, x1, k, out=None):
         x1, k = _u8(x1, GT_BYTES, "x"), _u8(k, SCALAR_BYTES, "k")
         n = k.size // SCALAR_BYTES
         if x1.size != GT_BYTES:
             raise ValueError("invalid inputs sizes")
-        return self._call("bn254_gt_cyclo_exp_base_batch", [x1, k], [n], GT_BYTES, n).reshape(n, GT_BYTES)
+        return self._call("bn254_gt_cyclo_exp_base_batch", [x1, k], [n], GT_BYTES, n, out=out).reshape(n, GT_BYTES)
 
-    def gt_mul_batch(self, a, b):
-        return self._binary("bn254_gt_mul_batch", a, b, GT_BYTES)
+    def gt_mul_batch(self, a, b, out=None):
+        return self._binary("bn254_gt_mul_batch", a, b, GT_BYTES, out)
 
-    def gt_div_batch(self, a, b):
-        return self._binary("bn254_gt_div_batch", a, b, GT_BYTES)
+    def gt_div_batch(self, a, b, out=None):
+        return self._binary("bn254_gt_div_batch", a, b, GT_BYTES, out)
 
     def fp_mul_batch(self, a, b):
         return self._binary("bn254_fp_mul_batch", a, b, 32)
 
-    def pairing_check2_fixed_g1_batch(self, p0, p1, q0, q1):
-        """ok[i] = PairingCheck([p0, p1], [q0[i], q1[i]]): two G1 points shared by the batch (BLS verification shape)."""
+    def pairing_check2_fixed_g1_batch(self, p0, p1, q0, q1, out=None):
+        """ok[i] = PairingCheck([p0, p1], [q0[i], q1[i]]): two G1 points shared by the batch (BLS verification shape).
+        out: optional caller-owned (n,) uint8 buffer for the 0/1 results (returned as a bool view)."""
         p01 = np.concatenate([_u8(p0, G1_BYTES, "p0"), _u8(p1, G1_BYTES, "p1")])
         q0, q1 = _u8(q0, G2_BYTES, "q0"), _u8(q1, G2_BYTES, "q1")
         if p01.size != 2 * G1_BYTES or q0.size != q1.size:
             raise ValueError("invalid inputs sizes")
         n = q0.size // G2_BYTES
-        out = np.empty(n, dtype=np.uint8)
+        out = self._out(out, n)
         fn = self._lib.bn254_pairing_check2_fixed_g1_batch
         fn.restype = ctypes.c_int
         self._check(fn(self._h, p01.ctypes.data_as(ctypes.c_void_p), q0.ctypes.data_as(ctypes.c_void_p),
                        q1.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
-        return out.astype(bool)
+        return out.view(bool)
 
     # ---- hash-to-curve (gnark bn254.HashToG1 / HashToG2; hash/hash_to.go in the reference) ----
     def _hash_to_curve(self, name, msgs, dst, out_bytes):
@@ -347,25 +354,25 @@ class Engine:
         self._check(fn(self._h, ctypes.c_int(int(group)), base.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h)))
         return FixedBase(self, h, int(group))
 
-    def _fixed(self, name, table, scalars, item, group):
+    def _fixed(self, name, table, scalars, item, group, out=None):
         if table.engine is not self or table.group != group:
             raise ValueError("fixed-base handle of another engine or group")
         scalars = _u8(scalars, SCALAR_BYTES, "scalars")
         n = scalars.size // SCALAR_BYTES
-        out = np.empty(n * item, dtype=np.uint8)
+        out = self._out(out, n * item)
         fn = getattr(self._lib, name)
         fn.restype = ctypes.c_int
         self._check(fn(self._h, table.handle, scalars.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), out.ctypes.data_as(ctypes.c_void_p)))
         return out.reshape(n, item)
 
-    def g1_fixed_mul_batch(self, table, scalars):
-        return self._fixed("bn254_g1_fixed_mul_batch", table, scalars, G1_BYTES, 1)
+    def g1_fixed_mul_batch(self, table, scalars, out=None):
+        return self._fixed("bn254_g1_fixed_mul_batch", table, scalars, G1_BYTES, 1, out)
 
-    def g2_fixed_mul_batch(self, table, scalars):
-        return self._fixed("bn254_g2_fixed_mul_batch", table, scalars, G2_BYTES, 2)
+    def g2_fixed_mul_batch(self, table, scalars, out=None):
+        return self._fixed("bn254_g2_fixed_mul_batch", table, scalars, G2_BYTES, 2, out)
 
-    def gt_fixed_exp_batch(self, table, k):
-        return self._fixed("bn254_gt_fixed_exp_batch", table, k, GT_BYTES, 3)
+    def gt_fixed_exp_batch(self, table, k, out=None):
+        return self._fixed("bn254_gt_fixed_exp_batch", table, k, GT_BYTES, 3, out)
 
     def msm_table_create(self, group, points):
         """Per-point byte-window tables of `len` shared points (bn254_msm_table_create): group 1 = G1, 2 = G2."""
