@@ -171,6 +171,7 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")  # host-side wait for the one-process leg (an NCCL barrier would spin ON the GPUs it measures)
     torch.cuda.set_device(local)
     eng = bn254.Engine(local)
     n = 1 << args.log2_batch
@@ -310,6 +311,7 @@ def main():
                            "workload": "the same ONE batch of 2^%d pairs, host buffers, split over %d GPUs by ONE process" % (args.log2_batch, world),
                            "parity": "== the single-GPU result on all %d pairings" % n}
             del pool_out
+        dist.barrier(group=cpu_group)  # the other ranks block on the host here: their GPUs stay idle for rank 0's contexts
         barrier()
 
     # ---- verification (outside the timed regions): sampled bit-exact parity + device == host path ----
