@@ -273,18 +273,24 @@ func GTExpBaseBatch(x *GT, k []Scalar) ([]GT, error) {
 	return out, err
 }
 
-// GTMulBatch / GTDivBatch: out[i] = a[i] * b[i], a[i] / b[i].
-func GTMulBatch(a, b []GT) ([]GT, error) { return gtBinary(a, b, false) }
-func GTDivBatch(a, b []GT) ([]GT, error) { return gtBinary(a, b, true) }
+// GTMulBatch / GTDivBatch: out[i] = a[i] * b[i], a[i] / b[i].  GTDivCyclotomicBatch: the same quotient for divisors in
+// GT proper (pairing outputs and their products / powers -- the divisor of every Div in the reference's decryption
+// flows): b^-1 = conj(b), so it is one Fp12 product instead of an inversion and a product.
+func GTMulBatch(a, b []GT) ([]GT, error)           { return gtBinary(a, b, 0) }
+func GTDivBatch(a, b []GT) ([]GT, error)           { return gtBinary(a, b, 1) }
+func GTDivCyclotomicBatch(a, b []GT) ([]GT, error) { return gtBinary(a, b, 2) }
 
-func gtBinary(a, b []GT, div bool) ([]GT, error) {
+func gtBinary(a, b []GT, mode int) ([]GT, error) {
 	if len(a) != len(b) {
 		return nil, ErrInvalidSizes
 	}
 	out := make([]GT, len(a))
 	err := shard(len(a), wave, func(d *device, lo, hi int) error {
-		if div {
+		switch mode {
+		case 1:
 			return d.check(C.bn254_gt_div_batch(d.ctx, ptr(a[lo:hi]), ptr(b[lo:hi]), C.size_t(hi-lo), ptr(out[lo:hi])))
+		case 2:
+			return d.check(C.bn254_gt_cyclo_div_batch(d.ctx, ptr(a[lo:hi]), ptr(b[lo:hi]), C.size_t(hi-lo), ptr(out[lo:hi])))
 		}
 		return d.check(C.bn254_gt_mul_batch(d.ctx, ptr(a[lo:hi]), ptr(b[lo:hi]), C.size_t(hi-lo), ptr(out[lo:hi])))
 	})

@@ -29,7 +29,7 @@ SYMBOLS = [
     "bn254_g1_sum_batch_dev", "bn254_g2_sum_batch_dev", "bn254_gt_exp_batch", "bn254_gt_exp_base_batch",
     "bn254_gt_exp_batch_dev", "bn254_gt_cyclo_exp_batch", "bn254_gt_cyclo_exp_base_batch",
     "bn254_gt_cyclo_exp_batch_dev", "bn254_gt_mul_batch", "bn254_gt_div_batch", "bn254_gt_mul_batch_dev",
-    "bn254_gt_div_batch_dev", "bn254_pairing_check2_fixed_g1_batch", "bn254_pairing_check2_fixed_g1_batch_dev",
+    "bn254_gt_div_batch_dev", "bn254_gt_cyclo_div_batch", "bn254_gt_cyclo_div_batch_dev", "bn254_pairing_check2_fixed_g1_batch", "bn254_pairing_check2_fixed_g1_batch_dev",
     "bn254_hash_to_g1_batch", "bn254_hash_to_g2_batch", "bn254_hash_to_g1_batch_dev", "bn254_hash_to_g2_batch_dev",
     "bn254_fr_lagrange_basis", "bn254_fr_poly_from_roots", "bn254_fr_poly_from_roots_dev",
     "bn254_fr_quotient_coeffs", "bn254_fr_quotient_coeffs_dev", "bn254_fr_to_scalars_dev", "bn254_fr_to_scalars",

@@ -285,6 +285,10 @@ class Engine:
     def gt_div_batch(self, a, b, out=None):
         return self._binary("bn254_gt_div_batch", a, b, GT_BYTES, out)
 
+    def gt_cyclo_div_batch(self, a, b, out=None):
+        """a[i] / b[i] for b in GT proper (pairing outputs and their products / powers): b^-1 = conj(b), one product."""
+        return self._binary("bn254_gt_cyclo_div_batch", a, b, GT_BYTES, out)
+
     def fp_mul_batch(self, a, b):
         return self._binary("bn254_fp_mul_batch", a, b, 32)
 
@@ -430,7 +434,7 @@ class Engine:
         "g1_fixed_mul_batch_dev": "hpzp", "g2_fixed_mul_batch_dev": "hpzp", "gt_fixed_exp_batch_dev": "hpzp", "msm_batch_dev": "hpzp",
         "g1_add_batch_dev": "ppzp", "g2_add_batch_dev": "ppzp", "g1_neg_batch_dev": "pzp", "g2_neg_batch_dev": "pzp",
         "g1_subset_sum_batch_dev": "pzpzp", "g2_subset_sum_batch_dev": "pzpzp", "g1_sum_batch_dev": "pzzp", "g2_sum_batch_dev": "pzzp",
-        "gt_exp_batch_dev": "pzpzp", "gt_cyclo_exp_batch_dev": "pzpzp", "gt_mul_batch_dev": "pzpzzp", "gt_div_batch_dev": "pzpzzp",
+        "gt_exp_batch_dev": "pzpzp", "gt_cyclo_exp_batch_dev": "pzpzp", "gt_mul_batch_dev": "pzpzzp", "gt_div_batch_dev": "pzpzzp", "gt_cyclo_div_batch_dev": "pzpzzp",
         "pairing_check2_fixed_g1_batch_dev": "pppzp", "hash_to_g1_batch_dev": "ppzbp", "hash_to_g2_batch_dev": "ppzbp",
         "fr_poly_from_roots_dev": "pzp", "fr_quotient_coeffs_dev": "pzpzp", "fr_to_scalars_dev": "pzp",
     }

@@ -77,13 +77,29 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_msm_tables(const v
     row[d - 1] = e;  // (0, 0) stays (0, 0)
   }
 }
-// partial[v * nchunks + c] = sum over the chunk's points j of sum_w tables[j][w][byte_w(s[v][j])] (Jacobian)
-template <typename J, typename A>
+// Jacobian tree over groups of `width` consecutive threads of a CTA (width a power of two <= kBlock) through shared
+// memory: log2(width) dependent additions instead of width - 1.  The first thread of every group ends with the sum.
+// Every thread of the CTA must call it (barriers); idle lanes pass the point at infinity.
+template <typename J>
+__device__ __forceinline__ void cta_jac_tree(J& acc, int width) {
+  J* sm = reinterpret_cast<J*>(bn_dyn_smem);
+  const int tid = threadIdx.x, j = tid & (width - 1);
+  for (int step = 1; step < width; step <<= 1) {
+    sm[tid] = acc;
+    __syncthreads();
+    if ((j & (2 * step - 1)) == 0) { J e = sm[tid + step]; jac_add(acc, acc, e); }
+    __syncthreads();
+  }
+}
+// partial[v * nchunks + c] = sum over the chunk's points j of sum_w tables[j][w][byte_w(s[v][j])] (Jacobian).
+// TREE (the launch guarantees nchunks % kBlock == 0, so a CTA lies inside one vector and no thread is idle): the CTA's
+// kBlock sums are added by a shared-memory tree and ONE partial per CTA is written -- partial[blockIdx.x].
+template <typename J, typename A, bool TREE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_msm_partial(const A* __restrict__ tables, const void* scalars, size_t nvec, size_t len, int chunk, J* partial) {
   cta_lockstep_set(false);
   size_t nch = (len + chunk - 1) / chunk;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nvec * nch) return;
+  if (!TREE && t >= nvec * nch) return;
   size_t v = t / nch, c = t % nch;
   size_t first = c * (size_t)chunk, last = first + chunk < len ? first + chunk : len;
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
@@ -99,7 +115,24 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_msm_partial(const 
       }
     }
   }
-  partial[t] = acc;
+  if (TREE) {
+    cta_jac_tree(acc, kBlock);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+  } else {
+    partial[t] = acc;
+  }
+}
+// out_a[g] = affine sum of group g's `len` Jacobian points, len a power of two <= kBlock: one thread per point, tree
+// per group (3 dependent additions for len = 8 instead of 7), one inversion per group.
+template <typename J, typename A>
+__global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_jac_tree(const J* in, size_t groups, int len, void* out_a) {
+  cta_lockstep_set(false);
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  J acc;
+  if (t < groups * (size_t)len) acc = in[t];
+  else { f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z); }
+  cta_jac_tree(acc, len);
+  if (t < groups * (size_t)len && (threadIdx.x & (len - 1)) == 0) { A r; jac_to_aff(r, acc); store_struct(out_a, t / len, r); }
 }
 // out[g * nch + c] = sum of the c-th chunk of group g's `len` Jacobian points; the last pass (nch == 1) may write affine
 template <typename J, typename A>
@@ -134,8 +167,20 @@ void msm_tables(int g, const void* pts, size_t len, void* tables, void* zs, void
 }
 void msm_partial(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s) {
   size_t threads = nvec * ((len + chunk - 1) / chunk);
-  BY_GROUP(g, (BN_LAUNCH, k_msm_partial<G1Jac, G1Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
-           (BN_LAUNCH, k_msm_partial<G2Jac, G2Aff><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
+  BY_GROUP(g, (BN_LAUNCH, k_msm_partial<G1Jac, G1Aff, false><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
+           (BN_LAUNCH, k_msm_partial<G2Jac, G2Aff, false><<<grid_for(threads), kBlock, 0, s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
+}
+// one partial per CTA (requires ((len + chunk - 1) / chunk) % kBlockThreads == 0)
+void msm_partial_tree(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s) {
+  size_t threads = nvec * ((len + chunk - 1) / chunk);
+  BY_GROUP(g, (BN_LAUNCH, k_msm_partial<G1Jac, G1Aff, true><<<grid_for(threads), kBlock, kBlock * sizeof(G1Jac), s>>>(static_cast<const G1Aff*>(tables), scalars, nvec, len, chunk, static_cast<G1Jac*>(partial))),
+           (BN_LAUNCH, k_msm_partial<G2Jac, G2Aff, true><<<grid_for(threads), kBlock, kBlock * sizeof(G2Jac), s>>>(static_cast<const G2Aff*>(tables), scalars, nvec, len, chunk, static_cast<G2Jac*>(partial))));
+}
+// out_a[g] = affine sum of `len` Jacobian points per group, len a power of two <= kBlockThreads
+void jac_tree(int g, const void* in, size_t groups, int len, void* out_a, cudaStream_t s) {
+  size_t threads = groups * (size_t)len;
+  BY_GROUP(g, (BN_LAUNCH, k_jac_tree<G1Jac, G1Aff><<<grid_for(threads), kBlock, kBlock * sizeof(G1Jac), s>>>(static_cast<const G1Jac*>(in), groups, len, out_a)),
+           (BN_LAUNCH, k_jac_tree<G2Jac, G2Aff><<<grid_for(threads), kBlock, kBlock * sizeof(G2Jac), s>>>(static_cast<const G2Jac*>(in), groups, len, out_a)));
 }
 void jac_sum(int g, const void* in, size_t groups, int len, int chunk, void* out_j, void* out_a, cudaStream_t s) {
   size_t threads = groups * (size_t)((len + chunk - 1) / chunk);

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_fixed_exp(const
   }
   store_struct(out, i, acc);
 }
-// mode 0: a*b ; mode 1: a/b
+// mode 0: a*b ; mode 1: a/b (generic Fp12 inverse) ; mode 2: a * conj(b) = a/b for b in the cyclotomic subgroup
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void* a, size_t a_stride, const void* b, size_t b_stride, size_t n, void* out) {
   cta_lockstep_set(false);
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_gt_mul(const void*
   if (i >= n) return;
   Fp12 x, y; load_struct(x, a, i * a_stride); load_struct(y, b, i * b_stride);
   if (MODE == 1) fp12_inv(y, y);
+  if (MODE == 2) fp12_conj(y, y);
   fp12_mul(x, x, y);
   store_struct(out, i, x);
 }
@@ -73,7 +74,8 @@ namespace launch {
 
 cudaError_t gt_init() {
 #ifdef BN254_SMEM_SCRATCH
-  const void* kernels[] = {(const void*)k_gt_fixed_exp, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>};
+  const void* kernels[] = {(const void*)k_gt_fixed_exp, (const void*)k_gt_exp<0>, (const void*)k_gt_exp<1>, (const void*)k_gt_mul<0>, (const void*)k_gt_mul<1>,
+                           (const void*)k_gt_mul<2>};
   for (const void* k : kernels) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTowerSmem);
     if (e != cudaSuccess) return e;
@@ -91,7 +93,8 @@ void gt_fixed_exp(const void* table, const void* k, size_t n, void* out, cudaStr
 }
 void gt_mul(int mode, const void* a, size_t a_stride, const void* b, size_t b_stride, size_t n, void* out, cudaStream_t s) {
   if (mode == 0) BN_LAUNCH, k_gt_mul<0><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
-  else BN_LAUNCH, k_gt_mul<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
+  else if (mode == 1) BN_LAUNCH, k_gt_mul<1><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
+  else BN_LAUNCH, k_gt_mul<2><<<grid_for(n), kBlock, kTowerSmem, s>>>(a, a_stride, b, b_stride, n, out);
 }
 void fp_mul(const void* a, const void* b, size_t n, void* out, cudaStream_t s) { BN_LAUNCH, k_fp_mul<<<grid_for(n), kBlock, 0, s>>>(a, b, n, out); }
 

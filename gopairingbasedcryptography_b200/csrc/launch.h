@@ -59,6 +59,8 @@ size_t subset_sum_max_bytes();
 // zs, pf: scratch of len * 32 * 255 field elements each (32 B G1 / 64 B G2), free after the launch completes
 void msm_tables(int g, const void* pts, size_t len, void* tables, void* zs, void* pf, cudaStream_t s);
 void msm_partial(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s);
+void msm_partial_tree(int g, const void* tables, const void* scalars, size_t nvec, size_t len, int chunk, void* partial, cudaStream_t s);  // one partial per CTA
+void jac_tree(int g, const void* in, size_t groups, int len, void* out_a, cudaStream_t s);  // len a power of two <= kBlockThreads
 // Jacobian partial sums (96 B G1 / 192 B G2 each): out_j (Jacobian) or, on the last pass, out_a (canonical affine)
 void jac_sum(int g, const void* in, size_t groups, int len, int chunk, void* out_j, void* out_a, cudaStream_t s);
 void neg_points(int g, const void* in, size_t n, void* out, cudaStream_t s);
@@ -66,7 +68,7 @@ void neg_points(int g, const void* in, size_t n, void* out, cudaStream_t s);
 // ---- GT family --------------------------------------------------------------------------------------------------
 void gt_exp(int cyclo, const void* x, size_t x_stride, const void* k, size_t n, void* out, void* tabmem, cudaStream_t s);
 void gt_fixed_exp(const void* table, const void* k, size_t n, void* out, cudaStream_t s);
-void gt_mul(int mode, const void* a, size_t a_stride, const void* b, size_t b_stride, size_t n, void* out, cudaStream_t s);  // mode 0: a*b, 1: a/b
+void gt_mul(int mode, const void* a, size_t a_stride, const void* b, size_t b_stride, size_t n, void* out, cudaStream_t s);  // mode 0: a*b, 1: a/b, 2: a*conj(b)
 void fp_mul(const void* a, const void* b, size_t n, void* out, cudaStream_t s);
 int gt_wave_threads(int sms);
 

@@ -169,7 +169,8 @@ def lw11_decrypt_batch(engine, c0, c1x, c2x, c3x, h_gid, k_rho, weights):
     den = c1e[:, 0]
     for x in range(1, m):
         den = engine.gt_mul_batch(den, c1e[:, x])
-    return engine.gt_mul_batch(engine.gt_div_batch(np.ascontiguousarray(c0).reshape(-1, GT_BYTES), den), prod)
+    # den is a product of powers of GT elements: unitary, so the quotient is a product with its conjugate
+    return engine.gt_mul_batch(engine.gt_cyclo_div_batch(np.ascontiguousarray(c0).reshape(-1, GT_BYTES), den), prod)
 
 
 def g2_msm_batch(engine, points, coeffs):
@@ -333,7 +334,8 @@ def afp25_decrypt_batch(engine, table, f_coeffs, ids_fr, c1, c2, d, sk):
         prod = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
         engine.dev("multi_pair_batch_dev", P.data_ptr(), d_c1.data_ptr(), n, 3, prod.data_ptr(), stream=s)
         out = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
-        engine.dev("gt_div_batch_dev", d_c2.data_ptr(), 1, prod.data_ptr(), 1, n, out.data_ptr(), stream=s)
+        # the divisor is a pairing product: C2 / prod = C2 * conj(prod) (bn254_gt_cyclo_div_batch), no Fp12 inversion
+        engine.dev("gt_cyclo_div_batch_dev", d_c2.data_ptr(), 1, prod.data_ptr(), 1, n, out.data_ptr(), stream=s)
         return out.cpu().numpy()
 
 

@@ -219,6 +219,9 @@ class DevicePool:
     def gt_div_batch(self, a, b):
         return self._binary("gt_div_batch", a, b, GT_BYTES)
 
+    def gt_cyclo_div_batch(self, a, b):
+        return self._binary("gt_cyclo_div_batch", a, b, GT_BYTES)
+
     def g1_add_batch(self, a, b):
         return self._binary("g1_add_batch", a, b, G1_BYTES)
 

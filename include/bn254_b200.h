@@ -202,6 +202,12 @@ int bn254_gt_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void*
 /* strides in elements: 0 broadcasts one element over the batch, 1 walks an array */
 int bn254_gt_mul_batch_dev(bn254_ctx*, const void* da, size_t a_stride, const void* db, size_t b_stride, size_t n, void* d_out, void* stream);
 int bn254_gt_div_batch_dev(bn254_ctx*, const void* da, size_t a_stride, const void* db, size_t b_stride, size_t n, void* d_out, void* stream);
+/* a / b for b in GT proper (a pairing output, or a product / quotient / power of pairing outputs -- the divisor at
+ * every Div of the reference's decryption flows: bsw07_cpabe.go:189-190, waters05_ibe.go:269-274, afp25_bibe.go:407-413):
+ * b is unitary there, so b^-1 = conj(b) and the quotient is ONE Fp12 product instead of an Fp12 inversion (~800 dependent
+ * Fp products on one thread) plus a product.  Same bytes as bn254_gt_div_batch for such b; undefined for other b. */
+int bn254_gt_cyclo_div_batch(bn254_ctx*, const void* a, const void* b, size_t n, void* out);
+int bn254_gt_cyclo_div_batch_dev(bn254_ctx*, const void* da, size_t a_stride, const void* db, size_t b_stride, size_t n, void* d_out, void* stream);
 
 /* ok[i] = PairingCheck({P0, P1}, {Q0[i], Q1[i]}) with the two G1 points shared by the batch: BLS verification
  * [signature/bls01_signature/bls_signature.go:71-89: P0 = pk, P1 = -g1, Q0[i] = H(m_i), Q1[i] = sigma_i].

@@ -463,3 +463,23 @@ print("ok")
 """ % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-800:]
+
+
+def test_gt_cyclo_div_equals_generic_div_on_gt_elements(engine):
+    """bn254_gt_cyclo_div_batch (a * conj(b)) == bn254_gt_div_batch (a * b^-1) == the oracle's GT.Div when b is a pairing
+    output, a product or a power of pairing outputs; host and device-pointer entry points."""
+    n = 70
+    P, Q, _, _ = common.points(n, seed=0x6D1)
+    b = engine.pair_batch(P, Q)
+    b2 = engine.gt_mul_batch(b, b[::-1].copy())                    # products of pairing outputs
+    b3 = engine.gt_cyclo_exp_batch(b, sb(common.scalars(n, seed=0x6D2)))   # powers (incl. the edge scalars 0, 1, r - 1 ...)
+    a = engine.final_exp_batch(engine.miller_loop_batch(P[::-1].copy(), Q, 1))
+    for den in (b, b2, b3):
+        want = engine.gt_div_batch(a, den)
+        assert (engine.gt_cyclo_div_batch(a, den) == want).all()
+        assert (want.reshape(-1) == port.gt_div_batch(a.reshape(-1), den.reshape(-1), n)).all()
+    torch, dev = _torch_dev(engine)
+    da, db = torch.from_numpy(a).to(dev), torch.from_numpy(b2).to(dev)
+    out = torch.empty_like(da)
+    engine.dev("gt_cyclo_div_batch_dev", da.data_ptr(), 1, db.data_ptr(), 1, n, out.data_ptr(), stream=torch.cuda.current_stream(dev).cuda_stream)
+    assert (out.cpu().numpy() == engine.gt_div_batch(a, b2)).all()
