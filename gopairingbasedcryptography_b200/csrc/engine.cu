@@ -330,7 +330,10 @@ cudaError_t seq_multi_pair_lines(bn254_ctx*, Scratch& sc, const void* P, const b
   return cudaSuccess;
 }
 cudaError_t seq_check2_fixed_g1(bn254_ctx* ctx, Scratch& sc, const void* P01, const void* Q0, const void* Q1, size_t n, uint8_t* ok) {
-  if (ctx->vm_mode != 2 && use_vm(ctx, 2 * n)) {  // small batch: lane-group kernels (see seq_multi_pair)
+  // small batch: lane-group kernels (see seq_multi_pair).  Crossover measured on the 2-pair check itself
+  // (profiles/r2/check2_routing.jsonl): 12 000 checks 12.5 ms against 15.2 ms on the thread kernel, 16 384: 14.3 / 15.3,
+  // 20 000: 19.1 / 19.6 -- so the limit is kVmAutoMax CHECKS, not pairs
+  if (ctx->vm_mode != 2 && use_vm(ctx, n)) {
     size_t bp = al256(2 * n * BN254_G1_BYTES), bq = al256(2 * n * BN254_G2_BYTES), bm = al256(2 * n * BN254_GT_BYTES), bo = al256(n * BN254_GT_BYTES);
     void *Pp, *Qp, *ml, *prod;
     cudaError_t e;
