@@ -26,6 +26,14 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "wvmprof": DEFAULT + ["-DBN254_WVM_PROFILE"],
     "wvmprof_noinline": DEFAULT + ["-DBN254_WVM_PROFILE"],  # built after `WVM_TINLINE=0 python csrc/wvmgen.py` (program-shape experiment)
     "nosmem": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=3"],
+    # timing-only probe of 4 CTAs per SM (128 registers, 16 warps): the 9 scratch slots are squeezed into a 400-byte stride, so
+    # slots 6-8 alias the next thread's -- results are WRONG, the instruction stream and its timing are those of a design
+    # whose three extra slots are as fast as shared memory (upper bound for a TMEM-backed variant)
+    "b4_timing_only": {"k_pairing": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP",
+                                     "-DBN254_SCRATCH_STRIDE=400"]},
+    "b4_timing_only_seq": {"k_pairing": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP",
+                                         "-DBN254_SCRATCH_STRIDE=400", "-DBN254_MULX_SEQ", "-DBN254_CYC_LATE_LOADS"]},
+    "mulx_seq": {"k_pairing": DEFAULT + ["-DBN254_MULX_SEQ", "-DBN254_CYC_LATE_LOADS"]},
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
 }
 # per-unit additions on top of the variant's flags

@@ -10,7 +10,8 @@ namespace bn254 {
 namespace {
 constexpr int kPairChunk = 4;  // pairs per shared-squaring pass inside one thread
 #ifdef BN254_SMEM_SCRATCH
-constexpr size_t kTowerSmem = (size_t)kBlock * kScratchStride;  // per-thread Fp2 scratch of the tower routines
+// per-thread Fp2 scratch of the tower routines (+ a tail when a timing-only probe squeezes the stride below 9 slots)
+constexpr size_t kTowerSmem = (size_t)kBlock * kScratchStride + (kScratchSlots * 64 > kScratchStride ? kScratchSlots * 64 - kScratchStride + 64 : 0);
 #else
 constexpr size_t kTowerSmem = 0;
 #endif

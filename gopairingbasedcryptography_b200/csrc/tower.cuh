@@ -156,6 +156,26 @@ BN_HD Fp2 fp2_mul_lazy(const Fp2& a, const Fp2& b) {
   z.a1 = fp_redc(t2);
   return z;
 }
+// The same arithmetic in an order that keeps fewer values alive (experiment for a 128-register build: two wide products,
+// their difference and sum, THEN the third product on the operand sums): c1 = (a0+a1)(b0+b1) - (a0b0 + a1b1).
+BN_HD Fp2 fp2_mul_lazy_seq(const Fp2& a, const Fp2& b) {
+  uint32_t t0[16], t1[16], s[16];
+  fp_mul_wide(t0, a.a0, b.a0);
+  fp_mul_wide(t1, a.a1, b.a1);
+  s[0] = add_cc(t0[0], t1[0]);
+#pragma unroll
+  for (int i = 1; i < 15; i++) s[i] = addc_cc(t0[i], t1[i]);
+  s[15] = addc(t0[15], t1[15]);  // a0b0 + a1b1 < 2 p^2 < 2^509
+  uint32_t mask;
+  wide_sub(t0, t0, t1, mask);
+  wide_add_psq_masked(t0, mask);
+  fp_mul_wide(t1, fp_add_noreduce(a.a0, a.a1), fp_add_noreduce(b.a0, b.a1));
+  wide_sub(t1, t1, s, mask);
+  Fp2 z;
+  z.a0 = fp_redc(t0);
+  z.a1 = fp_redc(t1);
+  return z;
+}
 // complex squaring: 2 Fp products
 BN_HD Fp2 fp2_sqr_inl(const Fp2& a) {
   Fp m = FP_MUL(a.a0, a.a1);
@@ -169,7 +189,9 @@ BN_HD Fp2 fp2_mul_best(const Fp2& a, const Fp2& b) { return fp2_mul_inl(a, b); }
 // inside, so none of the 16-limb intermediates crosses a call boundary (as separate out-of-line wide-product /
 // reduction calls the same arithmetic measured 10-20 % SLOWER than three Montgomery products; fused it is
 // 5.5 % faster: 2.83M vs 2.69M pairings/s).  -DBN254_KARATSUBA_MULX restores the three-product body.
-#ifndef BN254_KARATSUBA_MULX
+#if defined(BN254_MULX_SEQ)
+BN_NOINLINE Fp2 fp2_mulx(Fp2 a, Fp2 b) { return fp2_mul_lazy_seq(a, b); }
+#elif !defined(BN254_KARATSUBA_MULX)
 BN_NOINLINE Fp2 fp2_mulx(Fp2 a, Fp2 b) { return fp2_mul_lazy(a, b); }
 #else
 BN_NOINLINE Fp2 fp2_mulx(Fp2 a, Fp2 b) { return fp2_mul_inl(a, b); }
@@ -192,7 +214,10 @@ BN_HD void fp2_inv(Fp2& z, const Fp2& a) {
 // (ncu: the 7 KB/thread stack drives 3 TB/s of DRAM traffic and a third of all stall samples).  9 slots of
 // 64 B, thread stride 592 B = 16 B x 37 (odd) so 128-bit accesses of a quarter-warp hit distinct bank quads.
 constexpr int kScratchSlots = 9;
-constexpr int kScratchStride = 592;
+#ifndef BN254_SCRATCH_STRIDE
+#define BN254_SCRATCH_STRIDE 592
+#endif
+constexpr int kScratchStride = BN254_SCRATCH_STRIDE;  // (a smaller stride is a TIMING-ONLY experiment: slots then overlap between threads)
 #if defined(BN254_SMEM_SCRATCH) && defined(__CUDACC__)
 extern __shared__ uint4 bn_dyn_smem[];
 BN_D Fp2* bn_scratch() { return reinterpret_cast<Fp2*>(reinterpret_cast<char*>(bn_dyn_smem) + threadIdx.x * kScratchStride); }

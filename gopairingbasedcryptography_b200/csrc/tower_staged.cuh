@@ -192,6 +192,17 @@ BN_NOINLINE void fp12_sqr(Fp12& z, const Fp12& x) {
 //   g4' = 3 r0(g2,g5) - 2 g4   g1' = 3 xi r1(g2,g5) + 2 g1
 // One leaf per pair: 3 Fp2 squarings and both outputs, everything in registers.
 BN_NOINLINE void fp2_cyc(Fp2& zm, Fp2& zp, const Fp2& a, const Fp2& b, const Fp2& gm, const Fp2& gp, int xi) {
+#ifdef BN254_CYC_LATE_LOADS
+  // 128-register builds: the linear terms are fetched after the squarings (two 16-register values less across six calls)
+  Fp2 A = fp2_ld(a), B = fp2_ld(b);
+  Fp2 S = FP2_SQR(fp2_add_i(A, B));
+  A = FP2_SQR(A);
+  B = FP2_SQR(B);
+  Fp2 r1 = fp2_sub_i(fp2_sub_i(S, A), B);
+  Fp2 r0 = fp2_add_i(A, fp2_mul_xi_bv(B));
+  if (xi) r1 = fp2_mul_xi_bv(r1);
+  Fp2 Gm = fp2_ld(gm), Gp = fp2_ld(gp);
+#else
   Fp2 A = fp2_ld(a), B = fp2_ld(b), Gm = fp2_ld(gm), Gp = fp2_ld(gp);
   Fp2 S = FP2_SQR(fp2_add_i(A, B));
   A = FP2_SQR(A);
@@ -199,6 +210,7 @@ BN_NOINLINE void fp2_cyc(Fp2& zm, Fp2& zp, const Fp2& a, const Fp2& b, const Fp2
   Fp2 r1 = fp2_sub_i(fp2_sub_i(S, A), B);
   Fp2 r0 = fp2_add_i(A, fp2_mul_xi_bv(B));
   if (xi) r1 = fp2_mul_xi_bv(r1);
+#endif
   fp2_st(zm, fp2_add_i(fp2_dbl_i(fp2_sub_i(r0, Gm)), r0));
   fp2_st(zp, fp2_add_i(fp2_dbl_i(fp2_add_i(r1, Gp)), r1));
 }
