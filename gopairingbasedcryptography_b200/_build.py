@@ -34,6 +34,10 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "b4_timing_only_seq": {"k_pairing": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=4", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP",
                                          "-DBN254_SCRATCH_STRIDE=400", "-DBN254_MULX_SEQ", "-DBN254_CYC_LATE_LOADS"]},
     "mulx_seq": {"k_pairing": DEFAULT + ["-DBN254_MULX_SEQ", "-DBN254_CYC_LATE_LOADS"]},
+    "wvm_ahead2": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=2"]},
+    "wvm_ahead3": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=3"]},
+    "wvm_onepass": {"k_wvm": DEFAULT + ["-DWVM_FINISH_ONEPASS=1"]},
+    "wvm_linbatch": {"k_wvm": DEFAULT + ["-DWVM_LIN_BATCH=1"]},
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
 }
 # per-unit additions on top of the variant's flags
