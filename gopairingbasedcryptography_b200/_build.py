@@ -72,7 +72,7 @@ def ensure_generated():
         return
     """The warp-VM programs (wvm_prog_*.inc, ~8 MB of text) are generated, not committed: wvmgen.py rebuilds them from
     the traced pairing formulas in a few seconds."""
-    outs = [os.path.join(CSRC, f) for f in ("wvm_prog_miller.inc", "wvm_prog_finalexp.inc", "wvm_prog_meta.cuh")]
+    outs = [os.path.join(CSRC, f) for f in ("wvm_prog_miller.inc", "wvm_prog_miller2.inc", "wvm_prog_finalexp.inc", "wvm_prog_meta.cuh")]
     srcs = [os.path.join(CSRC, f) for f in ("wvmgen.py", "vmgen.py")]
     if all(os.path.exists(o) for o in outs) and min(os.path.getmtime(o) for o in outs) >= max(os.path.getmtime(s) for s in srcs):
         return

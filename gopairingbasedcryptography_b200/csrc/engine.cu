@@ -60,7 +60,7 @@ struct bn254_ctx {
   int vm_mode = 0;  // 0 auto, 1 lane-group always, 2 never (thread kernels only), 3 warp-VM always
   int sms = 0;
   int vm_blocks_per_sm[3] = {0, 0, 0};
-  int wvm_blocks_per_sm[3] = {0, 0, 0};
+  int wvm_blocks_per_sm[4] = {0, 0, 0, 0};
   bool g2_glv = false;  // BN254_G2_LADDER=glv: 2-dimensional GLV on G2 instead of the 4-dimensional GLS ladder
   size_t wvm_auto_max = 0;  // launches of at most this many items take the warp-VM kernels (one warp per item)
   void* vm_cold_dev = nullptr;  // scratch for the *_dev entry points (launches are serialised by vm_dev_done)
@@ -303,8 +303,12 @@ cudaError_t seq_multi_pair(bn254_ctx* ctx, Scratch& sc, int mode, const void* P,
     void *ml, *prod_s;
     if ((e = sc.get(pairs * BN254_GT_BYTES, &ml)) != cudaSuccess || (e = sc.get(n * BN254_GT_BYTES, &prod_s)) != cudaSuccess) return e;
     void* prod = mode == 2 ? prod_s : out;
-    if ((e = vm_any(ctx, sc, L::kVmMiller, P, Q, pairs, ml)) != cudaSuccess) return e;
-    L::mp_combine(0, ml, n, k, prod, sc.stream);
+    if (k == 2 && use_wvm(ctx, n)) {  // one warp per PRODUCT: the two-pair Miller program (shared squarings), no combine
+      L::wvm_run(L::kVmMiller2, P, Q, n, prod, ctx->sms, ctx->wvm_blocks_per_sm, sc.stream);
+    } else {
+      if ((e = vm_any(ctx, sc, L::kVmMiller, P, Q, pairs, ml)) != cudaSuccess) return e;
+      L::mp_combine(0, ml, n, k, prod, sc.stream);
+    }
     if (mode >= 1 && (e = vm_any(ctx, sc, L::kVmFinalExp, prod, nullptr, n, prod)) != cudaSuccess) return e;
     if (mode == 2) L::gt_is_one(prod, n, static_cast<uint8_t*>(out), sc.stream);
     return cudaSuccess;
@@ -341,8 +345,12 @@ cudaError_t seq_check2_fixed_g1(bn254_ctx* ctx, Scratch& sc, const void* P01, co
     if ((e = sc.get(bp, &Pp)) != cudaSuccess || (e = sc.get(bq, &Qp)) != cudaSuccess || (e = sc.get(bm, &ml)) != cudaSuccess ||
         (e = sc.get(bo, &prod)) != cudaSuccess) return e;
     L::pack_check2(P01, Q0, Q1, n, Pp, Qp, sc.stream);
-    if ((e = vm_any(ctx, sc, L::kVmMiller, Pp, Qp, 2 * n, ml)) != cudaSuccess) return e;
-    L::mp_combine(0, ml, n, 2, prod, sc.stream);
+    if (use_wvm(ctx, n)) {  // one warp per check: two-pair Miller program
+      L::wvm_run(L::kVmMiller2, Pp, Qp, n, prod, ctx->sms, ctx->wvm_blocks_per_sm, sc.stream);
+    } else {
+      if ((e = vm_any(ctx, sc, L::kVmMiller, Pp, Qp, 2 * n, ml)) != cudaSuccess) return e;
+      L::mp_combine(0, ml, n, 2, prod, sc.stream);
+    }
     if ((e = vm_any(ctx, sc, L::kVmFinalExp, prod, nullptr, n, prod)) != cudaSuccess) return e;
     L::gt_is_one(prod, n, ok, sc.stream);
     return cudaSuccess;

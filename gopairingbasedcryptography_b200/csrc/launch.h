@@ -83,14 +83,14 @@ void fr_lagrange_basis_host(const void* s, size_t n, const void* x, void* out); 
 void fr_to_scalars_host(const void* in, size_t n, void* out);
 
 // ---- lane-group (tower VM) kernels ------------------------------------------------------------------------------
-enum { kVmPair = 0, kVmMiller = 1, kVmFinalExp = 2 };
+enum { kVmPair = 0, kVmMiller = 1, kVmFinalExp = 2, kVmMiller2 = 3 };  // Miller2: product of TWO Miller loops per item (warp-VM only)
 constexpr int kVmPairingsPerCta = 40;  // 4 warps x 10 lane groups of 3 (k_vm.cu asserts it)
 cudaError_t vm_prepare(int* blocks_per_sm /* [3] */);
 size_t vm_cold_bytes(int sms, const int* blocks_per_sm);
 void vm_run(int prog, const void* a, const void* b, size_t n, void* out, void* cold, int sms, const int* blocks_per_sm, cudaStream_t s);
 
 // ---- warp-VM kernels (k_wvm.cu): one warp per item, the latency path; same program ids as the lane-group kernels ----
-cudaError_t wvm_prepare(int* blocks_per_sm /* [3] */);
+cudaError_t wvm_prepare(int* blocks_per_sm /* [4] */);
 int wvm_items_per_cta();
 void wvm_run(int prog, const void* a, const void* b, size_t n, void* out, int sms, const int* blocks_per_sm, cudaStream_t s);
 

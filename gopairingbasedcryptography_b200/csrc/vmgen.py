@@ -451,6 +451,35 @@ def trace_miller(t, Pslot, Q, f=None):
     return f
 
 
+def trace_miller_multi(t, Pslots, Qs):
+    """Miller product of several pairs with SHARED squarings of f (the value equals the product of the single-pair
+    Miller values exactly: field arithmetic is exact).  The G2 steps of the pairs are independent of each other and of
+    f^2, so a wide scheduler runs them side by side; only the sparse line multiplications chain through f."""
+    one = t.ldc(C_ONE)
+    Ts = [(Q[0], Q[1], one) for Q in Qs]
+    negQs = [(Q[0], t.neg(Q[1])) for Q in Qs]
+    digits = naf(6 * X0 + 2)
+    f = None
+    for i in range(len(digits) - 2, -1, -1):
+        if f is not None:
+            f = fp12_sqr(t, f)
+        for j in range(len(Qs)):
+            Ts[j], line = g2_dbl_step(t, Ts[j])
+            f = apply_line(t, f, Pslots[j], line)
+        if digits[i]:
+            for j in range(len(Qs)):
+                Ts[j], line = g2_add_step(t, Ts[j], Qs[j] if digits[i] > 0 else negQs[j])
+                f = apply_line(t, f, Pslots[j], line)
+    for j, Q in enumerate(Qs):
+        q1 = (t.mulc(t.conj(Q[0]), C_G1[2]), t.mulc(t.conj(Q[1]), C_G1[3]))
+        q2 = (t.mulcfp(Q[0], 2), Q[1])
+        Ts[j], line = g2_add_step(t, Ts[j], q1)
+        f = apply_line(t, f, Pslots[j], line)
+        _, line = g2_add_step(t, Ts[j], q2, update=False)
+        f = apply_line(t, f, Pslots[j], line)
+    return f
+
+
 def trace_final_exp(t, z, park=True):
     x0d = naf(X0, 3)
     f = fp12_mul(t, fp12_conj(t, z), fp12_inv(t, z))

@@ -37,7 +37,7 @@ DUP_MAX = int(os.environ.get("WVM_DUP_MAX", "6"))   # a LIN of at most this many
 # term cap when LIN -> LIN chains are collapsed (0 = off).  Measured on B200 (benchmarks/wvm_ab.py, profiles/r2/wvm_ab.jsonl):
 # collapsing helps the Miller program (0.705 -> 0.672 ms) and hurts the final exponentiation (0.76 -> 0.86 ms).
 TINLINE_ENV = os.environ.get("WVM_TINLINE")
-TINLINE_BY_PROGRAM = {"miller": 15, "finalexp": 0, "pair": 0}
+TINLINE_BY_PROGRAM = {"miller": 15, "miller2": 15, "finalexp": 0, "pair": 0}
 TINLINE = 0
 SHARE_MIN = int(os.environ.get("WVM_SHARE_MIN", "3"))  # ... when the form has at least this many terms
 OP_NOP, OP_MUL, OP_LIN, OP_INV = 0, 1, 2, 3
@@ -496,7 +496,18 @@ def build(name):
         t = g.Tracer()
         low = Lowering()
         in_forms, pinned_in = {}, []
-        if name in ("pair", "miller"):
+        if name == "miller2":  # product of two Miller loops with shared squarings (the BLS verification shape)
+            Ps, Qs = [], []
+            for j in range(2):
+                names = ("P%d" % j, "Q%dx" % j, "Q%dy" % j)
+                Pslot, Qx, Qy = (t.input(nm) for nm in names)
+                for nm in names:
+                    b0, b1 = low.input(nm + ".0"), low.input(nm + ".1")
+                    pinned_in += [b0, b1]
+                    in_forms[nm] = (low.form_of(b0), low.form_of(b1))
+                Ps.append(Pslot); Qs.append((Qx, Qy))
+            f = g.trace_miller_multi(t, Ps, Qs)
+        elif name in ("pair", "miller"):
             Pslot, Qx, Qy = t.input("P"), t.input("Qx"), t.input("Qy")
             for nm in ("P", "Qx", "Qy"):
                 b0, b1 = low.input(nm + ".0"), low.input(nm + ".1")
@@ -552,7 +563,7 @@ def mont32(v):
 
 def emit(outdir):
     lines = ["// GENERATED by wvmgen.py -- do not edit.", "#pragma once", "namespace bn254 { namespace wvm {"]
-    for name in ("miller", "finalexp"):  # a pairing runs the two programs back to back (k_wvm.cu)
+    for name in ("miller", "miller2", "finalexp"):  # a pairing runs the Miller and final-exponentiation programs back to back (k_wvm.cu)
         words, meta = build(name)
         with open(os.path.join(outdir, "wvm_prog_%s.inc" % name), "w") as f:  # u32 words = two u16 fields, little-endian
             for i in range(0, len(words), 16):

@@ -159,6 +159,9 @@ namespace {
 const uint32_t kWvmMillerH[] = {
 #include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_miller.inc"
 };
+const uint32_t kWvmMiller2H[] = {
+#include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_miller2.inc"
+};
 const uint32_t kWvmFinalExpH[] = {
 #include "../../gopairingbasedcryptography_b200/csrc/wvm_prog_finalexp.inc"
 };
@@ -200,6 +203,22 @@ void emu_wvm(const void* in0, const void* in1, size_t n, int mode, void* out) {
       for (int k = 0; k < 12; k++) v[k] = slots[FINALEXP_OUT[k]];
     }
     memcpy((char*)out + i * 384, v, 384);
+  }
+}
+// the two-pair Miller program (k_wvm_miller2): in0 = P[2n], in1 = Q[2n] -> n Miller products
+void emu_wvm_miller2(const void* in0, const void* in1, size_t n, void* out) {
+  using namespace wvm;
+  for (size_t i = 0; i < n; i++) {
+    Fp slots[1024];
+    memset(slots, 0, sizeof(slots));
+    for (int k = 0; k < MILLER2_NCONST; k++) slots[MILLER2_CONST_SLOT[k]] = MILLER2_CONST_VAL[k];
+    for (int j = 0; j < 2; j++) {
+      memcpy(&slots[MILLER2_IN[6 * j]], (const char*)in0 + i * 128 + j * 64, 32);
+      memcpy(&slots[MILLER2_IN[6 * j + 1]], (const char*)in0 + i * 128 + j * 64 + 32, 32);
+      for (int k = 0; k < 4; k++) memcpy(&slots[MILLER2_IN[6 * j + 2 + k]], (const char*)in1 + i * 256 + j * 128 + k * 32, 32);
+    }
+    wvm_rounds(slots, kWvmMiller2H, MILLER2_ROUNDS);
+    for (int k = 0; k < 12; k++) memcpy((char*)out + i * 384 + k * 32, &slots[MILLER2_OUT[k]], 32);
   }
 }
 // the LIN reduction on its own: any 9-limb total below 256 p

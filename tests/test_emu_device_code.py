@@ -296,6 +296,21 @@ def test_warp_vm_programs_on_host(emu):
     assert (fe[:384] == port.final_exp_batch(x, 1)).all()
 
 
+def test_warp_vm_two_pair_miller_program_on_host(emu):
+    """wvmgen's "miller2" program (two Miller loops with shared squarings, one warp: the BLS verification shape) run by
+    wvm.cuh's exec_op on the host == the product of the two single-pair Miller values bit for bit, and its final
+    exponentiation == the oracle's 2-pair product."""
+    n = 2
+    P, Q, _, _ = common.points(2 * n, seed=322)
+    out = np.zeros(384 * n, np.uint8)
+    emu.emu_wvm_miller2(vp(P), vp(Q), sz(n), vp(out))
+    single = np.zeros(384 * 2 * n, np.uint8)
+    emu.emu_wvm(vp(P), vp(Q), sz(2 * n), 0, vp(single))
+    want = port.gt_mul_batch(single.reshape(n, 2, 384)[:, 0].copy().reshape(-1), single.reshape(n, 2, 384)[:, 1].copy().reshape(-1), n)
+    assert (out == want).all()
+    assert (port.final_exp_batch(out, n) == port.multi_pair_batch(P, Q, n, 2)).all()
+
+
 def test_warp_vm_lin_reduction_bounds(emu):
     """lin_reduce accepts any 9-limb v < 256 p: multiples of p and their neighbours up to the bound, and random values."""
     rng = o.SplitMix64(79)

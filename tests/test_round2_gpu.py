@@ -483,3 +483,39 @@ def test_gt_cyclo_div_equals_generic_div_on_gt_elements(engine):
     out = torch.empty_like(da)
     engine.dev("gt_cyclo_div_batch_dev", da.data_ptr(), 1, db.data_ptr(), 1, n, out.data_ptr(), stream=torch.cuda.current_stream(dev).cuda_stream)
     assert (out.cpu().numpy() == engine.gt_div_batch(a, b2)).all()
+
+
+def test_two_pair_products_on_the_warp_vm(engine):
+    """Small 2-pair products (BLS verification, every 2-pair PairingCheck) run ONE warp per product on the two-pair
+    Miller program (k_wvm_miller2).  Against the oracle, including items whose first, second or both pairs contain the
+    point at infinity (gnark skips such pairs: the kernel falls back to the single-pair program / to 1)."""
+    n = 41
+    P, Q, _, _ = common.points(2 * n, seed=0x2A1)
+    P, Q = P.reshape(n, 2, 64).copy(), Q.reshape(n, 2, 128).copy()
+    P[3, 0] = 0            # G1 infinity in the first pair
+    Q[5, 1] = 0            # G2 infinity in the second pair
+    P[7, 1] = 0; Q[7, 0] = 0   # both pairs skipped -> 1
+    P[9, 0] = 0; P[9, 1] = 0
+    ref = port.multi_pair_batch(P.reshape(-1), Q.reshape(-1), n, 2).reshape(n, 384)
+    assert (engine.multi_pair_batch(P, Q, 2) == ref).all()
+    ml = engine.miller_loop_batch(P, Q, 2)
+    assert (engine.final_exp_batch(ml) == ref).all()
+    ok = engine.pairing_check_batch(P, Q, 2)
+    assert (ok == port.pairing_check_batch(P.reshape(-1), Q.reshape(-1), n, 2).astype(bool)).all()
+    assert ok[7] and ok[9] and not ok[0]
+    # the BLS shape: valid and forged signatures through the fixed-G1 entry point
+    g1, g2 = port.generators()
+    sk = sb([0x1234567])
+    pk = engine.g1_mul_base_batch(g1, sk)[0]
+    hm = Q[:, 0].copy(); hm[5] = Q[5, 0]
+    sig = engine.g2_mul_batch(hm, np.tile(sk, n))
+    sig[11] = sig[12]      # forged
+    negg1 = port.g1_neg(g1) if hasattr(port, "g1_neg") else None
+    from gopairingbasedcryptography_b200 import schemes
+
+    negg1 = schemes.neg_g1(np.frombuffer(g1, dtype=np.uint8).reshape(1, 64))[0] if negg1 is None else negg1
+    got = engine.pairing_check2_fixed_g1_batch(pk, negg1, hm, sig)
+    Pc = np.concatenate([np.tile(pk.reshape(1, 64), (n, 1)), np.tile(np.asarray(negg1).reshape(1, 64), (n, 1))], axis=1).reshape(-1)
+    Qc = np.concatenate([hm, sig], axis=1).reshape(-1)
+    assert (got == port.pairing_check_batch(Pc, Qc, n, 2).astype(bool)).all()
+    assert got.sum() == n - 1 and not got[11]
