@@ -96,6 +96,11 @@ inline int cu_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? BN25
 // Small launches are latency-bound: up to wvm_auto_max items run one WARP per item (warp-VM), up to kVmAutoMax three
 // lanes per item (lane-group VM), beyond that one thread per item.  BN254_IMPL = thread | vm | wvm forces one path.
 inline bool use_wvm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 3 || (ctx->vm_mode == 0 && n <= ctx->wvm_auto_max); }
+// Two-pair products on the warp-VM: ONE warp on the two-pair Miller program (1 221 rounds) or TWO warps on the single-pair
+// program (803 rounds) plus a product kernel.  Two warps win while they find idle schedulers; from about two warps per
+// scheduler on (n products > a quarter of the warp-VM grid) the shared squarings win (1024 BLS checks: 2.60 -> 2.41 ms,
+// 64 checks: 1.58 ms on two warps against 1.88 ms on one; profiles/r2/bls_config0_latency.jsonl).
+inline bool use_wvm_miller2(const bn254_ctx* ctx, size_t n) { return use_wvm(ctx, n) && (ctx->vm_mode == 3 ? n > 592 : 4 * n > ctx->wvm_auto_max); }
 inline bool use_vm(const bn254_ctx* ctx, size_t n) { return ctx->vm_mode == 1 || ctx->vm_mode == 3 || (ctx->vm_mode == 0 && n <= kVmAutoMax); }
 inline size_t pt_bytes(int g) { return g == 1 ? BN254_G1_BYTES : BN254_G2_BYTES; }
 inline size_t jac_bytes(int g) { return g == 1 ? kG1Jac : kG2Jac; }
@@ -303,7 +308,7 @@ cudaError_t seq_multi_pair(bn254_ctx* ctx, Scratch& sc, int mode, const void* P,
     void *ml, *prod_s;
     if ((e = sc.get(pairs * BN254_GT_BYTES, &ml)) != cudaSuccess || (e = sc.get(n * BN254_GT_BYTES, &prod_s)) != cudaSuccess) return e;
     void* prod = mode == 2 ? prod_s : out;
-    if (k == 2 && use_wvm(ctx, n)) {  // one warp per PRODUCT: the two-pair Miller program (shared squarings), no combine
+    if (k == 2 && use_wvm_miller2(ctx, n)) {  // one warp per PRODUCT: the two-pair Miller program (shared squarings), no combine
       L::wvm_run(L::kVmMiller2, P, Q, n, prod, ctx->sms, ctx->wvm_blocks_per_sm, sc.stream);
     } else {
       if ((e = vm_any(ctx, sc, L::kVmMiller, P, Q, pairs, ml)) != cudaSuccess) return e;
@@ -345,7 +350,7 @@ cudaError_t seq_check2_fixed_g1(bn254_ctx* ctx, Scratch& sc, const void* P01, co
     if ((e = sc.get(bp, &Pp)) != cudaSuccess || (e = sc.get(bq, &Qp)) != cudaSuccess || (e = sc.get(bm, &ml)) != cudaSuccess ||
         (e = sc.get(bo, &prod)) != cudaSuccess) return e;
     L::pack_check2(P01, Q0, Q1, n, Pp, Qp, sc.stream);
-    if (use_wvm(ctx, n)) {  // one warp per check: two-pair Miller program
+    if (use_wvm_miller2(ctx, n)) {  // one warp per check: two-pair Miller program
       L::wvm_run(L::kVmMiller2, Pp, Qp, n, prod, ctx->sms, ctx->wvm_blocks_per_sm, sc.stream);
     } else {
       if ((e = vm_any(ctx, sc, L::kVmMiller, Pp, Qp, 2 * n, ml)) != cudaSuccess) return e;

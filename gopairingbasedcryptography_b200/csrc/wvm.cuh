@@ -65,7 +65,7 @@ BN_HD void lin_acc(LinAcc& a, const Fp& v, int c) {
 #define WVM_FINISH_ONEPASS 0
 #endif
 #ifndef WVM_LIN_BATCH
-#define WVM_LIN_BATCH 0
+#define WVM_LIN_BATCH 1  // LIN terms in batches of four loads: Pair(1) 1.44 -> 1.32 ms (profiles/r2/wvm_interpreter_variants.jsonl)
 #endif
 #ifndef WVM_AHEAD
 #define WVM_AHEAD 1

@@ -488,8 +488,9 @@ def test_gt_cyclo_div_equals_generic_div_on_gt_elements(engine):
 def test_two_pair_products_on_the_warp_vm(engine):
     """Small 2-pair products (BLS verification, every 2-pair PairingCheck) run ONE warp per product on the two-pair
     Miller program (k_wvm_miller2).  Against the oracle, including items whose first, second or both pairs contain the
-    point at infinity (gnark skips such pairs: the kernel falls back to the single-pair program / to 1)."""
-    n = 41
+    point at infinity (gnark skips such pairs: the kernel falls back to the single-pair program / to 1).  Batches below
+    about 600 products stay on two warps per product (lower latency while schedulers are idle), hence n = 601."""
+    n = 601
     P, Q, _, _ = common.points(2 * n, seed=0x2A1)
     P, Q = P.reshape(n, 2, 64).copy(), Q.reshape(n, 2, 128).copy()
     P[3, 0] = 0            # G1 infinity in the first pair
@@ -498,6 +499,7 @@ def test_two_pair_products_on_the_warp_vm(engine):
     P[9, 0] = 0; P[9, 1] = 0
     ref = port.multi_pair_batch(P.reshape(-1), Q.reshape(-1), n, 2).reshape(n, 384)
     assert (engine.multi_pair_batch(P, Q, 2) == ref).all()
+    assert (engine.multi_pair_batch(P[:41], Q[:41], 2) == ref[:41]).all()  # the two-warps-per-product route, same inputs
     ml = engine.miller_loop_batch(P, Q, 2)
     assert (engine.final_exp_batch(ml) == ref).all()
     ok = engine.pairing_check_batch(P, Q, 2)
