@@ -45,6 +45,18 @@ COST = {OP_MUL: 1.0, OP_LIN: 0.35, OP_INV: 40.0}
 INV2 = pow(2, -1, P)
 
 
+SPLIT_BIG = os.environ.get("WVM_SPLIT_BIG", "0") == "1"  # measured: no fewer LIN rounds (profiles/r2/wvm_generator_shapes.txt)
+
+
+def nfields(f):
+    """Term fields a form occupies in one LIN record: a coefficient beyond the 6-bit field is written as several terms on
+    the same slot (54 b = 31 b + 23 b) instead of materialising 31 b in a LIN of its own (one dependent round less)."""
+    vals = f.values() if isinstance(f, dict) else [c for _, c in f]
+    if not SPLIT_BIG:
+        return len(vals) if all(abs(c) <= CMAX for c in vals) else 99
+    return sum(max(1, -(-abs(c) // CMAX)) for c in vals)
+
+
 class Base:
     """A materialised Fp value living in a slot."""
     __slots__ = ("id", "kind", "op", "src", "flags", "terms", "value_const", "users", "round", "slot", "prio", "name", "depth")
@@ -101,7 +113,7 @@ class Lowering:
         return {b.id: 1}
 
     def fits(self, f):
-        return len(f) <= TMAX and all(abs(c) <= CMAX for c in f.values()) and sum(abs(c) for c in f.values()) <= CSUM_MAX
+        return nfields(f) <= TMAX and sum(abs(c) for c in f.values()) <= CSUM_MAX
 
     def normalise(self, f):
         """Keep forms encodable: materialise when they outgrow one LIN op."""
@@ -120,7 +132,7 @@ class Lowering:
         if not self.fits(f):
             items = sorted(f.items())
             # (a) coefficients beyond the 6-bit field: c b = q (CMAX b) + rem b with CMAX b materialised once
-            if any(abs(c) > CMAX for _, c in items):
+            if not SPLIT_BIG and any(abs(c) > CMAX for _, c in items):
                 g2 = {}
                 for k, c in items:
                     if abs(c) > CMAX:
@@ -136,7 +148,13 @@ class Lowering:
             # (b) too many terms / too large a coefficient sum: chunks in producer order, then the sum of the chunks
             chunks, cur, csum = [], {}, 0
             for k, c in items:
-                if len(cur) == TMAX or csum + abs(c) > CSUM_MAX:
+                while abs(c) > CSUM_MAX:  # (never in the pairing programs) peel full-budget pieces off a huge coefficient
+                    if cur:
+                        chunks.append(cur)
+                    sg = 1 if c > 0 else -1
+                    chunks.append({k: sg * CSUM_MAX})
+                    cur, csum, c = {}, 0, c - sg * CSUM_MAX
+                if nfields(cur) + nfields({k: c}) > TMAX or csum + abs(c) > CSUM_MAX:
                     chunks.append(cur)
                     cur, csum = {}, 0
                 cur[k] = c
@@ -334,7 +352,7 @@ def inline_lins(low, outputs, tmax):
                 g2 = dict(f)
                 del g2[k]
                 g2 = low.f_add(g2, dict(d.terms), c)
-                if len(g2) <= tmax and g2 and all(abs(v) <= CMAX for v in g2.values()) and sum(abs(v) for v in g2.values()) <= CSUM_MAX:
+                if nfields(g2) <= tmax and g2 and sum(abs(v) for v in g2.values()) <= CSUM_MAX:
                     f = g2
                     changed = True
                     total += 1
@@ -446,9 +464,16 @@ def encode(low, rounds):
                     rec[0] = OP_INV | (b.slot << 2)
                     rec[1] = b.src[0].slot
                 else:
-                    assert len(b.terms) <= 15
-                    rec[0] = OP_LIN | (b.slot << 2) | (len(b.terms) << 12)
-                    for i, (k, c) in enumerate(b.terms):
+                    fields = []
+                    for k, c in b.terms:  # a coefficient beyond the 6-bit field becomes several terms on the same slot
+                        sg = 1 if c > 0 else -1
+                        while abs(c) > CMAX:
+                            fields.append((k, sg * CMAX))
+                            c -= sg * CMAX
+                        fields.append((k, c))
+                    assert len(fields) <= 15
+                    rec[0] = OP_LIN | (b.slot << 2) | (len(fields) << 12)
+                    for i, (k, c) in enumerate(fields):
                         assert -32 <= c <= 31
                         rec[1 + i] = low.bases[k].slot | ((c & 63) << 10)
             out.extend(rec)
@@ -539,7 +564,7 @@ def build(name):
                 b.users.append(c)
                 b = c
             outputs.append(b)
-    tinline = int(TINLINE_ENV) if TINLINE_ENV is not None else TINLINE_BY_PROGRAM[name]
+    tinline = int(TINLINE_ENV) if TINLINE_ENV is not None else int(os.environ.get("WVM_TINLINE_" + name.upper(), TINLINE_BY_PROGRAM[name]))
     if tinline:
         inline_lins(low, outputs, tinline)
     rounds, live = schedule(low, outputs)
