@@ -521,3 +521,29 @@ def test_two_pair_products_on_the_warp_vm(engine):
     Qc = np.concatenate([hm, sig], axis=1).reshape(-1)
     assert (got == port.pairing_check_batch(Pc, Qc, n, 2).astype(bool)).all()
     assert got.sum() == n - 1 and not got[11]
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_fixed_base_four_items_per_thread_kernel(engine, group):
+    """From 65 536 scalars on a fixed-base launch gives every thread four consecutive scalars and ONE inversion
+    (Montgomery's trick): same affine points as the one-item kernel (two half-size calls), incl. the scalars 0, r, r + 1
+    and 2^256 - 1, a batch size that is not a multiple of four, and sampled points against the oracle."""
+    n = 70001
+    g1, g2 = port.generators()
+    base = np.frombuffer(g1 if group == 1 else g2, dtype=np.uint8)
+    rng = np.random.default_rng(0xF1BED + group)
+    s = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    edge = [0, o.R, o.R + 1, (1 << 256) - 1, 1, 2]
+    for i, e in enumerate(edge):
+        s[4 * i + (i % 4)] = np.frombuffer(int(e).to_bytes(32, "little"), dtype=np.uint8)
+    s[n - 1] = 0
+    table = engine.fixed_base_create(group, base)
+    mul = engine.g1_fixed_mul_batch if group == 1 else engine.g2_fixed_mul_batch
+    big = mul(table, s)
+    half = np.concatenate([mul(table, s[:35000]), mul(table, s[35000:])], axis=0)
+    assert (big == half).all()
+    idx = np.concatenate([np.arange(24), [n - 3, n - 2, n - 1], rng.integers(0, n, 21)])
+    ref_fn = port.g1_mul_base_batch if group == 1 else port.g2_mul_base_batch
+    ref = ref_fn(base, s[idx].reshape(-1), len(idx), 4).reshape(len(idx), -1)
+    assert (big[idx] == ref).all()
+    table.close()
