@@ -44,6 +44,66 @@ BN_HD bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
 BN_HD void f_set_one(Fp2& a) { a = fp2_one(); }
 BN_HD void f_set_zero(Fp2& a) { a = fp2_zero(); }
 
+// ---- who inverts ----------------------------------------------------------------------------------------------------
+// InvThread: every thread runs its own Fermat ladder (380 dependent Fp products).
+// InvCta (kernels only): the kBlock threads of a CTA share ONE ladder.  SIMT lanes run in lock step, so batching inside a
+// warp saves nothing -- a ladder costs a warp the same time for 1 or 32 lanes -- but across the 4 warps of a CTA it does:
+// a product tree over the 128 values in shared memory (7 levels up, one inversion by thread 0, 7 levels down with two
+// products each) costs the CTA ~400 warp-level products instead of 4 x 380.  Every thread of the CTA must call it the same
+// number of times (barriers); inv(0) = 0 as in f_inv.
+#if defined(__CUDACC__)
+#define BN_MEMBER __device__ __forceinline__ static
+#else
+#define BN_MEMBER static inline
+#endif
+struct InvThread {
+  BN_MEMBER Fp inv(const Fp& a) { return f_inv(a); }
+  BN_MEMBER Fp2 inv(const Fp2& a) { return f_inv(a); }
+};
+#if defined(__CUDACC__)
+#ifndef BN254_BLOCK
+#define BN254_BLOCK 128
+#endif
+BN_NOINLINE Fp cta_fp_inv(Fp z) {
+  constexpr int B = BN254_BLOCK;
+  __shared__ Fp tree[2 * B];  // level l (B >> l entries) starts at 2B - (2B >> l)
+  const int tid = threadIdx.x;
+  const bool zero = fp_is_zero(z);
+  tree[tid] = zero ? fp_one() : z;
+  __syncthreads();
+  int lo = 0;
+  for (int w = B >> 1; w >= 1; w >>= 1) {  // up: parent = left * right
+    int up = lo + 2 * w;
+    if (tid < w) tree[up + tid] = FP_MUL(tree[lo + 2 * tid], tree[lo + 2 * tid + 1]);
+    __syncthreads();
+    lo = up;
+  }
+  if (tid == 0) tree[lo] = fp_inv_bv(tree[lo]);
+  __syncthreads();
+  for (int w = 1; w <= B >> 1; w <<= 1) {  // down: inv(left) = inv(parent) * right, inv(right) = inv(parent) * left
+    int dn = lo - 2 * w;
+    if (tid < w) {
+      Fp pinv = tree[lo + tid], l = tree[dn + 2 * tid], r = tree[dn + 2 * tid + 1];
+      tree[dn + 2 * tid] = FP_MUL(pinv, r);
+      tree[dn + 2 * tid + 1] = FP_MUL(pinv, l);
+    }
+    __syncthreads();
+    lo = dn;
+  }
+  Fp r = tree[tid];
+  __syncthreads();  // the tree is reused by the next call
+  return zero ? fp_zero() : r;
+}
+struct InvCta {
+  BN_MEMBER Fp inv(const Fp& a) { return cta_fp_inv(a); }
+  BN_MEMBER Fp2 inv(const Fp2& a) {  // conj(a) / norm(a): the norm is the shared inversion
+    Fp ni = cta_fp_inv(fp_add(f_sqr(a.a0), f_sqr(a.a1)));
+    Fp2 r; r.a0 = f_mul(a.a0, ni); r.a1 = fp_neg(f_mul(a.a1, ni));
+    return r;
+  }
+};
+#endif
+
 #ifdef BN254_OOL_JAC
 #define BN_JAC BN_NOINLINE
 #else
@@ -88,6 +148,14 @@ template <typename J, typename A>
 BN_HD void jac_to_aff(A& r, const J& p) {
   if (jac_is_inf(p)) { f_set_zero(r.x); f_set_zero(r.y); return; }
   auto zi = f_inv(p.z);
+  auto zi2 = f_sqr(zi);
+  r.x = f_mul(p.x, zi2);
+  r.y = f_mul(p.y, f_mul(zi2, zi));
+}
+// the same with the inversion policy INV; no early exit (InvCta needs every thread): inv(0) = 0 maps infinity to (0, 0)
+template <typename INV, typename J, typename A>
+BN_HD void jac_to_aff_inv(A& r, const J& p) {
+  auto zi = INV::inv(p.z);
   auto zi2 = f_sqr(zi);
   r.x = f_mul(p.x, zi2);
   r.y = f_mul(p.y, f_mul(zi2, zi));
@@ -166,9 +234,9 @@ BN_HD Fp f_mul_beta(const Fp& x, const Fp& beta) { return f_mul(x, beta); }
 BN_HD Fp2 f_mul_beta(const Fp2& x, const Fp& beta) { return fp2_mul_fp(x, beta); }
 
 // [s]base by 2-dimensional GLV with the joint (Shamir) ladder over {P1, P2, P1+P2}; canonical affine out.
-template <typename J, typename A>
+template <typename J, typename A, typename INV = InvThread>
 BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& beta) {
-  if (aff_is_inf(base)) { out = base; return; }
+  if (aff_is_inf(base)) { out = base; return; }  // (InvCta callers substitute a finite point: every thread must reach both inversions)
   uint32_t k1[8], k2[8];
   bool n1, n2;
   glv_decompose(s, k1, n1, k2, n2);
@@ -186,7 +254,7 @@ BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& be
   {
     J t; t.x = p1.x; t.y = p1.y; f_set_one(t.z);
     jac_add_aff(t, t, p2);
-    jac_to_aff(tab[2], t);  // (0, 0) if P1 + P2 is the point at infinity (only off the prime-order subgroup)
+    jac_to_aff_inv<INV>(tab[2], t);  // (0, 0) if P1 + P2 is the point at infinity (only off the prime-order subgroup)
   }
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
   for (int i = GLV_MAX_BITS - 1; i >= 0; i--) {
@@ -198,7 +266,7 @@ BN_HD void scalar_mul_glv(A& out, const A& base, const uint32_t* s, const Fp& be
       if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
     }
   }
-  jac_to_aff(out, acc);
+  jac_to_aff_inv<INV>(out, acc);
 }
 
 // ---- 4-dimensional GLS scalar multiplication on G2 (Galbraith-Scott) ------------------------------------------------
@@ -251,8 +319,9 @@ constexpr int kGlsTable = 15, kGlsComposite = 11;
 constexpr int kGlsSliceFp2 = kGlsTable * 2 + 2 * kGlsComposite;  // in Fp2 units (64 B): 52 -> 3 328 B per thread
 BN_HD G2Aff gls_ld(const Fp2* slice, int e) { G2Aff r; r.x = fp2_ld(slice[2 * e]); r.y = fp2_ld(slice[2 * e + 1]); return r; }
 BN_HD void gls_st(Fp2* slice, int e, const G2Aff& v) { fp2_st(slice[2 * e], v.x); fp2_st(slice[2 * e + 1], v.y); }
+template <typename INV = InvThread>
 BN_HD void scalar_mul_gls4(G2Aff& out, const G2Aff& base, const uint32_t* s, Fp2* slice) {
-  if (aff_is_inf(base)) { out = base; return; }
+  if (aff_is_inf(base)) { out = base; return; }  // (InvCta callers substitute a finite point)
   uint32_t kv[4][4];
   bool neg[4];
   gls4_decompose(s, kv, neg);
@@ -296,7 +365,7 @@ BN_HD void scalar_mul_gls4(G2Aff& out, const G2Aff& base, const uint32_t* s, Fp2
     nc++;
   }
   {
-    Fp2 inv = f_inv(run);
+    Fp2 inv = INV::inv(run);
     int ci = kGlsComposite - 1;
     for (int idx = 15; idx >= 3; idx--) {
       if (!(idx & (idx - 1))) continue;
@@ -322,7 +391,7 @@ BN_HD void scalar_mul_gls4(G2Aff& out, const G2Aff& base, const uint32_t* s, Fp2
       if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
     }
   }
-  jac_to_aff(out, acc);
+  jac_to_aff_inv<INV>(out, acc);
 }
 
 // Fixed base: table[w*255 + d-1] = [d * 2^(8w)] base (affine), w = 0..31, d = 1..255; 32 mixed additions.
@@ -338,11 +407,11 @@ BN_HD void scalar_mul_fixed_jac(J& acc, const A* table, const uint32_t* s) {
     }
   }
 }
-template <typename J, typename A>
+template <typename J, typename A, typename INV = InvThread>
 BN_HD void scalar_mul_fixed(A& out, const A* table, const uint32_t* s) {
   J acc;
   scalar_mul_fixed_jac<J, A>(acc, table, s);
-  jac_to_aff(out, acc);
+  jac_to_aff_inv<INV>(out, acc);
 }
 // N Jacobian points -> affine with ONE inversion (Montgomery's trick over the finite z-coordinates): 3 (N - 1) extra
 // products instead of N - 1 inversions of ~380 products each.  Same canonical affine results as jac_to_aff.

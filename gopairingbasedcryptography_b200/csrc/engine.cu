@@ -389,7 +389,8 @@ cudaError_t seq_scalar_mul(bn254_ctx* ctx, Scratch& sc, int g, const void* base,
   const size_t sub = std::max<size_t>(1, std::min<size_t>(n, (size_t(1) << 30) / per));
   void* scratch;
   cudaError_t e;
-  if ((e = sc.reserve(al256(sub * per))) != cudaSuccess || (e = sc.get(sub * per, &scratch)) != cudaSuccess) return e;
+  const size_t slices = sub + L::kBlockThreads;  // every thread of the last CTA owns a slice (the CTA shares its inversions)
+  if ((e = sc.reserve(al256(slices * per))) != cudaSuccess || (e = sc.get(slices * per, &scratch)) != cudaSuccess) return e;
   for (size_t off = 0; off < n; off += sub) {
     size_t c = std::min(sub, n - off);
     L::scalar_mul_g2_gls(static_cast<const char*>(base) + off * stride * BN254_G2_BYTES, stride, static_cast<const char*>(scalars) + off * BN254_SCALAR_BYTES, c,

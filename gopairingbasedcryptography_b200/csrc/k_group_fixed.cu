@@ -7,16 +7,14 @@ namespace {
 // fixed base: 32 windowed mixed additions from a precomputed affine table (L2-resident, 0.5-1 MB)
 template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_fixed_mul(const A* table, const void* scalars, size_t n, void* out) {
-  cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
+  cta_lockstep_set(false);  // no lockstep barriers in this kernel; the flag is read by the shared field routines
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s[8];
-  const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(scalars) + i * 32);
-  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  const bool live = i < n;
+  uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // threads past the end add nothing and hand z = 0 to the CTA's shared inversion
+  if (live) load_scalar(s, scalars, i);
   A r;
-  scalar_mul_fixed<J, A>(r, table, s);
-  store_struct(out, i, r);
+  scalar_mul_fixed<J, A, InvCta>(r, table, s);
+  if (live) store_struct(out, i, r);
 }
 // Large batches: FOUR consecutive scalars per thread, one inversion for the four results (the final inversion is half of
 // a G1 fixed-base multiplication: 380 of 732 Fp products).  Items [4t, 4t + 4) are contiguous for the thread.
