@@ -8,10 +8,17 @@ template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_aff_add(const void* a, const void* b, size_t n, void* out) {
   cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  A x, y, r; load_struct(x, a, i); load_struct(y, b, i);
-  aff_add<J, A>(r, x, y);
-  store_struct(out, i, r);
+  const bool live = i < n;
+  A x, y, r;
+  if (live) { load_struct(x, a, i); load_struct(y, b, i); }
+  else { f_set_zero(x.x); f_set_zero(x.y); y = x; }
+  // gnark Add semantics with the CTA's shared inversion: infinity operands pass the other one through (z = 1 is
+  // inverted, harmlessly), everything else is one mixed addition and a shared normalisation
+  J t;
+  if (aff_is_inf(x)) { t.x = y.x; t.y = y.y; f_set_one(t.z); if (aff_is_inf(y)) f_set_zero(t.z); }
+  else { t.x = x.x; t.y = x.y; f_set_one(t.z); if (!aff_is_inf(y)) jac_add_aff(t, t, y); }
+  jac_to_aff_inv<InvCta>(r, t);
+  if (live) store_struct(out, i, r);
 }
 // out[i] = U[0] + sum_{j < m, bit j of sel_i set} U[j+1]   (Waters hash: ibe/waters05_ibe/waters05_ibe.go:227-233).
 // Bit j is bit (7 - j%8) of byte j/8 -- the MSB-first order of waters05_ibe.go:302-313.  The m+1 public
@@ -29,20 +36,20 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum(const A
   }
   __syncthreads();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t* bits = sel + i * (size_t)((m + 7) / 8);
+  const bool live = i < n;
+  const uint8_t* bits = sel + (live ? i : 0) * (size_t)((m + 7) / 8);
   J acc;
   if (aff_is_inf(su[0])) { f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z); }
   else { acc.x = su[0].x; acc.y = su[0].y; f_set_one(acc.z); }
-  for (int j = 0; j < m; j++) {
+  for (int j = 0; j < (live ? m : 0); j++) {
     if ((bits[j >> 3] >> (7 - (j & 7))) & 1) {
       A e = su[j + 1];
       if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
     }
   }
   A r;
-  jac_to_aff(r, acc);
-  store_struct(out, i, r);
+  jac_to_aff_inv<InvCta>(r, acc);  // one inversion per CTA (threads past the end take part with the base point)
+  if (live) store_struct(out, i, r);
 }
 // Byte-window form of the same subset sum for large batches: table[b * 256 + v] = sum of the points U[1 + 8b + i] whose
 // bit (7 - i) is set in v (affine; v = 0 -> infinity), built once per call by 256 threads per selector byte; an
@@ -70,14 +77,14 @@ template <typename J, typename A>
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum_tab(const A* U, const A* __restrict__ table, int m, const uint8_t* sel, size_t n, void* out) {
   cta_lockstep_set(false);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const bool live = i < n;
   int nbytes = (m + 7) / 8;
-  const uint8_t* bits = sel + i * (size_t)nbytes;
+  const uint8_t* bits = sel + (live ? i : 0) * (size_t)nbytes;
   J acc;
   A u0 = U[0];
   if (aff_is_inf(u0)) { f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z); }
   else { acc.x = u0.x; acc.y = u0.y; f_set_one(acc.z); }
-  for (int b = 0; b < nbytes; b++) {
+  for (int b = 0; b < (live ? nbytes : 0); b++) {
     int v = bits[b];
     if (v) {
       A e; load_struct(e, table, (size_t)b * 256 + v);
@@ -85,8 +92,8 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_subset_sum_tab(con
     }
   }
   A r;
-  jac_to_aff(r, acc);
-  store_struct(out, i, r);
+  jac_to_aff_inv<InvCta>(r, acc);  // one inversion per CTA
+  if (live) store_struct(out, i, r);
 }
 // out[g] = sum of the `len` consecutive points of group g, processed as ceil(len/32)-way partial sums per pass
 template <typename J, typename A>
@@ -94,18 +101,18 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_segment_sum(const 
   cta_lockstep_set(false);  // no barriers in this kernel; the flag is read by the shared field routines
   int nch = (len + chunk - 1) / chunk;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= groups * (size_t)nch) return;
-  size_t g = t / nch;
-  int c = (int)(t % nch);
-  int first = c * chunk, cnt = min(chunk, len - first);
+  const bool live = t < groups * (size_t)nch;
+  size_t g = live ? t / nch : 0;
+  int c = live ? (int)(t % nch) : 0;
+  int first = c * chunk, cnt = live ? min(chunk, len - first) : 0;
   J acc; f_set_zero(acc.x); f_set_zero(acc.y); f_set_zero(acc.z);
   for (int j = 0; j < cnt; j++) {
     A e; load_struct(e, pts, g * (size_t)len + first + j);
     if (!aff_is_inf(e)) jac_add_aff(acc, acc, e);
   }
   A r;
-  jac_to_aff(r, acc);
-  store_struct(out, t, r);
+  jac_to_aff_inv<InvCta>(r, acc);  // one inversion per CTA
+  if (live) store_struct(out, t, r);
 }
 // out[i] = -in[i]
 template <typename A>
