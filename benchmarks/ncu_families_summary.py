@@ -19,7 +19,7 @@ for r in csv.DictReader(lines):
 units = json.load(open(sys.argv[2]))
 out = ["kernel%sgrid   time ms  regs  warps%%  issue%%  fmaheavy%%   DRAM MB   fmaheavy thread-instr   units   IMAD-class/unit  DRAM B/unit" % (" " * 40)]
 imad = {}
-NAMES = {"k_pair": "pair", "k_check2_fixed_g1": "bls_verify", "k_scalar_mul<bn254::G1Jac": "g1_var", "k_scalar_mul_g2_gls": "g2_var",
+NAMES = {"k_subset_sum_tab": "_subset_sum_tab", "k_gt_mul<0>": "_gt_mul", "k_pair": "pair", "k_check2_fixed_g1": "bls_verify", "k_scalar_mul<bn254::G1Jac": "g1_var", "k_scalar_mul_g2_gls": "g2_var",
          "k_fixed_mul<G1": "g1_fixed", "k_fixed_mul<G2": "g2_fixed", "k_gt_exp<0>": "gt_exp", "k_gt_exp<1>": "gt_cyclo_exp", "k_gt_fixed_exp": "gt_fixed_exp",
          "k_miller_lines": "bsw07_decrypt_policy_lines"}
 def short_name(name):
@@ -53,5 +53,11 @@ for (i, name), m in rows.items():
 open(sys.argv[3] + "/ncu_kernel_families_summary.txt", "w").write(
     "one launch per kernel family, benchmarks/profile_driver_r2.py; ncu --metrics pass (cold-cache, serialised: the utilisation and per-unit\n"
     "columns are what this file is for).  IMAD-class/unit = sm__inst_executed_pipe_fmaheavy.sum x 32 / units of the launch.\n\n" + "\n".join(out) + "\n")
+# composite flows: sums of the measured per-unit counts of the kernels they launch (derived, not captured as one unit)
+if all(k in imad for k in ("bsw07_decrypt_policy_lines", "g1_var")):
+    imad["bsw07_decrypt_key_lines"] = imad["bsw07_decrypt_policy_lines"] + 200 * imad["g1_var"]  # + [Delta_i]Cy_i, [Delta_i]Cy'_i per ciphertext
+if all(k in imad for k in ("g1_fixed", "_subset_sum_tab", "g2_var", "gt_fixed_exp", "_gt_mul")):
+    imad["waters05_encrypt"] = imad["g1_fixed"] + imad["_subset_sum_tab"] + imad["g2_var"] + imad["gt_fixed_exp"] + imad["_gt_mul"]
+imad = {k: v for k, v in imad.items() if not k.startswith("_")}
 json.dump(imad, open(sys.argv[3] + "/executed_imad_per_unit.json", "w"), indent=1)
 print("\n".join(out))
