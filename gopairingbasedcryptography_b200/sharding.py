@@ -87,9 +87,10 @@ class DevicePool:
         return len(self.engines)
 
     # ---- the dispatcher -----------------------------------------------------------------------------------------
-    def spans(self, n):
+    def spans(self, n, min_per_device=None):
         """[(engine, lo, hi)] for a batch of n items."""
-        world = max(1, min(len(self.engines), -(-n // self.min_per_device)))
+        per = self.min_per_device if min_per_device is None else min_per_device
+        world = max(1, min(len(self.engines), -(-n // per)))
         out = []
         for r in range(world):
             lo, hi = shard_range(n, r, world)
@@ -97,10 +98,10 @@ class DevicePool:
                 out.append((self.engines[r], lo, hi))
         return out
 
-    def shard(self, n, fn):
+    def shard(self, n, fn, min_per_device=None):
         """Runs fn(engine, lo, hi) for every chunk, concurrently; returns the chunk results in order.  The first
         failure is re-raised after every chunk has finished (no call is left running on a context)."""
-        spans = self.spans(n)
+        spans = self.spans(n, min_per_device)
         if len(spans) <= 1:
             return [fn(*s) for s in spans]
         futs = [self._workers.submit(fn, *s) for s in spans]
@@ -169,11 +170,7 @@ class DevicePool:
         k = len(P)
         if k == 0 or k != len(Q):
             raise ValueError("invalid inputs sizes")
-        saved, self.min_per_device = self.min_per_device, 1
-        try:
-            partials = self.shard(k, lambda e, lo, hi: e.miller_loop_batch(P[lo:hi], Q[lo:hi], hi - lo)[0])
-        finally:
-            self.min_per_device = saved
+        partials = self.shard(k, lambda e, lo, hi: e.miller_loop_batch(P[lo:hi], Q[lo:hi], hi - lo)[0], min_per_device=1)
         return combine_partials(self.engines[0], partials)
 
     # ---- groups and GT ------------------------------------------------------------------------------------------
