@@ -547,3 +547,41 @@ def test_fixed_base_four_items_per_thread_kernel(engine, group):
     ref = ref_fn(base, s[idx].reshape(-1), len(idx), 4).reshape(len(idx), -1)
     assert (big[idx] == ref).all()
     table.close()
+
+
+def test_group_kernels_with_shared_inversion_edge_cases(engine):
+    """The group kernels share one inversion per CTA (every thread takes part: threads past the end and infinity
+    operands run on substitutes).  Ragged batch sizes around the CTA size with infinity bases / operands in both groups,
+    the zero scalar and r, against the oracle."""
+    for n in (1, 127, 129, 257):
+        P, Q, _, _ = common.points(n, seed=0x5EED + n)
+        ks = common.scalars(n, seed=n)
+        ks[0] = 0
+        if n > 2:
+            ks[2] = o.R
+        k = sb(ks)
+        P, Q = P.copy(), Q.copy()
+        if n > 5:
+            P[64 * 3:64 * 4] = 0
+            Q[128 * 4:128 * 5] = 0
+            Q[128 * (n - 1):] = 0
+        assert (engine.g1_mul_batch(P, k).reshape(-1) == port.g1_mul_batch(P, k, n, 4)).all()
+        assert (engine.g2_mul_batch(Q, k).reshape(-1) == port.g2_mul_batch(Q, k, n, 4)).all()
+        Pr, Qr = np.roll(P, 64), np.roll(Q, 128)
+        assert (engine.g1_add_batch(P, Pr).reshape(-1) == port.g1_add_batch(P, Pr, n, 4)).all()
+        assert (engine.g2_add_batch(Q, Qr).reshape(-1) == port.g2_add_batch(Q, Qr, n, 4)).all()
+        assert (engine.g2_add_batch(Q, Q).reshape(-1) == port.g2_add_batch(Q, Q, n, 4)).all()
+        g1, g2 = port.generators()
+        assert (engine.g2_mul_base_batch(g2, k).reshape(-1) == port.g2_mul_base_batch(g2, k, n, 4)).all()
+        if n >= 16:
+            m = 16
+            sel = np.frombuffer(np.random.default_rng(n).bytes(n * 2), dtype=np.uint8).reshape(n, 2).copy()
+            sel[0] = 0
+            U = Q[:128 * (m + 1)].copy()
+            got = engine.g2_subset_sum_batch(U, sel)
+            for i in (0, 1, n // 2, n - 1):
+                acc = U[:128].copy()
+                for j in range(m):
+                    if (sel[i, j >> 3] >> (7 - (j & 7))) & 1:
+                        acc = port.g2_add_batch(acc, U[128 * (j + 1):128 * (j + 2)], 1, 1)
+                assert (got[i] == acc).all()
