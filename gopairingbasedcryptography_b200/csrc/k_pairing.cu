@@ -222,13 +222,7 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
     // it >= 0: tangent (+ chord if the digit is non-zero); it == -1, -2: the two Frobenius lines
     if (it >= 0 && it != ATE_NAF_LEN - 2) fp12_sqr(f, f);
     int reps = (it >= 0 && ATE_NAF[it]) ? 2 : 1;
-    for (int r = 0; r < reps; r++, s++) {
-      for (int j = 0; j < cnt; j++) {
-        if ((skip >> j) & 1u) continue;
-        const Fp2* L = table + ((size_t)(first + j) * kLinesPerPoint + s) * 3;
-        apply_line_mem(f, p[j], L, sc_);
-      }
-    }
+    for (int r = 0; r < reps; r++, s++) miller_lines_step(f, p, table, first, cnt, skip, s, sc_);
   }
   store_struct(partial, i * (size_t)nchunks + ci, f);
 }

@@ -16,6 +16,7 @@ namespace bn254 {
 struct G1Aff { Fp x, y; };
 struct G2Aff { Fp2 x, y; };
 struct G2Proj { Fp2 x, y, z; };
+static constexpr int kLinesPerPoint = 65 + 21 + 2;  // lines per fixed G2 point (line tables, below)
 
 BN_HD bool g1_is_inf(const G1Aff& p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
 BN_HD bool g2_is_inf(const G2Aff& q) { return fp2_is_zero(q.x) && fp2_is_zero(q.y); }
@@ -86,6 +87,28 @@ BN_NOINLINE void g2_add_step_sc(G2Proj& T, const G2Aff& Q, bool neg, bool update
 BN_NOINLINE void apply_line_sc(Fp12& f, const G1Aff& P, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc, nullptr); }
 // f *= line(P), raw line (r0, r1, r2) in memory (line tables): fetched together with f.c1, one round trip
 BN_NOINLINE void apply_line_mem(Fp12& f, const G1Aff& P, const Fp2* r, Fp2* sc) { BN_SC_REBIND(sc) apply_line_staged(f, P.x, P.y, sc + 3, sc + 6, sc, r); }
+// f *= line_a(Pa) * line_b(Pb), both raw lines in memory (line tables): see tower_staged.cuh
+BN_NOINLINE void apply_line_pair_mem(Fp12& f, const G1Aff& Pa, const Fp2* ra, const G1Aff& Pb, const Fp2* rb, Fp2* sc) {
+  BN_SC_REBIND(sc)
+  Fp12 y;
+  line_pair_stage(sc, ra, Pa.x, Pa.y, rb, Pb.x, Pb.y);
+  fp12_mul_034_034(y, sc);
+  fp12_mul_by_01234(f, y);
+}
+// One schedule position s of the line-table Miller loop for a chunk of `cnt` table points (bit j of skip: pair j holds a
+// point at infinity): the lines are taken two at a time, a left-over one alone.
+BN_HD void miller_lines_step(Fp12& f, const G1Aff* p, const Fp2* table, int first, int cnt, unsigned skip, int s, Fp2* sc) {
+  int pending = -1;
+  for (int j = 0; j < cnt; j++) {
+    if ((skip >> j) & 1u) continue;
+    if (pending < 0) { pending = j; continue; }
+    const Fp2* La = table + ((size_t)(first + pending) * kLinesPerPoint + s) * 3;
+    const Fp2* Lb = table + ((size_t)(first + j) * kLinesPerPoint + s) * 3;
+    apply_line_pair_mem(f, p[pending], La, p[j], Lb, sc);
+    pending = -1;
+  }
+  if (pending >= 0) apply_line_mem(f, p[pending], table + ((size_t)(first + pending) * kLinesPerPoint + s) * 3, sc);
+}
 BN_HD void apply_line(Fp12& f, const G1Aff& P, const Fp2& r0, const Fp2& r1, const Fp2& r2) {
   BN_SCRATCH_DECL
   Fp2 r[3] = {r0, r1, r2};
@@ -152,7 +175,6 @@ BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k
 // computed once (g2_precompute_lines) and every later pairing against Q costs per line: 2 Fp2 x Fp products
 // (evaluation at P) + one sparse 034 multiply -- no G2 arithmetic, no T state.
 // Order: for i = 64..0 { tangent line; chord line if NAF digit != 0 }, then the two Frobenius lines.
-static constexpr int kLinesPerPoint = 65 + 21 + 2;
 BN_HD void g2_precompute_lines(const G2Aff& Q, Fp2* out /* kLinesPerPoint x 3 */) {
   G2Proj T; T.x = Q.x; T.y = Q.y; T.z = fp2_one();
   G2Aff qn; qn.x = Q.x; qn.y = fp2_neg(Q.y);

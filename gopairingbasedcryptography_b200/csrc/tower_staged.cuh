@@ -294,3 +294,55 @@ BN_NOINLINE void fp12_mul_034(Fp12& z, const Fp2& l0, const Fp2& l1, const Fp2& 
   fp6_mul_01_staged(z.c1, Y, L[0], L[2], W[0], W[1], &a, &b);
   fp6_add_mul_v(z.c0, a, b);
 }
+
+// ---- two lines of one Miller step at once ----------------------------------------------------------------------------
+// f *= l(P) * l'(P'):  the two sparse factors are multiplied first -- 034 x 034 has five non-zero coefficients, six Fp2
+// products -- and f takes ONE multiplication by that 01234-sparse element (17 Fp2 products: 6 + 5 + 6) instead of two
+// 034 multiplications (2 x 13); f is read and written once instead of twice.  Exact field arithmetic: same bytes as the
+// two single-line multiplications in either order.
+//   A = (a0, a3, a4) = (r0 yP, r1 xP, r2) on (c0.b0, c1.b0, c1.b1), B likewise:
+//   y0 = a0 b0 + xi a4 b4   y1 = a3 b3   y2 = a3 b4 + a4 b3   y3 = a0 b3 + a3 b0   y4 = a0 b4 + a4 b0   (y5 = 0)
+BN_LEAF Fp2 fp2_add_mul_xi(const Fp2& a, const Fp2& b) { return fp2_add_i(fp2_ld(a), fp2_mul_xi_bv(fp2_ld(b))); }
+BN_NOINLINE void line_pair_stage(Fp2* sc, const Fp2* ra, const Fp& ax, const Fp& ay, const Fp2* rb, const Fp& bx, const Fp& by) {
+  Fp2 a0 = fp2_ld(ra[0]), a1 = fp2_ld(ra[1]), a2 = fp2_ld(ra[2]), b0 = fp2_ld(rb[0]), b1 = fp2_ld(rb[1]), b2 = fp2_ld(rb[2]);
+  Fp pax = fp_ld(ax), pay = fp_ld(ay), pbx = fp_ld(bx), pby = fp_ld(by);
+  fp2_st(sc[2], a2); fp2_st(sc[5], b2);
+  fp2_st(sc[0], fp2_mul_fp_i(a0, pay));
+  fp2_st(sc[1], fp2_mul_fp_i(a1, pax));
+  fp2_st(sc[3], fp2_mul_fp_i(b0, pby));
+  fp2_st(sc[4], fp2_mul_fp_i(b1, pbx));
+}
+BN_NOINLINE void fp12_mul_034_034(Fp12& y, Fp2* sc) {  // operands in sc[0..5] (line_pair_stage), sc[6..8] temporaries
+  BN_CTA_SYNC();
+  fp2_mul(sc[6], sc[0], sc[3]);  // a0 b0
+  fp2_mul(sc[7], sc[1], sc[4]);  // a3 b3
+  fp2_mul(sc[8], sc[2], sc[5]);  // a4 b4
+  fp2_cross(y.c0.b2, sc[1], sc[2], sc[4], &sc[5], sc[7], &sc[8], nullptr, kCrossNone, nullptr, nullptr);
+  fp2_cross(y.c1.b0, sc[0], sc[1], sc[3], &sc[4], sc[6], &sc[7], nullptr, kCrossNone, nullptr, nullptr);
+  fp2_cross(y.c1.b1, sc[0], sc[2], sc[3], &sc[5], sc[6], &sc[8], nullptr, kCrossNone, nullptr, nullptr);
+  y.c0.b0 = fp2_add_mul_xi(sc[6], sc[8]);
+  { Fp2 t = fp2_ld(sc[7]); fp2_st(y.c0.b1, t); }
+  y.c1.b2 = fp2_zero();
+}
+BN_NOINLINE void stage_y01234(Fp2* dst, const Fp12& y, bool sum) {  // sum: (y0 + y3, y1 + y4, y2); else (y3, y4)
+  if (sum) {
+    Fp2 a = fp2_ld(y.c0.b0), b = fp2_ld(y.c0.b1), c = fp2_ld(y.c0.b2), d = fp2_ld(y.c1.b0), e = fp2_ld(y.c1.b1);
+    fp2_st(dst[0], fp2_add_i(a, d)); fp2_st(dst[1], fp2_add_i(b, e)); fp2_st(dst[2], c);
+  } else {
+    Fp2 d = fp2_ld(y.c1.b0), e = fp2_ld(y.c1.b1);
+    fp2_st(dst[0], d); fp2_st(dst[1], e);
+  }
+}
+BN_NOINLINE void fp12_mul_by_01234(Fp12& f, const Fp12& y) {  // y.c1.b2 == 0
+  BN_SCRATCH_DECL
+  Fp6 a, b;
+  stage6x2(sc_, f.c0, y.c0);
+  fp6_mul_staged(a, sc_, nullptr, nullptr);
+  stage6(sc_, f.c1);
+  stage_y01234(sc_ + 3, y, false);
+  fp6_mul_01_staged(b, sc_, sc_[3], sc_[4], sc_[5], sc_[6], nullptr, nullptr);
+  stage6_sum(sc_, f.c0, f.c1);
+  stage_y01234(sc_ + 3, y, true);
+  fp6_mul_staged(f.c1, sc_, &a, &b);
+  fp6_add_mul_v(f.c0, a, b);
+}

@@ -129,11 +129,13 @@ extern "C" void emu_multi_pair_lines(const void* P, const void* Q, size_t n, siz
       if (it >= 0 && it != ATE_NAF_LEN - 2) fp12_sqr(f, f);
       int reps = (it >= 0 && ATE_NAF[it]) ? 2 : 1;
       for (int r = 0; r < reps; r++, s++)
-        for (size_t j = 0; j < m; j++) {
-          G1Aff p = ld<G1Aff>(P, i * m + j);
-          if (g1_is_inf(p) || qs[j]) continue;
-          const Fp2* L = table + (j * kLinesPerPoint + s) * 3;
-          apply_line(f, p, L[0], L[1], L[2]);
+        for (size_t j0 = 0; j0 < m; j0 += 8) {  // chunks of 8 table points, lines two at a time: the kernel's own step function
+          int cnt = (int)(m - j0 < 8 ? m - j0 : 8);
+          G1Aff p[8];
+          unsigned skip = 0;
+          for (int j = 0; j < cnt; j++) { p[j] = ld<G1Aff>(P, i * m + j0 + j); if (g1_is_inf(p[j]) || qs[j0 + j]) skip |= 1u << j; }
+          Fp2 sc[kScratchSlots];
+          miller_lines_step(f, p, table, (int)j0, cnt, skip, s, sc);
         }
     }
     final_exp(f, f);

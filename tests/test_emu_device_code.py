@@ -249,11 +249,13 @@ def test_gt_exp_fixed_windows(emu):
 
 def test_precomputed_g2_lines(emu):
     """Line tables of fixed G2 points + line-based Miller product == the ordinary multi-pairing (incl. infinity)."""
-    n, m = 3, 5
+    n, m = 3, 11             # two chunks of table points (8 + 3): lines are applied two at a time, left-overs alone
     _, Q, _, _ = common.points(m, seed=401)
     P, _, _, _ = common.points(n * m, seed=402)
     Q[128 * 2:128 * 3] = 0   # an infinity G2 point in the key
-    P[64 * 7:64 * 8] = 0     # and an infinity G1 operand
+    P[64 * 7:64 * 8] = 0     # and infinity G1 operands (odd and even numbers of live lines per chunk)
+    P[64 * 12:64 * 13] = 0
+    P[64 * 31:64 * 32] = 0
     out = np.zeros(384 * n, np.uint8)
     emu.emu_multi_pair_lines(vp(P), vp(Q), sz(n), sz(m), vp(out))
     ref = port.multi_pair_batch(P, np.tile(Q, n), n, m)
