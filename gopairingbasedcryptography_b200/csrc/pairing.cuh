@@ -126,6 +126,35 @@ BN_HD void g2_add_step(G2Proj& T, const G2Aff& Q, Fp2& r0, Fp2& r1, Fp2& r2, boo
   r0 = sc_[3]; r1 = sc_[4]; r2 = sc_[5];
 }
 
+// One G2 step (kind 0: tangent; 1: chord with +-Q[j]; 2: chord with q1; 3: chord with q2, no update) for every live pair,
+// lines applied to f two at a time: the first line of a couple is parked on the stack while the second pair's step uses
+// the scratch, then both go through ONE multiplication of f (apply_line_pair_mem); a left-over line is applied alone.
+template <int KC>
+BN_HD void miller_lines_of_step(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k, unsigned skip, int kind, bool neg, Fp2* sc_) {
+  int pending = -1, last = -1;
+  for (int j = 0; j < k; j++) if (!((skip >> j) & 1u)) last = j;
+  Fp2 park[3];
+  for (int j = 0; j < k; j++) {
+    if ((skip >> j) & 1u) continue;
+    if (kind == 0) g2_dbl_step_sc(T[j], sc_);
+    else if (kind == 1) g2_add_step_sc(T[j], Q[j], neg, true, sc_);
+    else {
+      G2Aff q;
+      if (kind == 2) { fp2_mul(q.x, fp2_conj(Q[j].x), GAMMA1[2]); fp2_mul(q.y, fp2_conj(Q[j].y), GAMMA1[3]); }
+      else { q.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q.y = Q[j].y; }  // -pi^2(Q): xi^((p^2-1)/2) = -1
+      g2_add_step_sc(T[j], q, false, kind == 2, sc_);
+    }
+    if (pending < 0) {
+      if (j == last) { apply_line_sc(f, P[j], sc_); continue; }  // nobody to pair with: straight from the scratch
+      Fp2 a = fp2_ld(sc_[3]), b = fp2_ld(sc_[4]), c = fp2_ld(sc_[5]);
+      fp2_st(park[0], a); fp2_st(park[1], b); fp2_st(park[2], c);
+      pending = j;
+      continue;
+    }
+    apply_line_pair_mem(f, P[pending], park, P[j], sc_ + 3, sc_);
+    pending = -1;
+  }
+}
 template <int KC>
 BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k_rt) {
   BN_SCRATCH_DECL
@@ -137,32 +166,35 @@ BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int
     T[j].x = Q[j].x; T[j].y = Q[j].y; T[j].z = fp2_one();
   }
   if (skip == (k >= 32 ? 0xffffffffu : ((1u << k) - 1u))) return;
+  if (KC == 1) {  // the single pairing (k_pair): every line straight from the scratch
+    for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
+      if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
+      int d = ATE_NAF[i];
+      g2_dbl_step_sc(T[0], sc_);
+      apply_line_sc(f, P[0], sc_);
+      if (d) {
+        g2_add_step_sc(T[0], Q[0], d < 0, true, sc_);
+        apply_line_sc(f, P[0], sc_);
+      }
+    }
+    G2Aff q1, q2;
+    fp2_mul(q1.x, fp2_conj(Q[0].x), GAMMA1[2]);
+    fp2_mul(q1.y, fp2_conj(Q[0].y), GAMMA1[3]);
+    q2.x = fp2_mul_fp(Q[0].x, GAMMA2[2]); q2.y = Q[0].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
+    g2_add_step_sc(T[0], q1, false, true, sc_);
+    apply_line_sc(f, P[0], sc_);
+    g2_add_step_sc(T[0], q2, false, false, sc_);
+    apply_line_sc(f, P[0], sc_);
+    return;
+  }
   for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
     if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
     int d = ATE_NAF[i];
-#pragma unroll
-    for (int j = 0; j < k; j++) {
-      if ((skip >> j) & 1u) continue;
-      g2_dbl_step_sc(T[j], sc_);
-      apply_line_sc(f, P[j], sc_);
-      if (d) {
-        g2_add_step_sc(T[j], Q[j], d < 0, true, sc_);
-        apply_line_sc(f, P[j], sc_);
-      }
-    }
+    miller_lines_of_step<KC>(f, P, Q, T, k, skip, 0, false, sc_);
+    if (d) miller_lines_of_step<KC>(f, P, Q, T, k, skip, 1, d < 0, sc_);
   }
-#pragma unroll
-  for (int j = 0; j < k; j++) {
-    if ((skip >> j) & 1u) continue;
-    G2Aff q1, q2;
-    fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
-    fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
-    q2.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q2.y = Q[j].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
-    g2_add_step_sc(T[j], q1, false, true, sc_);
-    apply_line_sc(f, P[j], sc_);
-    g2_add_step_sc(T[j], q2, false, false, sc_);
-    apply_line_sc(f, P[j], sc_);
-  }
+  miller_lines_of_step<KC>(f, P, Q, T, k, skip, 2, false, sc_);
+  miller_lines_of_step<KC>(f, P, Q, T, k, skip, 3, false, sc_);
 }
 BN_HD void miller_loop(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int k) {
   if (k == 1) miller_loop_t<1>(f, P, Q, T, 1);
