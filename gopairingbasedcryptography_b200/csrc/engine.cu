@@ -329,7 +329,7 @@ cudaError_t seq_multi_pair(bn254_ctx* ctx, Scratch& sc, int mode, const void* P,
 }
 cudaError_t seq_multi_pair_lines(bn254_ctx*, Scratch& sc, const void* P, const bn254_lines* Lt, size_t n, void* out) {
   const int m = (int)Lt->m;
-  const int nchunks = (m + L::kMpChunk - 1) / L::kMpChunk;
+  const int nchunks = (m + L::kLinesChunk - 1) / L::kLinesChunk;
   size_t need = n * (size_t)nchunks * BN254_GT_BYTES;
   void* partial;
   cudaError_t e;

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
                                                                           size_t n, int m, int nchunks, void* partial) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int ci = blockIdx.y;
-  int first = ci * kMpChunk, cnt = min(kMpChunk, m - first);
-  G1Aff p[kMpChunk];
+  int first = ci * launch::kLinesChunk, cnt = min(launch::kLinesChunk, m - first);
+  G1Aff p[launch::kLinesChunk];
   unsigned skip = 0;
   if (i < n) {
     for (int j = 0; j < cnt; j++) {

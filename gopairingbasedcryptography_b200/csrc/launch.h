@@ -16,6 +16,10 @@ extern std::atomic<uint64_t> g_launches;
 
 constexpr int kBlockThreads = 128;        // CTA size of every thread kernel
 constexpr int kMpChunk = 8;               // pairs per thread in split multi-pairings
+#ifndef BN254_LINES_CHUNK
+#define BN254_LINES_CHUNK 8
+#endif
+constexpr int kLinesChunk = BN254_LINES_CHUNK;  // table points per thread in the line-table Miller kernel
 constexpr int kLinesPerPoint = 65 + 21 + 2;  // lines of one G2 point's Miller schedule
 constexpr size_t kLineBytes = 3 * 64;     // (r0, r1, r2) Fp2 coefficients
 constexpr int kFixedWindows = 32, kFixedEntries = 255;  // fixed-base tables: 8-bit windows, digits 1..255
