@@ -171,11 +171,22 @@ BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int
       if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
       int d = ATE_NAF[i];
       g2_dbl_step_sc(T[0], sc_);
+#ifdef BN254_PAIR_ADD_LINES
+      if (d) {  // tangent and chord of this step as ONE multiplication of f (the tangent waits on the stack)
+        Fp2 park[3];
+        { Fp2 a = fp2_ld(sc_[3]), b = fp2_ld(sc_[4]), c = fp2_ld(sc_[5]); fp2_st(park[0], a); fp2_st(park[1], b); fp2_st(park[2], c); }
+        g2_add_step_sc(T[0], Q[0], d < 0, true, sc_);
+        apply_line_pair_mem(f, P[0], park, P[0], sc_ + 3, sc_);
+      } else {
+        apply_line_sc(f, P[0], sc_);
+      }
+#else
       apply_line_sc(f, P[0], sc_);
       if (d) {
         g2_add_step_sc(T[0], Q[0], d < 0, true, sc_);
         apply_line_sc(f, P[0], sc_);
       }
+#endif
     }
     G2Aff q1, q2;
     fp2_mul(q1.x, fp2_conj(Q[0].x), GAMMA1[2]);
