@@ -166,36 +166,47 @@ BN_HD void miller_loop_t(Fp12& f, const G1Aff* P, const G2Aff* Q, G2Proj* T, int
     T[j].x = Q[j].x; T[j].y = Q[j].y; T[j].z = fp2_one();
   }
   if (skip == (k >= 32 ? 0xffffffffu : ((1u << k) - 1u))) return;
-  if (KC == 1) {  // the single pairing (k_pair): every line straight from the scratch
+  if (KC >= 1 && KC <= 3) {
+    // small compile-time pair counts (k_pair, the 2-pair BLS check, 3-pair products): every line straight from the scratch.
+    // Pairing the lines was measured on them too: k_pair -2.7 % (instruction footprint), the 2-pair check neutral in
+    // time with twice the local-memory traffic (a parked line per step) -- so they keep the direct path.
     for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
       if (i != ATE_NAF_LEN - 2) fp12_sqr(f, f);
       int d = ATE_NAF[i];
-      g2_dbl_step_sc(T[0], sc_);
+#pragma unroll
+      for (int j = 0; j < KC; j++) {
+        if ((skip >> j) & 1u) continue;
+        g2_dbl_step_sc(T[j], sc_);
 #ifdef BN254_PAIR_ADD_LINES
-      if (d) {  // tangent and chord of this step as ONE multiplication of f (the tangent waits on the stack)
-        Fp2 park[3];
-        { Fp2 a = fp2_ld(sc_[3]), b = fp2_ld(sc_[4]), c = fp2_ld(sc_[5]); fp2_st(park[0], a); fp2_st(park[1], b); fp2_st(park[2], c); }
-        g2_add_step_sc(T[0], Q[0], d < 0, true, sc_);
-        apply_line_pair_mem(f, P[0], park, P[0], sc_ + 3, sc_);
-      } else {
-        apply_line_sc(f, P[0], sc_);
-      }
+        if (d) {  // tangent and chord of this step as ONE multiplication of f (the tangent waits on the stack)
+          Fp2 park[3];
+          { Fp2 a = fp2_ld(sc_[3]), b = fp2_ld(sc_[4]), c = fp2_ld(sc_[5]); fp2_st(park[0], a); fp2_st(park[1], b); fp2_st(park[2], c); }
+          g2_add_step_sc(T[j], Q[j], d < 0, true, sc_);
+          apply_line_pair_mem(f, P[j], park, P[j], sc_ + 3, sc_);
+        } else {
+          apply_line_sc(f, P[j], sc_);
+        }
 #else
-      apply_line_sc(f, P[0], sc_);
-      if (d) {
-        g2_add_step_sc(T[0], Q[0], d < 0, true, sc_);
-        apply_line_sc(f, P[0], sc_);
-      }
+        apply_line_sc(f, P[j], sc_);
+        if (d) {
+          g2_add_step_sc(T[j], Q[j], d < 0, true, sc_);
+          apply_line_sc(f, P[j], sc_);
+        }
 #endif
+      }
     }
-    G2Aff q1, q2;
-    fp2_mul(q1.x, fp2_conj(Q[0].x), GAMMA1[2]);
-    fp2_mul(q1.y, fp2_conj(Q[0].y), GAMMA1[3]);
-    q2.x = fp2_mul_fp(Q[0].x, GAMMA2[2]); q2.y = Q[0].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
-    g2_add_step_sc(T[0], q1, false, true, sc_);
-    apply_line_sc(f, P[0], sc_);
-    g2_add_step_sc(T[0], q2, false, false, sc_);
-    apply_line_sc(f, P[0], sc_);
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+      if ((skip >> j) & 1u) continue;
+      G2Aff q1, q2;
+      fp2_mul(q1.x, fp2_conj(Q[j].x), GAMMA1[2]);
+      fp2_mul(q1.y, fp2_conj(Q[j].y), GAMMA1[3]);
+      q2.x = fp2_mul_fp(Q[j].x, GAMMA2[2]); q2.y = Q[j].y;  // -pi^2(Q): xi^((p^2-1)/2) = -1
+      g2_add_step_sc(T[j], q1, false, true, sc_);
+      apply_line_sc(f, P[j], sc_);
+      g2_add_step_sc(T[j], q2, false, false, sc_);
+      apply_line_sc(f, P[j], sc_);
+    }
     return;
   }
   for (int i = ATE_NAF_LEN - 2; i >= 0; i--) {
