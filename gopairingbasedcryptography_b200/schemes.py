@@ -251,6 +251,55 @@ def waters05_setup(engine, alpha, u_exponents):
     return g1a, engine.g2_mul_base_batch(g2, _scalar_bytes(u_exponents))
 
 
+def bb04_setup(engine, alpha, u_exponents):
+    """BB04-IBE SetUp (ibe/bb04_ibe/bb04_ibe.go:109-136): g1^alpha and the n x s = 256 x 2 identity-encoding matrix
+    u[i][j] = g2^{u_ij} as ONE fixed-base G2 batch of 512 (the reference runs 512 ScalarMultiplicationBase calls).
+    u_exponents: n*s integers in row-major (i, j) order.  -> (g1_alpha (64,), u (n, s, 128)) with s = 2."""
+    g1, g2 = _generators(engine)
+    g1a = engine.g1_mul_base_batch(g1, _scalar_bytes([alpha]))[0]
+    u = engine.g2_mul_base_batch(g2, _scalar_bytes(u_exponents))
+    return g1a, u.reshape(-1, 2, G2_BYTES)
+
+
+def bb04_keygen(engine, g2_alpha, u, identity_bits, r):
+    """BB04-IBE KeyGenerate (bb04_ibe.go:138-168) for one identity: d_i = g1^{r_i} (fixed-base batch of n) and
+    d0 = g2^alpha + sum_i [r_i] u[i][a_i] -- n variable-base G2 multiplications and one segment sum instead of the
+    reference's n ScalarMultiplication + n affine Add (one inversion each).  u: (n, 2, 128); identity_bits: n values in
+    {0, 1}; r: n integers.  -> (d0 (128,), dj (n, 64))."""
+    g1, _ = _generators(engine)
+    n = len(r)
+    sel = np.ascontiguousarray(u).reshape(n, 2, G2_BYTES)[np.arange(n), np.asarray(identity_bits, dtype=np.int64)]
+    rb = _scalar_bytes(r)
+    dj = engine.g1_mul_base_batch(g1, rb)
+    terms = engine.g2_mul_batch(sel, rb)
+    prod = engine.g2_sum_batch(terms, n)
+    d0 = engine.g2_add_batch(np.ascontiguousarray(g2_alpha).reshape(1, G2_BYTES), prod)[0]
+    return d0, dj
+
+
+def bb04_encrypt_batch(engine, g1_alpha, u, identity_bits, msgs, ts):
+    """BB04-IBE Encrypt (bb04_ibe.go:170-206) of m messages to ONE identity: a_k = M_k e(g1^alpha, g2)^{t_k} (the
+    constant pairing computed once, a fixed-base GT table for the powers), b_k = g1^{t_k}, c_k[i] = [t_k] u[i][a_i]
+    (m x n variable-base G2 multiplications in one launch).  msgs: (m, 384) GT; ts: m integers.
+    -> (a (m, 384), b (m, 64), c (m, n, 128))."""
+    g1, g2 = _generators(engine)
+    m = len(ts)
+    uu = np.ascontiguousarray(u).reshape(-1, 2, G2_BYTES)
+    n = uu.shape[0]
+    sel = uu[np.arange(n), np.asarray(identity_bits, dtype=np.int64)]
+    tb = _scalar_bytes(ts)
+    e_ag = engine.pair_batch(np.ascontiguousarray(g1_alpha).reshape(1, G1_BYTES), g2.reshape(1, G2_BYTES))[0]
+    table = engine.fixed_base_create(3, e_ag)
+    try:
+        a = engine.gt_mul_batch(engine.gt_fixed_exp_batch(table, tb), np.ascontiguousarray(msgs).reshape(m, GT_BYTES))
+    finally:
+        table.close()
+    b = engine.g1_mul_base_batch(g1, tb)
+    c = engine.g2_mul_batch(np.broadcast_to(sel.reshape(1, n, G2_BYTES), (m, n, G2_BYTES)).reshape(-1, G2_BYTES),
+                            np.repeat(tb.reshape(m, 32), n, axis=0))
+    return a, b, c.reshape(m, n, G2_BYTES)
+
+
 def bsw07_keygen(engine, g2_alpha, beta, r, rj):
     """BSW07 KeyGenerate (cpabe/bsw07/bsw07_cpabe.go:96-129) for one user with len(rj) attributes, with the reference's
     stub hash H2(j) = g2: D = (g2^alpha g2^r)^{1/beta}, Dj = g2^r H2(j)^{rj}, Dj' = g2^{rj}.

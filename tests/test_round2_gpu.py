@@ -585,3 +585,39 @@ def test_group_kernels_with_shared_inversion_edge_cases(engine):
                     if (sel[i, j >> 3] >> (7 - (j & 7))) & 1:
                         acc = port.g2_add_batch(acc, U[128 * (j + 1):128 * (j + 2)], 1, 1)
                 assert (got[i] == acc).all()
+
+
+def test_bb04_setup_keygen_encrypt_decrypt_at_reference_size(engine):
+    """BB04-IBE at the reference's size (n = 256 identity bits, s = 2: the 512-point SetUp of ibe/bb04_ibe/bb04_ibe.go:109-136,
+    KeyGenerate :138-168, Encrypt :170-206, Decrypt :210-241) through the batch drivers: sampled pieces bit-exact against
+    the oracle's unfused formulas, and decrypt(encrypt(M)) == M for a batch of messages."""
+    from gopairingbasedcryptography_b200 import schemes
+
+    n, m = 256, 5
+    g1, g2 = port.generators()
+    alpha = common.scalars(1, seed=0xBB04, edges=False)[0]
+    us = common.scalars(2 * n, seed=0xBB05, edges=False)
+    g1a, u = schemes.bb04_setup(engine, alpha, us)
+    assert u.shape == (n, 2, 128)
+    assert g1a.tobytes() == port.g1_mul_base_batch(g1, sb([alpha]), 1, 1).tobytes()
+    for idx in (0, 1, 255, 511):
+        assert u.reshape(-1, 128)[idx].tobytes() == port.g2_mul_base_batch(g2, sb([us[idx]]), 1, 1).tobytes()
+    ident = np.random.default_rng(4).integers(0, 2, n)
+    g2a = port.g2_mul_base_batch(g2, sb([alpha]), 1, 1)
+    rs = common.scalars(n, seed=0xBB06, edges=False)
+    d0, dj = schemes.bb04_keygen(engine, g2a, u, ident, rs)
+    assert (dj.reshape(-1) == port.g1_mul_base_batch(g1, sb(rs), n, 4)).all()
+    acc = g2a.copy()   # the reference's chain: prod.Add(prod, [r_i] u[i][a_i]) then Add(g2^alpha, prod)
+    for i in range(n):
+        acc = port.g2_add_batch(acc, port.g2_mul_batch(u[i, ident[i]].copy().reshape(-1), sb([rs[i]]), 1, 1), 1, 1)
+    assert d0.tobytes() == acc.tobytes()
+    P, Q, _, _ = common.points(m, seed=0xBB07)
+    msgs = engine.pair_batch(P, Q)
+    ts = common.scalars(m, seed=0xBB08, edges=False)
+    a, b, c = schemes.bb04_encrypt_batch(engine, g1a, u, ident, msgs, ts)
+    k = port.gt_exp_batch(port.pair_batch(g1a, g2, 1), sb([ts[0]]), 1)
+    assert a[0].tobytes() == port.gt_mul_batch(k, msgs[0].reshape(-1), 1).tobytes()
+    assert b[0].tobytes() == port.g1_mul_base_batch(g1, sb([ts[0]]), 1, 1).tobytes()
+    assert c[m - 1, 17].tobytes() == port.g2_mul_batch(u[17, ident[17]].copy().reshape(-1), sb([ts[m - 1]]), 1, 1).tobytes()
+    back = schemes.bb04_ibe_decrypt_batch(engine, a, b, c, d0, dj)
+    assert (back == msgs).all()
