@@ -21,7 +21,40 @@ BN_HD Fp f_neg(const Fp& a) { return fp_neg(a); }
 // by-reference form (fp_mul_ool(z, a, b) with a temporary z) is avoided: nvcc 12.9 was seen to give the temporary
 // the stack slot of a still-live operand (t = sqr(x); y = mul(t, x) read x^2 for x -- hash_to_curve.cuh, found by
 // the GPU parity test against the oracle); values whose address is never taken cannot be hit by that.
-BN_NOINLINE Fp fp_inv_bv(Fp a) { return fp_inv(a); }
+// base^e for a CONSTANT 256-bit exponent (the same in every lane: no SIMT divergence) by a sliding window of four bits
+// over the odd powers base^1 .. base^15: ~254 squarings + ~51 products + 8 for the table instead of the 254 + ~127 of
+// the bit-by-bit ladder (p - 2, (p - 1)/2 and (p + 1)/4 are dense).  0^e = 0 for e > 0.  Same value, fewer products:
+// the inversions of the group kernels and the seven fixed-exponent ladders per SVDW map of hash-to-curve.
+BN_NOINLINE Fp fp_pow_win(Fp b, const uint32_t* e) {
+  Fp tab[8];
+  {
+    Fp b2 = FP_MUL(b, b);
+    tab[0] = b;
+#pragma unroll
+    for (int i = 1; i < 8; i++) tab[i] = FP_MUL(tab[i - 1], b2);
+  }
+  Fp acc = fp_one();
+  bool started = false;
+  int i = 255;
+  while (i >= 0 && !((e[i >> 5] >> (i & 31)) & 1u)) i--;
+  while (i >= 0) {
+    if (!((e[i >> 5] >> (i & 31)) & 1u)) { acc = FP_MUL(acc, acc); i--; continue; }
+    int j = i - 3 < 0 ? 0 : i - 3;
+    while (!((e[j >> 5] >> (j & 31)) & 1u)) j++;  // the window [j, i] ends in a set bit
+    int w = 0;
+    for (int t = i; t >= j; t--) w = (w << 1) | (int)((e[t >> 5] >> (t & 31)) & 1u);
+    if (started) {
+      for (int t = i; t >= j; t--) acc = FP_MUL(acc, acc);
+      acc = FP_MUL(acc, tab[w >> 1]);
+    } else {
+      acc = tab[w >> 1];
+      started = true;
+    }
+    i = j - 1;
+  }
+  return acc;
+}
+BN_NOINLINE Fp fp_inv_bv(Fp a) { return fp_pow_win(a, FP_PM2); }  // a^(p-2); inv(0) = 0 like gnark's Inverse
 BN_HD Fp f_mul(const Fp& a, const Fp& b) { return FP_MUL(a, b); }
 BN_HD Fp f_sqr(const Fp& a) { return FP_MUL(a, a); }
 BN_HD Fp f_inv(const Fp& a) { return fp_inv_bv(a); }

@@ -117,15 +117,7 @@ BN_HD void hash_to_field(Fp* u, const uint8_t* msg, size_t msg_len, const uint8_
 }
 
 // ---- field helpers: fixed-exponent powers, squareness, square roots, sgn0 -----------------------------------
-BN_NOINLINE Fp fp_pow_fixed(Fp base, const uint32_t* e) {  // base^e, e = 8 constant limbs
-  Fp acc = fp_one();
-  bool started = false;
-  for (int i = 255; i >= 0; i--) {
-    if (started) acc = h_sqr(acc);
-    if ((e[i >> 5] >> (i & 31)) & 1u) { if (started) acc = h_mul(acc, base); else { acc = base; started = true; } }
-  }
-  return acc;
-}
+BN_HD Fp fp_pow_fixed(const Fp& base, const uint32_t* e) { return fp_pow_win(base, e); }  // base^e, e = 8 constant limbs (curve.cuh: sliding window)
 BN_HD bool fp_is_square(const Fp& a) {  // Euler: a^((p-1)/2) is 1 (or a = 0)
   Fp t = fp_pow_fixed(a, FP_PM1H);
   return fp_is_zero(a) || fp_eq(t, fp_one());
