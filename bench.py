@@ -31,10 +31,10 @@ METRIC = "bn254_pairings_per_sec"
 UNIT = "pairings/s"
 MACS_PER_PAIRING = 2.081e6  # SURVEY.md §8d Model-M: 15300 Fp-mul equivalents x 136 limb-MACs
 BYTES_PER_PAIRING = 64 + 128 + 384
-# dram__bytes_read.sum + dram__bytes_write.sum of k_pair from the committed ncu --set full capture
-# (profiles/r1/ncu_k_pair_final_r1_summary.txt: 3.46 + 21.17 GB for 2^18 pairings): what is left of the
-# local-memory stack traffic after the staged tower (was 188.5 GB / 2^18 before it), still ~160x the algorithmic 576 B.
-NCU_DRAM_BYTES_PER_PAIRING = (3.463922e9 + 21.169908e9) / (1 << 18)
+# dram__bytes_read.sum + dram__bytes_write.sum of k_pair from the committed ncu --set full capture of round 2
+# (profiles/r2/ncu_k_pair_r2_summary.txt, 2^18 pairings): what is left of the local-memory stack traffic after the staged
+# tower (188.5 GB / 2^18 before it), still ~160x the algorithmic 576 B per pairing.
+NCU_DRAM_BYTES_PER_PAIRING = (3.396864e9 + 21.053526e9) / (1 << 18)
 
 
 def host_threads():
@@ -351,7 +351,7 @@ def main():
                          "kernel": "k_pair", "kernel_ms": kernel_ms,
                          "note": "algorithmic 2.081e6 32x32->64 MACs per pairing (SURVEY 8d) x %d per k_pair launch / %.1f ms (timed alone on a thread-kernel context); "
                                  "peak = IMAD.WIDE rate %s; algorithmic HBM: %.2f GB/s of %.0f measured (not the bound); traffic = DRAM bytes per launch "
-                                 "scaled from the ncu capture at 2^18 (local-memory stack spill, see profiles/r1)"
+                                 "scaled from the ncu capture at 2^18 (local-memory stack spill, see profiles/r2)"
                                  % (n, kernel_ms, peak_how, BYTES_PER_PAIRING * n / (kernel_ms * 1e-3) / 1e9, 6472.1)},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d pairings on %d threads, C restatement of gnark (gnark itself cannot run here: no Go)" % (sample, threads)},
