@@ -42,6 +42,7 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "fe_tinline12": DEFAULT, "fe_tinline15": DEFAULT,
     "lines16": DEFAULT + ["-DBN254_LINES_CHUNK=16"], "lines12": DEFAULT + ["-DBN254_LINES_CHUNK=12"],
     "pair_add_lines": {"k_pairing": DEFAULT + ["-DBN254_PAIR_ADD_LINES"]},
+    "lines_global": {"k_pairing": DEFAULT + ["-DBN254_LINES_TMA=0"]},  # line tables read straight from global memory (A/B of the TMA ring)
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
 }
 # per-unit additions on top of the variant's flags

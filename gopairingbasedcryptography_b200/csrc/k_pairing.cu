@@ -196,9 +196,71 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_g2_lines(const voi
   qskip[j] = inf ? 1 : 0;
   if (!inf) g2_precompute_lines(q, table + j * (size_t)kLinesPerPoint * 3);
 }
+#ifndef BN254_LINES_TMA
+#define BN254_LINES_TMA 1
+#endif
+#if BN254_LINES_TMA && defined(BN254_CTA_LOCKSTEP)
+// Line coefficients through shared memory (north_star: the Miller loop "reads precomputed G2 line coefficients for the
+// schemes' fixed public-parameter G2 points from shared memory").  Every thread of a CTA walks the SAME table lines in
+// the same order, so ONE thread fetches each couple of lines (2 x 192 B, contiguous per line) with the bulk-copy engine
+// (cp.async.bulk = 1-D TMA) into a two-deep ring in shared memory, one application ahead of its use, and signals an
+// mbarrier with the byte count; the 128 threads then read the coefficients as shared-memory broadcasts.  Fetch q of a
+// CTA lands in buffer q & 1 and completes phase (q >> 1) & 1 of that buffer's mbarrier.  The ring holds 768 B per CTA:
+// 3 CTAs x (74 KB scratch + 1 KB reserved + ring) still fit the 228 KB of an SM.  Only CTAs running in lockstep (full,
+// no pair skipped -- the CTA barrier is what makes a shared ring safe) take this path; ragged CTAs read the table directly.
+__shared__ alignas(128) Fp2 bn_line_ring[2][6];
+__shared__ alignas(8) unsigned long long bn_line_bar[2];
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void line_ring_init() {  // one thread; the caller separates it from the first fetch by a CTA barrier
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bn_line_bar[0])) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bn_line_bar[1])) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// fetch q = schedule position q / F, couple q % F of the chunk's `cnt` table points (F couples per position, the last one
+// a single line when cnt is odd)
+__device__ __forceinline__ void line_ring_fetch(const Fp2* table, int first, int cnt, int q) {
+  const int F = (cnt + 1) >> 1, s = q / F, ja = 2 * (q - s * F);
+  const int nl = ja + 1 < cnt ? 2 : 1;
+  const uint32_t bar = smem_addr(&bn_line_bar[q & 1]);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nl * (int)launch::kLineBytes) : "memory");
+  for (int l = 0; l < nl; l++) {
+    const Fp2* src = table + ((size_t)(first + ja + l) * kLinesPerPoint + s) * 3;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(&bn_line_ring[q & 1][3 * l])), "l"(src), "r"((int)launch::kLineBytes), "r"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ void line_ring_wait(int q) {
+  const uint32_t bar = smem_addr(&bn_line_bar[q & 1]), parity = (uint32_t)(q >> 1) & 1u;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LINE_RING_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LINE_RING_DONE;\n"
+      "bra LINE_RING_WAIT;\n"
+      "LINE_RING_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// One schedule position of the line-table Miller loop out of the ring (lockstep CTAs: every pair live).
+__device__ void miller_lines_step_ring(Fp12& f, const G1Aff* p, const Fp2* table, int first, int cnt, int& q, int nfetch, Fp2* sc) {
+  for (int j = 0; j < cnt; j += 2, q++) {
+    __syncthreads();  // every thread is done with the buffer the next fetch overwrites (it was read one application ago)
+    if (threadIdx.x == 0 && q + 1 < nfetch) line_ring_fetch(table, first, cnt, q + 1);
+    line_ring_wait(q);
+    const Fp2* L = bn_line_ring[q & 1];
+    if (j + 1 < cnt) apply_line_pair_mem(f, p[j], L, p[j + 1], L + 3, sc);
+    else apply_line_mem(f, p[j], L, sc);
+  }
+}
+#define BN254_LINES_RING 1
+#else
+#define BN254_LINES_RING 0
+#endif
 // Partial Miller products from line tables.  Grid: x = blocks of kBlock items, y = groups of kMpChunk pairs.
-// Every thread of a CTA walks the SAME pairs, so each line read is one warp-uniform (broadcast) load of 192 B
-// served by L1; P[i][j] is the only per-thread operand.  out: partial[i * nchunks + chunk].
+// Every thread of a CTA walks the SAME pairs: lockstep CTAs read each line out of the shared-memory ring above (one
+// bulk copy per CTA), the others with warp-uniform (broadcast) loads of 192 B; P[i][j] is the only per-thread operand.
+// out: partial[i * nchunks + chunk].
 __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const void* P, const Fp2* __restrict__ table, const uint8_t* __restrict__ qskip,
                                                                           size_t n, int m, int nchunks, void* partial) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,11 +280,26 @@ __global__ void __launch_bounds__(kBlock, BN254_MIN_BLOCKS) k_miller_lines(const
   fp12_set_one(f);
   BN_SCRATCH_DECL
   int s = 0;
+#if BN254_LINES_RING
+  const bool ring = cta_lockstep_on();  // CTA-uniform
+  const int nfetch = kLinesPerPoint * ((cnt + 1) >> 1);
+  int q = 0;
+  if (ring) {
+    if (threadIdx.x == 0) line_ring_init();
+    __syncthreads();
+    if (threadIdx.x == 0) line_ring_fetch(table, first, cnt, 0);
+  }
+#endif
   for (int it = ATE_NAF_LEN - 2; it >= -2; it--) {
     // it >= 0: tangent (+ chord if the digit is non-zero); it == -1, -2: the two Frobenius lines
     if (it >= 0 && it != ATE_NAF_LEN - 2) fp12_sqr(f, f);
     int reps = (it >= 0 && ATE_NAF[it]) ? 2 : 1;
-    for (int r = 0; r < reps; r++, s++) miller_lines_step(f, p, table, first, cnt, skip, s, sc_);
+    for (int r = 0; r < reps; r++, s++) {
+#if BN254_LINES_RING
+      if (ring) { miller_lines_step_ring(f, p, table, first, cnt, q, nfetch, sc_); continue; }
+#endif
+      miller_lines_step(f, p, table, first, cnt, skip, s, sc_);
+    }
   }
   store_struct(partial, i * (size_t)nchunks + ci, f);
 }

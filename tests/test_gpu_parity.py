@@ -479,6 +479,23 @@ def test_precomputed_g2_line_tables(engine):
     assert (a == b).all()
 
 
+def test_line_tables_through_the_shared_memory_ring(engine):
+    """Full, skip-free CTAs of the line-table Miller kernel fetch every couple of lines with one bulk copy into a
+    shared-memory ring (k_pairing.cu); chunk sizes 8 + 1 (single lines only), 8 + 8 + 5 (odd tail) and 2 (one couple per
+    position), full CTAs next to a ragged one -- all bit-identical to the generic multi-pairing and to the oracle."""
+    for n, m in ((259, 9), (384, 2), (128, 21)):
+        _, Q, _, _ = common.points(m, seed=511 + m, threads=8)
+        P, _, _, _ = common.points(n * m, seed=512 + m, threads=8)
+        lines = engine.g2_lines_create(Q)
+        got = engine.multi_pair_lines_batch(P, lines)
+        assert (got == engine.multi_pair_batch(P, np.tile(Q, n), m)).all()
+        k = 16  # oracle on the first and last items
+        for lo in (0, n - k):
+            want = port.multi_pair_batch(P[64 * m * lo:64 * m * (lo + k)], np.tile(Q, k), k, m, 8)
+            assert (got[lo:lo + k].reshape(-1) == want).all()
+        lines.close()
+
+
 def test_gt_fixed_base_table(engine):
     """>= 4096 exponents on one base use the cached 32x255 GT window table (built with the generic ladder, so it is
     valid for ANY Fp12 base, not only pairing outputs)."""
