@@ -36,6 +36,8 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "mulx_seq": {"k_pairing": DEFAULT + ["-DBN254_MULX_SEQ", "-DBN254_CYC_LATE_LOADS"]},
     "wvm_ahead2": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=2"]},
     "wvm_ahead3": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=3"]},
+    "wvm_ahead4": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=4"]},
+    "wvm_ahead1": {"k_wvm": DEFAULT + ["-DWVM_AHEAD=1"]},
     "wvm_onepass": {"k_wvm": DEFAULT + ["-DWVM_FINISH_ONEPASS=1"]},
     "wvm_linbatch": {"k_wvm": DEFAULT + ["-DWVM_LIN_BATCH=1"]},
     # program-shape experiments: built after `WVM_TINLINE_FINALEXP=<n> python csrc/wvmgen.py` with BN254_KEEP_GENERATED=1

@@ -230,9 +230,34 @@ BN_HD bool exec_op(const Fp* slots, const uint4& w0, const uint4& w1, unsigned n
 #if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
 __device__ unsigned long long wvm_prof[8];  // cycles and rounds per op class (debug build: profiles/r2/wvm_round_costs.json)
 #endif
+BN_HD void run_round(Fp* slots, const uint4& w0, const uint4& w1, int lane) {
+#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
+  long long t0_ = clock64();
+  unsigned cls_ = __reduce_max_sync(0xffffffffu, w0.x & 3u);
+#endif
+  unsigned h = w0.x & 0xFFFFu;
+  unsigned nterms = (h & 3u) == OP_LIN ? (h >> 12) : 0u;
+#if defined(__CUDACC__)
+  unsigned nmax = warp_max(nterms);
+#else
+  unsigned nmax = 15;
+#endif
+  unsigned dst = 0;
+  Fp out;
+  bool st = exec_op(slots, w0, w1, nmax, dst, out);
+  if (st) st_slot(slots, dst, out);
+  round_sync();
+#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
+  if (lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) { wvm_prof[cls_] += (unsigned long long)(clock64() - t0_); wvm_prof[4 + cls_] += 1; }
+#endif
+  (void)lane;
+}
 BN_HD void run(Fp* slots, const uint4* __restrict__ prog, int rounds, int lane) {
-  // the program words of round r + kAhead are requested in round r: a LIN round is shorter than an L2 round trip, and a
-  // one-round prefetch left every LIN round waiting ~500 cycles for its own instructions (measured)
+  // The program words of round r + kAhead are requested in round r, into a ring of kAhead register pairs that is indexed
+  // STATICALLY (the round loop is unrolled by kAhead, no register shifting).  kAhead = 1 is the measured best: a lone warp
+  // is bound by its ~375 instructions per round at ~3.3 cycles each, not by the fetch of its program words
+  // (long_scoreboard 4.8 % of its stall samples, profiles/r2/ncu_k_wvm_pair1_lone_warp_summary.txt); rings 2 / 3 / 4
+  // rounds deep measure 1.34 / 1.41 / 1.44 ms for a 1-element Pair against 1.31 ms (profiles/r2/wvm_prefetch_ring_ab.jsonl).
   constexpr int kAhead = WVM_AHEAD;
   const uint4* p = prog + (size_t)lane * 2;
   uint4 q0[kAhead], q1[kAhead];
@@ -241,33 +266,17 @@ BN_HD void run(Fp* slots, const uint4* __restrict__ prog, int rounds, int lane) 
     int rr = k < rounds ? k : rounds - 1;
     q0[k] = p[(size_t)rr * kLanes * 2]; q1[k] = p[(size_t)rr * kLanes * 2 + 1];
   }
-  for (int r = 0; r < rounds; r++) {
-    uint4 w0 = q0[0], w1 = q1[0];
+  for (int r0 = 0; r0 < rounds; r0 += kAhead) {
 #pragma unroll
-    for (int k = 0; k + 1 < kAhead; k++) { q0[k] = q0[k + 1]; q1[k] = q1[k + 1]; }
-    {
-      int rr = r + kAhead < rounds ? r + kAhead : rounds - 1;
-      q0[kAhead - 1] = p[(size_t)rr * kLanes * 2]; q1[kAhead - 1] = p[(size_t)rr * kLanes * 2 + 1];
+    for (int k = 0; k < kAhead; k++) {
+      const int r = r0 + k;
+      if (r < rounds) {  // warp-uniform
+        const uint4 w0 = q0[k], w1 = q1[k];
+        const int rr = r + kAhead < rounds ? r + kAhead : rounds - 1;
+        q0[k] = p[(size_t)rr * kLanes * 2]; q1[k] = p[(size_t)rr * kLanes * 2 + 1];
+        run_round(slots, w0, w1, lane);
+      }
     }
-#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
-    long long t0_ = clock64();
-    unsigned cls_ = __reduce_max_sync(0xffffffffu, w0.x & 3u);
-#endif
-    unsigned h = w0.x & 0xFFFFu;
-    unsigned nterms = (h & 3u) == OP_LIN ? (h >> 12) : 0u;
-#if defined(__CUDACC__)
-    unsigned nmax = warp_max(nterms);
-#else
-    unsigned nmax = 15;
-#endif
-    unsigned dst = 0;
-    Fp out;
-    bool st = exec_op(slots, w0, w1, nmax, dst, out);
-    if (st) st_slot(slots, dst, out);
-    round_sync();
-#if defined(BN254_WVM_PROFILE) && defined(__CUDACC__)
-    if (lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) { wvm_prof[cls_] += (unsigned long long)(clock64() - t0_); wvm_prof[4 + cls_] += 1; }
-#endif
   }
 }
 
