@@ -356,36 +356,78 @@ def afp25_batch_setup(engine, tau_powers_g1, identities_fr):
     return engine.msm_table_create(1, pts), engine.fr_poly_from_roots(ids)
 
 
+class _Afp25Workspace:
+    """Reusable buffers of afp25_decrypt_batch for one (ciphertexts per call, identities per batch) shape: ONE page-locked
+    staging area for everything that goes up (ids | C1 | C2 | D | sk), its device image, every intermediate, and a
+    page-locked area for the messages coming down -- a call then costs one H2D copy, the kernels and one D2H copy, with no
+    allocation and no per-argument copies (six separate uploads and five allocations were ~0.2 ms of a 2.6 ms batch)."""
+
+    def __init__(self, torch, dev, n, B):
+        self.n, self.B = n, B
+        self.o_ids, self.o_c1, self.o_c2 = 0, n * 32, n * 32 + n * 3 * G2_BYTES
+        self.o_d = self.o_c2 + n * GT_BYTES
+        self.o_sk = self.o_d + G1_BYTES
+        total = self.o_sk + G1_BYTES
+        self.h_in = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self.h_np = self.h_in.numpy()
+        self.d_in = torch.empty(total, dtype=torch.uint8, device=dev)
+        self.q = torch.empty((n, B, 32), dtype=torch.uint8, device=dev)
+        self.pi = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
+        self.P = torch.empty((n, 3, G1_BYTES), dtype=torch.uint8, device=dev)
+        self.prod = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        self.out = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
+        self.h_out = torch.empty((n, GT_BYTES), dtype=torch.uint8).pin_memory()
+        self.f_key, self.d_f = None, None
+        import threading
+
+        self.lock = threading.Lock()  # the buffers serve one call at a time (callers sharing a table handle queue up here)
+
+
 def afp25_decrypt_batch(engine, table, f_coeffs, ids_fr, c1, c2, d, sk):
     """AFP25 batch decryption (bibe/afp25_bibe/afp25_bibe.go:369-418) of n ciphertexts for n identities of one batch:
         q_id(X) = f(X) / (X - id)            O(B) synthetic division per identity (reference: O(B^2) re-expansion)
         pi_id   = sum_k [q_k] T_k            one shared-point MSM over the table (reference: B mults + B affine adds)
         M       = C2 / ( e(D, C1[0]) e(pi, C1[1]) e(sk, C1[2]) )   ONE 3-pair product, one final exponentiation
-    All stages run back to back on one stream; only ids / ciphertexts go up and the n messages come down.
-    ids_fr: (n, 32) fr.Element; c1: (n, 3, 128); c2: (n, 384); d, sk: (64,).  Returns (n, 384)."""
+    All stages run back to back on one stream; only ids / ciphertexts go up (one packed page-locked copy) and the n
+    messages come down; buffers are cached per (n, B) on the table handle, f(X) stays on the device while the same
+    coefficient array is passed.  ids_fr: (n, 32) fr.Element; c1: (n, 3, 128); c2: (n, 384); d, sk: (64,).
+    Returns (n, 384)."""
     torch = _torch()
     dev = torch.device("cuda", engine.device)
     ids = np.ascontiguousarray(ids_fr).reshape(-1, 32)
     n, B = ids.shape[0], table.len
     with torch.cuda.device(dev):
-        s = torch.cuda.current_stream().cuda_stream
-        d_f, d_ids = _up(f_coeffs, torch, dev), _up(ids, torch, dev)
-        d_c1, d_c2 = _up(c1, torch, dev), _up(c2, torch, dev)
-        # P rows = (D, pi_v, sk): D and sk broadcast on the host side of the upload (2 x 64 B per row)
-        P = torch.empty((n, 3, G1_BYTES), dtype=torch.uint8, device=dev)
-        P[:, 0] = _up(d, torch, dev)
-        P[:, 2] = _up(sk, torch, dev)
-        q = torch.empty((n, B, 32), dtype=torch.uint8, device=dev)
-        pi = torch.empty((n, G1_BYTES), dtype=torch.uint8, device=dev)
-        engine.dev("fr_quotient_coeffs_dev", d_f.data_ptr(), B, d_ids.data_ptr(), n, q.data_ptr(), stream=s)
-        engine.dev("msm_batch_dev", table, q.data_ptr(), n, pi.data_ptr(), stream=s)
-        P[:, 1] = pi
-        prod = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
-        engine.dev("multi_pair_batch_dev", P.data_ptr(), d_c1.data_ptr(), n, 3, prod.data_ptr(), stream=s)
-        out = torch.empty((n, GT_BYTES), dtype=torch.uint8, device=dev)
-        # the divisor is a pairing product: C2 / prod = C2 * conj(prod) (bn254_gt_cyclo_div_batch), no Fp12 inversion
-        engine.dev("gt_cyclo_div_batch_dev", d_c2.data_ptr(), 1, prod.data_ptr(), 1, n, out.data_ptr(), stream=s)
-        return out.cpu().numpy()
+        cache = table.__dict__.setdefault("_afp25_ws", {})
+        ws = cache.get(n)
+        if ws is None:
+            ws = cache[n] = _Afp25Workspace(torch, dev, n, B)
+        with ws.lock:
+            stream = torch.cuda.current_stream()
+            s = stream.cuda_stream
+            f_np = np.ascontiguousarray(f_coeffs).reshape(-1)
+            f_key = (f_np.ctypes.data, f_np.size, bytes(f_np[:64].view(np.uint8)), bytes(f_np[-64:].view(np.uint8)))
+            if ws.f_key != f_key:  # f(X) belongs to the identity batch: uploaded once per coefficient array
+                ws.d_f, ws.f_key = _up(f_np, torch, dev), f_key
+            h = ws.h_np
+            h[ws.o_ids:ws.o_c1] = ids.reshape(-1).view(np.uint8)
+            h[ws.o_c1:ws.o_c2] = np.ascontiguousarray(c1).reshape(-1).view(np.uint8)
+            h[ws.o_c2:ws.o_d] = np.ascontiguousarray(c2).reshape(-1).view(np.uint8)
+            h[ws.o_d:ws.o_sk] = np.ascontiguousarray(d).reshape(-1).view(np.uint8)
+            h[ws.o_sk:] = np.ascontiguousarray(sk).reshape(-1).view(np.uint8)
+            ws.d_in.copy_(ws.h_in, non_blocking=True)
+            base = ws.d_in.data_ptr()
+            # P rows = (D, pi_v, sk): D and sk broadcast on the device
+            ws.P[:, 0] = ws.d_in[ws.o_d:ws.o_sk]
+            ws.P[:, 2] = ws.d_in[ws.o_sk:]
+            engine.dev("fr_quotient_coeffs_dev", ws.d_f.data_ptr(), B, base + ws.o_ids, n, ws.q.data_ptr(), stream=s)
+            engine.dev("msm_batch_dev", table, ws.q.data_ptr(), n, ws.pi.data_ptr(), stream=s)
+            ws.P[:, 1] = ws.pi
+            engine.dev("multi_pair_batch_dev", ws.P.data_ptr(), base + ws.o_c1, n, 3, ws.prod.data_ptr(), stream=s)
+            # the divisor is a pairing product: C2 / prod = C2 * conj(prod) (bn254_gt_cyclo_div_batch), no Fp12 inversion
+            engine.dev("gt_cyclo_div_batch_dev", base + ws.o_c2, 1, ws.prod.data_ptr(), 1, n, ws.out.data_ptr(), stream=s)
+            ws.h_out.copy_(ws.out, non_blocking=True)
+            stream.synchronize()
+            return ws.h_out.numpy().copy()
 
 
 def bsw07_decrypt_batch_dev(engine, cy, cy_prime, lines, c, c_tilde, deltas=None):
