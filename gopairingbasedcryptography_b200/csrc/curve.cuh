@@ -24,7 +24,7 @@ BN_HD Fp f_neg(const Fp& a) { return fp_neg(a); }
 // base^e for a CONSTANT 256-bit exponent (the same in every lane: no SIMT divergence) by a sliding window of four bits
 // over the odd powers base^1 .. base^15: ~254 squarings + ~51 products + 8 for the table instead of the 254 + ~127 of
 // the bit-by-bit ladder (p - 2, (p - 1)/2 and (p + 1)/4 are dense).  0^e = 0 for e > 0.  Same value, fewer products:
-// the inversions of the group kernels and the seven fixed-exponent ladders per SVDW map of hash-to-curve.
+// the inversions of the group kernels and the fixed-exponent ladders of hash-to-curve (four per G1 map, five per G2 map).
 BN_NOINLINE Fp fp_pow_win(Fp b, const uint32_t* e) {
   Fp tab[8];
   {

@@ -292,6 +292,7 @@ def main():
     w("BN_CONST Fp CURVE_B = %s;" % fp_init(3))
     w("BN_CONST uint32_t FP_PM1H[8] = {%s};  // (p-1)/2, Euler criterion" % limbs32((P - 1) // 2))
     w("BN_CONST uint32_t FP_PP1Q[8] = {%s};  // (p+1)/4, square root (p = 3 mod 4)" % limbs32((P + 1) // 4))
+    w("BN_CONST uint32_t FP_PM3Q[8] = {%s};  // (p-3)/4: c^((p-3)/4) gives a square root (times c) and its inverse at once" % limbs32((P - 3) // 4))
     w("BN_CONST Fp FP_HALF = %s;" % fp_init(pow(2, -1, P)))
     # hash_to_field: a 48-byte big-endian integer c2 2^256 + c1 2^128 + c0 enters Montgomery form as
     # mont(c0, R^2) + mont(c1, 2^128 R^2) + mont(c2, 2^256 R^2)  (raw limbs, every c_i < 2^128 < p)

@@ -130,6 +130,13 @@ BN_HD uint32_t fp2_sgn0(const Fp2& a) {
   uint32_t s0 = fp_sgn0(a.a0), z0 = fp_is_zero(a.a0) ? 1u : 0u;
   return s0 | (z0 & fp_sgn0(a.a1));
 }
+BN_HD Fp fp_sel(bool c, const Fp& a, const Fp& b) {  // c ? a : b, as a mask blend
+  uint32_t m = 0u - (c ? 1u : 0u);
+  Fp z;
+#pragma unroll
+  for (int i = 0; i < 8; i++) z.l[i] = (a.l[i] & m) | (b.l[i] & ~m);
+  return z;
+}
 // some square root of a square in Fp2 (complex method); which of the two is irrelevant, the map fixes the sign
 BN_NOINLINE Fp2 fp2_sqrt(Fp2 a) {
   Fp2 r;
@@ -140,21 +147,23 @@ BN_NOINLINE Fp2 fp2_sqrt(Fp2 a) {
     r.a1 = sq ? fp_zero() : t;
     return r;
   }
+  // Complex method with ONE more ladder instead of three (an Euler test, a square root and an inversion).  With
+  // n = sqrt(norm a) the candidates c+- = (a0 +- n) / 2 satisfy c+ c- = -a1^2 / 4, so exactly one of them is a square
+  // (p = 3 mod 4: -1 is a non-residue).  t = c+^((p-3)/4) and x = t c+ = c+^((p+1)/4) give t x = c+^((p-1)/2) = +-1:
+  //   c+ square:      x^2 = c+,   1/x = t    ->  root (x, a1 / (2 x)) = (x, a1 t / 2)           (the previous code's value)
+  //   c+ non-residue: x^2 = -c+,  1/x = -t,  c- = a1^2 / (4 x^2)  ->  root (a1 / (2 x), x) = (-a1 t / 2, x)
+  // In the second case this may be the negative of the root the three-ladder code returned; the only caller fixes the
+  // sign by sgn0 right after (map_to_curve_g2), so the mapped point is bit-identical.
   Fp n = fp_sqrt(fp2_norm(a));
   Fp half = FP_HALF;
-  Fp x2 = h_mul(fp_add(a.a0, n), half);
-  if (!fp_is_square(x2)) x2 = h_mul(fp_sub(a.a0, n), half);
-  Fp x = fp_sqrt(x2);
-  r.a0 = x;
-  r.a1 = h_mul(a.a1, h_inv(fp_dbl(x)));
+  Fp c = h_mul(fp_add(a.a0, n), half);
+  Fp t = fp_pow_fixed(c, FP_PM3Q);
+  Fp x = h_mul(t, c);
+  bool sq = fp_eq(h_sqr(x), c);
+  Fp a1t = h_mul(a.a1, h_mul(t, half));
+  r.a0 = fp_sel(sq, x, fp_neg(a1t));
+  r.a1 = fp_sel(sq, a1t, x);
   return r;
-}
-BN_HD Fp fp_sel(bool c, const Fp& a, const Fp& b) {  // c ? a : b, as a mask blend
-  uint32_t m = 0u - (c ? 1u : 0u);
-  Fp z;
-#pragma unroll
-  for (int i = 0; i < 8; i++) z.l[i] = (a.l[i] & m) | (b.l[i] & ~m);
-  return z;
 }
 BN_HD Fp2 fp2_sel(bool c, const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sel(c, a.a0, b.a0); z.a1 = fp_sel(c, a.a1, b.a1); return z; }
 

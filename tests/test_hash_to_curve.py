@@ -89,6 +89,16 @@ def test_device_code_on_host_matches_golden(emu, vectors):  # noqa: F811
         assert [o.fp_from_mont_bytes(f[32 * i:32 * i + 32]) for i in range(4)] == h.hash_to_fp(b"message", dst, 4)
 
 
+def test_device_g2_square_root_takes_both_branches(emu):  # noqa: F811
+    """The Fp2 square root of the device code derives the root from ONE ladder c^((p-3)/4) whichever of its two candidates
+    is the square (hash_to_curve.cuh fp2_sqrt): 40 more messages against the definitional oracle -- both branches of both
+    SVDW maps are taken many times over (each is a coin flip per map)."""
+    dst = h.DST_BYTES_G2
+    for i in range(40):
+        msg = b"square-root branch %d" % i
+        assert _emu(emu, "emu_hash_to_g2", msg, dst, 128) == o.g2_to_bytes(h.hash_to_g2(msg, dst)), i
+
+
 @pytest.mark.gpu
 def test_gpu_hash_to_curve_vs_oracle(engine, vectors):
     for grp, fn in (("g1", engine.hash_to_g1_batch), ("g2", engine.hash_to_g2_batch)):
