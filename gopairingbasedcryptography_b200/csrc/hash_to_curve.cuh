@@ -168,13 +168,19 @@ BN_NOINLINE Fp2 fp2_sqrt(Fp2 a) {
 BN_HD Fp2 fp2_sel(bool c, const Fp2& a, const Fp2& b) { Fp2 z; z.a0 = fp_sel(c, a.a0, b.a0); z.a1 = fp_sel(c, a.a1, b.a1); return z; }
 
 // ---- SVDW maps (steps as in RFC 9380 F.1 / gnark MapToCurve1, MapToCurve2) ------------------------------------
+// The map in two halves around its one inversion, so that the two maps of a message can SHARE it (Montgomery's trick:
+// 1 / a and 1 / b from one inversion of a b and three products -- one fixed-exponent ladder less per message on the
+// one-thread-per-message kernels).  inv0 semantics kept: a zero operand gets the inverse 0 and does not disturb the other.
 BN_HD Fp g1_curve_rhs(const Fp& x) { Fp b = CURVE_B; return fp_add(h_mul(h_sqr(x), x), b); }
-BN_NOINLINE void map_to_curve_g1(G1Aff& out, const Fp& u) {
-  Fp c1 = H2C_G1_C1, c2 = H2C_G1_C2, c3 = H2C_G1_C3, c4 = H2C_G1_C4, Z = H2C_G1_Z, one = fp_one();
-  Fp tv1 = h_mul(h_sqr(u), c1);
-  Fp tv2 = fp_add(one, tv1);
-  tv1 = fp_sub(one, tv1);
-  Fp tv3 = h_inv(h_mul(tv1, tv2));  // inv0
+BN_HD void svdw_pre_g1(Fp& tv1, Fp& tv2, Fp& prod, const Fp& u) {
+  Fp c1 = H2C_G1_C1, one = fp_one();
+  Fp t = h_mul(h_sqr(u), c1);
+  tv2 = fp_add(one, t);
+  tv1 = fp_sub(one, t);
+  prod = h_mul(tv1, tv2);
+}
+BN_NOINLINE void svdw_post_g1(G1Aff& out, const Fp& u, const Fp& tv1, const Fp& tv2, const Fp& tv3) {
+  Fp c2 = H2C_G1_C2, c3 = H2C_G1_C3, c4 = H2C_G1_C4, Z = H2C_G1_Z;
   Fp tv4 = h_mul(h_mul(h_mul(u, tv1), tv3), c3);
   Fp x1 = fp_sub(c2, tv4);
   bool e1 = fp_is_square(g1_curve_rhs(x1));
@@ -188,13 +194,33 @@ BN_NOINLINE void map_to_curve_g1(G1Aff& out, const Fp& u) {
   if (fp_sgn0(u) != fp_sgn0(y)) y = fp_neg(y);
   out.x = x; out.y = y;
 }
+BN_NOINLINE void map_to_curve_g1(G1Aff& out, const Fp& u) {
+  Fp tv1, tv2, prod;
+  svdw_pre_g1(tv1, tv2, prod, u);
+  svdw_post_g1(out, u, tv1, tv2, h_inv(prod));  // inv0
+}
+// both maps of one message, one inversion
+BN_HD void map_to_curve_g1_x2(G1Aff& q0, G1Aff& q1, const Fp& u0, const Fp& u1) {
+  Fp a1, a2, pa, b1, b2, pb, one = fp_one();
+  svdw_pre_g1(a1, a2, pa, u0);
+  svdw_pre_g1(b1, b2, pb, u1);
+  bool za = fp_is_zero(pa), zb = fp_is_zero(pb);
+  Fp sa = fp_sel(za, one, pa), sb = fp_sel(zb, one, pb);
+  Fp inv = h_inv(h_mul(sa, sb));
+  Fp ia = fp_sel(za, fp_zero(), h_mul(inv, sb)), ib = fp_sel(zb, fp_zero(), h_mul(inv, sa));
+  svdw_post_g1(q0, u0, a1, a2, ia);
+  svdw_post_g1(q1, u1, b1, b2, ib);
+}
 BN_HD Fp2 g2_curve_rhs(const Fp2& x) { Fp2 b = TWIST_B; return fp2_add_i(h_mul(h_sqr(x), x), b); }
-BN_NOINLINE void map_to_curve_g2(G2Aff& out, const Fp2& u) {
-  Fp2 c1 = H2C_G2_C1, c2 = H2C_G2_C2, c3 = H2C_G2_C3, c4 = H2C_G2_C4, Z = H2C_G2_Z, one = fp2_one();
-  Fp2 tv1 = h_mul(h_sqr(u), c1);
-  Fp2 tv2 = fp2_add_i(one, tv1);
-  tv1 = fp2_sub_i(one, tv1);
-  Fp2 tv3 = h_inv(h_mul(tv1, tv2));  // inv0 (fp_inv(0) = 0)
+BN_HD void svdw_pre_g2(Fp2& tv1, Fp2& tv2, Fp2& prod, const Fp2& u) {
+  Fp2 c1 = H2C_G2_C1, one = fp2_one();
+  Fp2 t = h_mul(h_sqr(u), c1);
+  tv2 = fp2_add_i(one, t);
+  tv1 = fp2_sub_i(one, t);
+  prod = h_mul(tv1, tv2);
+}
+BN_NOINLINE void svdw_post_g2(G2Aff& out, const Fp2& u, const Fp2& tv1, const Fp2& tv2, const Fp2& tv3) {
+  Fp2 c2 = H2C_G2_C2, c3 = H2C_G2_C3, c4 = H2C_G2_C4, Z = H2C_G2_Z;
   Fp2 tv4 = h_mul(h_mul(h_mul(u, tv1), tv3), c3);
   Fp2 x1 = fp2_sub_i(c2, tv4);
   bool e1 = fp2_is_square(g2_curve_rhs(x1));
@@ -207,6 +233,22 @@ BN_NOINLINE void map_to_curve_g2(G2Aff& out, const Fp2& u) {
   Fp2 y = fp2_sqrt(g2_curve_rhs(x));
   if (fp2_sgn0(u) != fp2_sgn0(y)) y = fp2_neg_i(y);
   out.x = x; out.y = y;
+}
+BN_NOINLINE void map_to_curve_g2(G2Aff& out, const Fp2& u) {
+  Fp2 tv1, tv2, prod;
+  svdw_pre_g2(tv1, tv2, prod, u);
+  svdw_post_g2(out, u, tv1, tv2, h_inv(prod));  // inv0 (fp_inv(0) = 0)
+}
+BN_HD void map_to_curve_g2_x2(G2Aff& q0, G2Aff& q1, const Fp2& u0, const Fp2& u1) {
+  Fp2 a1, a2, pa, b1, b2, pb, one = fp2_one();
+  svdw_pre_g2(a1, a2, pa, u0);
+  svdw_pre_g2(b1, b2, pb, u1);
+  bool za = fp2_is_zero(pa), zb = fp2_is_zero(pb);
+  Fp2 sa = fp2_sel(za, one, pa), sb = fp2_sel(zb, one, pb);
+  Fp2 inv = h_inv(h_mul(sa, sb));
+  Fp2 ia = fp2_sel(za, fp2_zero(), h_mul(inv, sb)), ib = fp2_sel(zb, fp2_zero(), h_mul(inv, sa));
+  svdw_post_g2(q0, u0, a1, a2, ia);
+  svdw_post_g2(q1, u1, b1, b2, ib);
 }
 
 // psi = twist o Frobenius o untwist on Jacobian coordinates: (X, Y, Z) -> (conj X g12, conj Y g13, conj Z)
@@ -247,8 +289,7 @@ BN_HD void hash_to_g1(G1Aff& out, const uint8_t* msg, size_t len, const uint8_t*
   Fp u[2];
   hash_to_field<2>(u, msg, len, dst, dst_len);
   G1Aff q0, q1;
-  map_to_curve_g1(q0, u[0]);
-  map_to_curve_g1(q1, u[1]);
+  map_to_curve_g1_x2(q0, q1, u[0], u[1]);
   aff_add<G1Jac, G1Aff>(out, q0, q1);
 }
 BN_HD void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len, const uint8_t* dst, uint32_t dst_len) {
@@ -257,8 +298,7 @@ BN_HD void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len, const uint8_t*
   G2Aff q0, q1;
   Fp2 u0, u1;
   u0.a0 = u[0]; u0.a1 = u[1]; u1.a0 = u[2]; u1.a1 = u[3];
-  map_to_curve_g2(q0, u0);
-  map_to_curve_g2(q1, u1);
+  map_to_curve_g2_x2(q0, q1, u0, u1);
   G2Jac s; s.x = q0.x; s.y = q0.y; s.z = fp2_one();
   jac_add_aff(s, s, q1);
   g2_clear_cofactor(s, s);
