@@ -45,6 +45,7 @@ VARIANTS = {  # experiment builds selected with BN254_VARIANT=<name>: flags for 
     "lines16": DEFAULT + ["-DBN254_LINES_CHUNK=16"], "lines12": DEFAULT + ["-DBN254_LINES_CHUNK=12"],
     "pair_add_lines": {"k_pairing": DEFAULT + ["-DBN254_PAIR_ADD_LINES"]},
     "gt_glv2": {"k_gt": DEFAULT + ["-DBN254_GT_EXP_GLV2"]},  # GT-proper exponentiation by the two-dimensional split (A/B of the GLS-4 ladder)
+    "euler_ladder": {"k_hash": DEFAULT + ["-DBN254_EULER_LADDER"]},  # quadratic character by the ladder a^((p-1)/2) (A/B of the Jacobi symbol)
     "lines_global": {"k_pairing": DEFAULT + ["-DBN254_LINES_TMA=0"]},  # line tables read straight from global memory (A/B of the TMA ring)
     "b2": ["-DBN254_OOL_ADDS", "-DBN254_OOL_FPMUL", "-DBN254_MIN_BLOCKS=2", "-DBN254_SMEM_SCRATCH", "-DBN254_CTA_LOCKSTEP"],
 }

@@ -149,6 +149,7 @@ extern "C" void emu_hash_to_g1(const unsigned char* msg, size_t len, const unsig
   G1Aff r; hash_to_g1(r, msg, len, dst, (uint32_t)dst_len); st(out, 0, r); }
 extern "C" void emu_hash_to_g2(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
   G2Aff r; hash_to_g2(r, msg, len, dst, (uint32_t)dst_len); st(out, 0, r); }
+extern "C" void emu_fp_is_square(const void* a, size_t n, int* out) { for (size_t i = 0; i < n; i++) out[i] = fp_is_square(ld<Fp>(a, i)) ? 1 : 0; }
 extern "C" void emu_hash_to_field(const unsigned char* msg, size_t len, const unsigned char* dst, size_t dst_len, void* out) {
   Fp u[4]; hash_to_field<4>(u, msg, len, dst, (uint32_t)dst_len); for (int i = 0; i < 4; i++) st(out, i, u[i]); }
 

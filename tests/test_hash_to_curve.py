@@ -89,6 +89,24 @@ def test_device_code_on_host_matches_golden(emu, vectors):  # noqa: F811
         assert [o.fp_from_mont_bytes(f[32 * i:32 * i + 32]) for i in range(4)] == h.hash_to_fp(b"message", dst, 4)
 
 
+def test_device_quadratic_character_is_the_jacobi_symbol(emu):  # noqa: F811
+    """fp_is_square of the device code (binary Jacobi symbol, no field multiplication) against Euler's criterion on Python
+    integers: edge values, small numbers, powers of two (long runs of trailing zeros, whole zero limbs) and 400 random ones."""
+    rng = o.SplitMix64(0x1ACB1)
+    vals = [0, 1, 2, 3, 4, 5, 7, 8, o.P - 1, o.P - 2, (o.P - 1) // 2, (o.P + 1) // 2, 1 << 32, 1 << 64, 1 << 200, 3 << 96, (1 << 253) + 1]
+    vals += [rng.fp() for _ in range(400)]
+    # the kernel sees Montgomery residues v R mod p; R is a square, so the character is that of v
+    buf = np.frombuffer(b"".join(o.fp_to_mont_bytes(v) for v in vals), dtype=np.uint8).copy()
+    out = (ctypes.c_int * len(vals))()
+    emu.emu_fp_is_square(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(vals)), out)
+    want = [1 if v == 0 or pow(v, (o.P - 1) // 2, o.P) == 1 else 0 for v in vals]
+    assert list(out) == want
+    # and on the raw limbs themselves (the routine does not care which representation it is handed)
+    raw = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
+    emu.emu_fp_is_square(raw.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(vals)), out)
+    assert list(out) == want
+
+
 def test_device_g2_square_root_takes_both_branches(emu):  # noqa: F811
     """The Fp2 square root of the device code derives the root from ONE ladder c^((p-3)/4) whichever of its two candidates
     is the square (hash_to_curve.cuh fp2_sqrt): 40 more messages against the definitional oracle -- both branches of both
