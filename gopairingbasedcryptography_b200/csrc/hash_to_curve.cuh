@@ -258,13 +258,14 @@ BN_NOINLINE void map_to_curve_g1(G1Aff& out, const Fp& u) {
   svdw_post_g1(out, u, tv1, tv2, h_inv(prod));  // inv0
 }
 // both maps of one message, one inversion
+template <typename INV = InvThread>
 BN_HD void map_to_curve_g1_x2(G1Aff& q0, G1Aff& q1, const Fp& u0, const Fp& u1) {
   Fp a1, a2, pa, b1, b2, pb, one = fp_one();
   svdw_pre_g1(a1, a2, pa, u0);
   svdw_pre_g1(b1, b2, pb, u1);
   bool za = fp_is_zero(pa), zb = fp_is_zero(pb);
   Fp sa = fp_sel(za, one, pa), sb = fp_sel(zb, one, pb);
-  Fp inv = h_inv(h_mul(sa, sb));
+  Fp inv = INV::inv(h_mul(sa, sb));
   Fp ia = fp_sel(za, fp_zero(), h_mul(inv, sb)), ib = fp_sel(zb, fp_zero(), h_mul(inv, sa));
   svdw_post_g1(q0, u0, a1, a2, ia);
   svdw_post_g1(q1, u1, b1, b2, ib);
@@ -297,13 +298,14 @@ BN_NOINLINE void map_to_curve_g2(G2Aff& out, const Fp2& u) {
   svdw_pre_g2(tv1, tv2, prod, u);
   svdw_post_g2(out, u, tv1, tv2, h_inv(prod));  // inv0 (fp_inv(0) = 0)
 }
+template <typename INV = InvThread>
 BN_HD void map_to_curve_g2_x2(G2Aff& q0, G2Aff& q1, const Fp2& u0, const Fp2& u1) {
   Fp2 a1, a2, pa, b1, b2, pb, one = fp2_one();
   svdw_pre_g2(a1, a2, pa, u0);
   svdw_pre_g2(b1, b2, pb, u1);
   bool za = fp2_is_zero(pa), zb = fp2_is_zero(pb);
   Fp2 sa = fp2_sel(za, one, pa), sb = fp2_sel(zb, one, pb);
-  Fp2 inv = h_inv(h_mul(sa, sb));
+  Fp2 inv = INV::inv(h_mul(sa, sb));
   Fp2 ia = fp2_sel(za, fp2_zero(), h_mul(inv, sb)), ib = fp2_sel(zb, fp2_zero(), h_mul(inv, sa));
   svdw_post_g2(q0, u0, a1, a2, ia);
   svdw_post_g2(q1, u1, b1, b2, ib);
@@ -343,24 +345,31 @@ BN_NOINLINE void g2_clear_cofactor(G2Jac& r, const G2Jac& q) {
   r = acc;
 }
 
+// INV = InvCta (kernels with every thread of the CTA alive): the shared SVDW inversion and the final normalisation go
+// through ONE Fermat ladder per CTA instead of one per thread (curve.cuh); every thread calls each exactly once.
+template <typename INV = InvThread>
 BN_HD void hash_to_g1(G1Aff& out, const uint8_t* msg, size_t len, const uint8_t* dst, uint32_t dst_len) {
   Fp u[2];
   hash_to_field<2>(u, msg, len, dst, dst_len);
   G1Aff q0, q1;
-  map_to_curve_g1_x2(q0, q1, u[0], u[1]);
-  aff_add<G1Jac, G1Aff>(out, q0, q1);
+  map_to_curve_g1_x2<INV>(q0, q1, u[0], u[1]);
+  // gnark Add semantics on two finite points: doubling when equal, infinity (0, 0) when opposite (inv(0) = 0)
+  G1Jac t; t.x = q0.x; t.y = q0.y; t.z = fp_one();
+  jac_add_aff(t, t, q1);
+  jac_to_aff_inv<INV>(out, t);
 }
+template <typename INV = InvThread>
 BN_HD void hash_to_g2(G2Aff& out, const uint8_t* msg, size_t len, const uint8_t* dst, uint32_t dst_len) {
   Fp u[4];
   hash_to_field<4>(u, msg, len, dst, dst_len);
   G2Aff q0, q1;
   Fp2 u0, u1;
   u0.a0 = u[0]; u0.a1 = u[1]; u1.a0 = u[2]; u1.a1 = u[3];
-  map_to_curve_g2_x2(q0, q1, u0, u1);
+  map_to_curve_g2_x2<INV>(q0, q1, u0, u1);
   G2Jac s; s.x = q0.x; s.y = q0.y; s.z = fp2_one();
   jac_add_aff(s, s, q1);
   g2_clear_cofactor(s, s);
-  jac_to_aff(out, s);
+  jac_to_aff_inv<INV>(out, s);
 }
 
 }  // namespace bn254
