@@ -621,3 +621,30 @@ def test_bb04_setup_keygen_encrypt_decrypt_at_reference_size(engine):
     assert c[m - 1, 17].tobytes() == port.g2_mul_batch(u[17, ident[17]].copy().reshape(-1), sb([ts[m - 1]]), 1, 1).tobytes()
     back = schemes.bb04_ibe_decrypt_batch(engine, a, b, c, d0, dj)
     assert (back == msgs).all()
+
+
+def test_gt_exp_four_dimensional_split_at_two_waves(engine):
+    """GT.Exp on GT proper (four-dimensional split of the exponent, curve.cuh gt_cyclo_exp_gls4) over 2^17 elements:
+    sampled outputs bit-exact against the oracle's ladder, the generic ladder and the size-independent group laws
+    x^a x^b = x^(a + b mod r) and (x^a)^b = x^(a b mod r) on ALL of them, edge exponents included."""
+    n = 1 << 17
+    P, Q, _, _ = common.points(512, seed=0x6E1, threads=8)
+    x = np.tile(engine.pair_batch(P, Q), (n // 512, 1))
+    rng = o.SplitMix64(0x6E2)
+    base = [rng.scalar() for _ in range(1021)]
+    a = [base[i % 1021] ^ (i * 0x9E3779B97F4A7C15 & ((1 << 200) - 1)) for i in range(n)]
+    b = [base[(7 * i + 3) % 1021] for i in range(n)]
+    edges = [0, 1, 2, o.R - 1, o.R, o.R + 1, (1 << 256) - 1, 1 << 255, (1 << 128) - 1, 1 << 67, (1 << 67) - 1]
+    a[:len(edges)] = edges
+    b[n - len(edges):] = edges
+    A, B = sb(a), sb(b)
+    xa, xb = engine.gt_cyclo_exp_batch(x, A), engine.gt_cyclo_exp_batch(x, B)
+    k = 24
+    for lo in (0, n - k):  # oracle on the ends (the edge exponents live there)
+        assert (xa[lo:lo + k].reshape(-1) == port.gt_exp_batch(x[lo:lo + k].reshape(-1), A[32 * lo:32 * (lo + k)], k)).all()
+        assert (xb[lo:lo + k].reshape(-1) == port.gt_exp_batch(x[lo:lo + k].reshape(-1), B[32 * lo:32 * (lo + k)], k)).all()
+    assert (engine.gt_exp_batch(x[:4096], A[:32 * 4096]) == xa[:4096]).all()          # generic ladder, same bytes
+    s = sb([(u + v) % o.R for u, v in zip(a, b)])
+    assert (engine.gt_mul_batch(xa, xb) == engine.gt_cyclo_exp_batch(x, s)).all()       # x^a x^b = x^(a + b)
+    m = sb([(u * v) % o.R for u, v in zip(a, b)])
+    assert (engine.gt_cyclo_exp_batch(xa, B) == engine.gt_cyclo_exp_batch(x, m)).all()  # (x^a)^b = x^(a b)
