@@ -89,3 +89,24 @@ def test_cgo_types_and_constants_exist_in_the_header():
                 names |= set(re.findall(r"C\.((?:bn254|BN254)_[A-Za-z0-9_]+)\b", _strip_comments(open(os.path.join(dirpath, fn)).read())))
     missing = sorted(n for n in names if not re.search(r"\b%s\b" % re.escape(n), hdr))
     assert not missing, "named in go/ but absent from the header: %r" % missing
+
+
+def test_python_mirror_device_signatures_match_the_header():
+    """Engine.dev() builds its ctypes argument list from a signature string per entry point (bn254.py _DEV_SIGS); a wrong
+    count there is a silent stack mismatch, so every string is checked against the header's prototype: context + one
+    argument per letter (two for a byte string: pointer and length) + the stream."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from gopairingbasedcryptography_b200 import bn254
+
+    protos, _ = header_prototypes()
+    sigs = bn254.Engine._DEV_SIGS
+    assert len(sigs) >= 30
+    bad = []
+    for name, sig in sigs.items():
+        want = protos.get("bn254_" + name)
+        got = 1 + sum(2 if c == "b" else 1 for c in sig) + 1
+        if want != got:
+            bad.append((name, sig, got, want))
+    assert not bad, "(entry point, signature, arguments built, arguments declared): %r" % bad
