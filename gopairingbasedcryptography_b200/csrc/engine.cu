@@ -518,6 +518,20 @@ int cached_table(bn254_ctx* ctx, int group, const void* base, const void** table
   return BN254_OK;
 }
 
+// Small one-base batches: a table that is ALREADY cached is used whatever n (32 mixed additions instead of a GLV ladder:
+// a 1-element ScalarMultiplicationBase 1.38 -> ~0.5 ms), and the generators' tables are built on their first use --
+// gnark's ScalarMultiplicationBase always multiplies the generator, so that is the base the reference's 1-element calls
+// pass (bls_signature.go:45, waters05_ibe.go:224, bsw07_cpabe.go:69,157).  ctx->mu held.
+bool small_batch_uses_table(bn254_ctx* ctx, int group, const void* base) {
+  if (group != BN254_GROUP_G1 && group != BN254_GROUP_G2) return false;
+  const size_t item = pt_bytes(group);
+  for (const FixedTable& t : ctx->cache)
+    if (t.group == group && memcmp(t.base, base, item) == 0) return true;
+  unsigned char g1[BN254_G1_BYTES], g2[BN254_G2_BYTES];
+  bn254_generators(g1, g2);
+  return memcmp(base, group == BN254_GROUP_G1 ? g1 : g2, item) == 0;
+}
+
 // n messages (concatenated bytes + n+1 offsets) -> points.  Chunks are sized to one staging slot; two slots in
 // flight: chunk i's kernel runs while chunk i-1's points are copied back and handed to the caller.
 int hash_to_curve_host(bn254_ctx* ctx, int G, const uint8_t* msgs, const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, void* out) {
@@ -871,7 +885,7 @@ MUL_ENTRY(bn254_g2_mul_batch, 2, BN254_G2_BYTES)
     std::lock_guard<std::mutex> lk(ctx->mu);                                                                          \
     CU(cudaSetDevice(ctx->device));                                                                                   \
     Operand in[2] = {{base, BYTES, true}, {scalars, BN254_SCALAR_BYTES, false}};                                      \
-    if (n < kFixedMin)                                                                                                \
+    if (n < kFixedMin && !small_batch_uses_table(ctx, G, base))                                                       \
       return run_host_locked(ctx, in, 2, out, BYTES, n, [ctx](const void* const* d, size_t c, void* o, Slot& sl) {    \
         Scratch sc; sc.slot = &sl; sc.stream = sl.stream;                                                             \
         return seq_scalar_mul(ctx, sc, G, d[0], 0, d[1], c, o);                                                       \
